@@ -1,0 +1,108 @@
+/* include/scpr_c.h -- C ABI of the B200-native ScreenPressor v4 frame codec (libscpr_b200.so).
+ *
+ * Drop-in boundary: these entry points replace the reference's `ScreenCodec` object
+ * (reference screencap.h:519-541, implementation screencap.cpp:1560-1743), which is what the
+ * VfW layer `CodecInst` holds and calls (screenpressor.cpp:381, 425, 575, 620, 444, 647).
+ * Plain pointers and sizes only; no exceptions cross this boundary; all work runs as CUDA
+ * kernels on the selected device -- there is no CPU fallback and nothing here touches oracle/.
+ *
+ * Bitstream: byte-identical to the reference encoder run with one worker thread (its only
+ * deterministic configuration); decoding reproduces frames bit-exactly.
+ */
+#ifndef SCPR_C_H
+#define SCPR_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces struct CodecParameters (reference screencap.h:49-55) */
+typedef struct scpr_params {
+    uint32_t width, height;
+    uint8_t bits_per_pixel;                  /* 24 or 32 (16 is not built yet: returns SCPR_E_UNSUPPORTED) */
+    uint16_t redmask, greenmask, bluemask;   /* 16 bpp only */
+    uint32_t high_range_x, high_range_y;     /* motion search ranges; v4 clamps these to 256 (screencap.cpp:79) */
+    uint32_t low_range_x, low_range_y;       /* 8, 8 (screenpressor.cpp:377-378) */
+    uint32_t loss;                           /* bits of loss, 0..4; only 0 is built yet */
+} scpr_params;
+
+typedef struct scpr_codec scpr_codec;
+
+enum {
+    SCPR_OK = 0,
+    SCPR_E_CUDA = -1000,        /* a CUDA call failed; scpr_last_error() has the text */
+    SCPR_E_PARAM = -1001,       /* bad argument */
+    SCPR_E_UNSUPPORTED = -1002, /* feature outside the built hot path (16 bpp, loss > 0, v2 streams) */
+    SCPR_E_DSTSIZE = -1003,     /* destination buffer too small */
+    SCPR_E_NODEVICE = -1004     /* no CUDA device: this library never computes on the CPU */
+};
+
+/* replaces ScreenCodec::ScreenCodec + Init (screencap.cpp:1560-1584).  `device` = CUDA ordinal. */
+int scpr_create(const scpr_params* p, int device, scpr_codec** out);
+/* replaces ScreenCodec::Deinit / ~ScreenCodec (screencap.cpp:1619-1629) */
+void scpr_destroy(scpr_codec* c);
+
+/* replaces ScreenCodec::CompressFrame (screencap.cpp:1632-1692).
+ * src: host frame, rows top to bottom, pitch width*4 (32 bpp) or (width*3+3)&~3 (24 bpp).
+ * *ftype in: 0 = I requested, 1 = P requested; out: type actually coded (first and flat frames
+ * are always I, screencap.cpp:1488-1511).  Returns the byte count written to dst, or < 0. */
+int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss);
+
+/* replaces ScreenCodec::DecompressFrame (screencap.cpp:1695-1743).
+ * Returns 1 on success, 0 for "P frame before any I frame", -v (v = 1..16) for a stream version
+ * this build cannot decode (the reference throws BadVersionException(v), screencap.cpp:1589-1590;
+ * v2 range-coder streams are out of scope here), or an SCPR_E_* code. */
+int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_t* dst, int pitch, int ftype);
+
+/* ---- throughput entry points (no reference equivalent): many frames per call -------------
+ * The frames of one call are processed as a batch: frame differencing, block typing, motion
+ * search, pixel typing and event generation run in parallel over all frames; the adaptive
+ * models are replayed per GOP in the reference's update order; every rANS block is its own
+ * stream.  Results are identical to n calls of scpr_compress_frame.
+ *
+ * frames   : n frames back to back (same layout as scpr_compress_frame's src).
+ * keyflags : n bytes, 1 = the host requests an I frame (ftype 0), 0 = P requested.
+ * dst      : concatenated frame bitstreams; sizes[i] / ftypes[i] describe frame i.
+ * Returns total bytes written or < 0.  `*_dev` variants take device pointers for the frames
+ * (inputs/outputs already resident in HBM); bitstreams stay host-side in both. */
+int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const uint8_t* keyflags,
+                           uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes);
+int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags,
+                               uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes);
+/* stream: concatenated frame bitstreams, sizes[i] bytes each, ftypes[i] = 0 I / 1 P.
+ * frames: n decoded frames back to back with row pitch `pitch`. Returns 1, 0 or < 0 as above. */
+int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes,
+                         int n, uint8_t* frames, int pitch);
+int scpr_decompress_clip_dev(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes,
+                             int n, uint8_t* d_frames, int pitch);
+
+/* ---- plumbing ------------------------------------------------------------------------------ */
+/* CUDA stream (cudaStream_t) all kernels of this codec are launched on; default: the legacy stream. */
+int scpr_set_stream(scpr_codec* c, void* cuda_stream);
+/* Text of the last error on this thread. */
+const char* scpr_last_error(void);
+/* Number of kernels this codec has launched so far (bench.py reports it as gpu_launches). */
+uint64_t scpr_kernel_launches(const scpr_codec* c);
+/* W*H*6, the output capacity the VfW layer promises (CompressGetSize, screenpressor.cpp:386-388). */
+size_t scpr_max_compressed_size(const scpr_params* p);
+
+/* ---- stage hooks for parity tests and profiling (not needed by a codec user) -------------- */
+/* Events ((context id << 16) | symbol, DESIGN.md "event format") and intervals
+ * ((cum << 16) | freq; freq 0 = raw byte) of frame `i` of the most recent compress call.
+ * Copies up to cap entries to host memory; returns the frame's event count. */
+int64_t scpr_debug_events(scpr_codec* c, int frame, uint32_t* ev, uint32_t* iv, size_t cap);
+/* Stage-A result of frame `i` of the most recent compress call: per 16x16 block, block type
+ * (bts, 0..4), changed sub-rect {x1,y1,x2,y2} and motion vector {mx,my}.  nb = nbx*nby entries. */
+int scpr_debug_blocks(scpr_codec* c, int frame, uint8_t* bts, int32_t* sxy4, int32_t* mv2);
+/* Runs only the frame-scan kernel (differencing + changed-block detection + flat test) over n
+ * device-resident frames `reps` times; returns the mean kernel time in milliseconds measured with
+ * CUDA events on the codec's stream (bench.py's roofline leg), or < 0. */
+float scpr_bench_frame_scan(scpr_codec* c, const uint8_t* d_frames, int n, int reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's `ScreenCodec` object (screencap.h:519-541) over the C ABI of
+`libscpr_b200.so` (include/scpr_c.h).  Same method names, argument meaning and error behaviour as
+the reference class so parity tests read like code written against the reference:
+
+    sc = ScreenCodec(); sc.Init(CodecParameters(1920, 1080, 32))
+    data, ftype = sc.CompressFrame(frame, ftype=1)        # bytes, actual frame type
+    out = sc.DecompressFrame(data, pitch, ftype)          # ndarray, raises BadVersionException
+    sc.Deinit()
+
+plus the throughput calls `CompressClip` / `DecompressClip` (many frames per call).  Every call runs
+CUDA kernels; importing this module fails loudly if the extension has not been built, and creating a
+codec fails loudly without a GPU -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscpr_b200.so")
+
+SCPR_E_CUDA, SCPR_E_PARAM, SCPR_E_UNSUPPORTED, SCPR_E_DSTSIZE, SCPR_E_NODEVICE = -1000, -1001, -1002, -1003, -1004
+
+
+class ScprError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"libscpr_b200 error {code}: {text}")
+        self.code = code
+
+
+class BadVersionException(Exception):
+    """Mirror of the reference's BadVersionException (screencap.h:86-90)."""
+
+    def __init__(self, version: int):
+        super().__init__(f"cannot decode stream version {version}")
+        self.version = version
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("bits_per_pixel", C.c_uint8),
+        ("redmask", C.c_uint16), ("greenmask", C.c_uint16), ("bluemask", C.c_uint16),
+        ("high_range_x", C.c_uint32), ("high_range_y", C.c_uint32),
+        ("low_range_x", C.c_uint32), ("low_range_y", C.c_uint32), ("loss", C.c_uint32),
+    ]
+
+
+@dataclass
+class CodecParameters:
+    """reference screencap.h:49-55; defaults from screenpressor.cpp:374-379"""
+    width: int
+    height: int
+    bits_per_pixel: int = 32
+    redmask: int = 0x7C00
+    greenmask: int = 0x3E0
+    bluemask: int = 0x1F
+    high_range_x: int = 256
+    high_range_y: int = 256
+    low_range_x: int = 8
+    low_range_y: int = 8
+    loss: int = 0
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libscpr_b200.so; raises if it was not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build the CUDA extension first (__graft_entry__.build()); "
+                          "screenpressor_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    lib.scpr_create.restype = i32
+    lib.scpr_create.argtypes = [C.POINTER(_Params), i32, C.POINTER(vp)]
+    lib.scpr_destroy.restype = None
+    lib.scpr_destroy.argtypes = [vp]
+    lib.scpr_compress_frame.restype = i32
+    lib.scpr_compress_frame.argtypes = [vp, vp, vp, i32, C.POINTER(i32), i32]
+    lib.scpr_decompress_frame.restype = i32
+    lib.scpr_decompress_frame.argtypes = [vp, vp, i32, vp, i32, i32]
+    for name in ("scpr_compress_clip", "scpr_compress_clip_dev"):
+        fn = getattr(lib, name)
+        fn.restype = i64
+        fn.argtypes = [vp, vp, i32, vp, vp, C.c_size_t, vp, vp]
+    for name in ("scpr_decompress_clip", "scpr_decompress_clip_dev"):
+        fn = getattr(lib, name)
+        fn.restype = i32
+        fn.argtypes = [vp, vp, vp, vp, i32, vp, i32]
+    lib.scpr_set_stream.restype = i32
+    lib.scpr_set_stream.argtypes = [vp, vp]
+    lib.scpr_last_error.restype = C.c_char_p
+    lib.scpr_kernel_launches.restype = u64
+    lib.scpr_kernel_launches.argtypes = [vp]
+    lib.scpr_max_compressed_size.restype = C.c_size_t
+    lib.scpr_max_compressed_size.argtypes = [C.POINTER(_Params)]
+    lib.scpr_debug_events.restype = i64
+    lib.scpr_debug_events.argtypes = [vp, i32, vp, vp, C.c_size_t]
+    lib.scpr_debug_blocks.restype = i32
+    lib.scpr_debug_blocks.argtypes = [vp, i32, vp, vp, vp]
+    lib.scpr_bench_frame_scan.restype = C.c_float
+    lib.scpr_bench_frame_scan.argtypes = [vp, vp, i32, i32]
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> int:
+    """host ndarray / bytes-like -> address"""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    raise TypeError(type(a))
+
+
+class ScreenCodec:
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.device = device
+        self.params: CodecParameters | None = None
+
+    # ---- reference interface -----------------------------------------------------------------
+    def Init(self, params: CodecParameters) -> None:
+        self.Deinit()
+        p = _Params(params.width, params.height, params.bits_per_pixel, params.redmask, params.greenmask,
+                    params.bluemask, params.high_range_x, params.high_range_y, params.low_range_x,
+                    params.low_range_y, params.loss)
+        self._check(self._lib.scpr_create(C.byref(p), self.device, C.byref(self._h)))
+        self.params = params
+        self.pitch = params.width * 4 if params.bits_per_pixel == 32 else (params.width * 3 + 3) & ~3
+        self.frame_bytes = self.pitch * params.height
+        self.max_size = params.width * params.height * 6  # CompressGetSize, screenpressor.cpp:386-388
+        self._dst = np.empty(self.max_size + 64, dtype=np.uint8)
+
+    def Deinit(self) -> None:
+        if self._h:
+            self._lib.scpr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Deinit()
+        except Exception:
+            pass
+
+    def CompressFrame(self, src: np.ndarray, ftype: int, loss: int = 0):
+        """-> (bytes, actual ftype).  ftype: 0 = I requested, 1 = P requested."""
+        src = np.ascontiguousarray(src).reshape(-1)
+        assert src.dtype == np.uint8 and src.size == self.frame_bytes, (src.size, self.frame_bytes)
+        ft = C.c_int(ftype)
+        n = self._check(self._lib.scpr_compress_frame(self._h, _ptr(src), _ptr(self._dst), self._dst.size, C.byref(ft), loss))
+        return bytes(self._dst[:n]), ft.value
+
+    def DecompressFrame(self, data: bytes, pitch: int | None = None, ftype: int = 0) -> np.ndarray:
+        """-> decoded frame as a flat uint8 array of height*pitch bytes."""
+        pitch = self.pitch if pitch is None else pitch
+        src = np.frombuffer(data, dtype=np.uint8)
+        out = np.zeros(self.params.height * pitch, dtype=np.uint8)
+        r = self._lib.scpr_decompress_frame(self._h, _ptr(np.ascontiguousarray(src)), len(data), _ptr(out), pitch, ftype)
+        if -16 <= r < 0:
+            raise BadVersionException(-r)
+        if r == 0:
+            raise ScprError(0, "P frame before any I frame")
+        self._check(r)
+        return out
+
+    # ---- throughput interface ------------------------------------------------------------------
+    def CompressClip(self, frames, keyflags: np.ndarray, device_ptr: int | None = None, n: int | None = None):
+        """frames: host ndarray of n frames back to back, or (device_ptr, n) for HBM-resident input.
+        -> (stream bytes ndarray, sizes uint32[n], ftypes uint8[n])"""
+        keyflags = np.ascontiguousarray(keyflags, dtype=np.uint8)
+        if device_ptr is None:
+            frames = np.ascontiguousarray(frames)
+            n = frames.size // self.frame_bytes
+            assert frames.size == n * self.frame_bytes
+        assert keyflags.size == n
+        cap = getattr(self, "_clip_cap", 0)
+        sizes = np.zeros(n, dtype=np.uint32)
+        ftypes = np.zeros(n, dtype=np.uint8)
+        while True:
+            if cap < n * self.max_size:
+                cap = n * self.max_size  # W*H*6 per frame (CompressGetSize); np.empty commits pages lazily
+            if getattr(self, "_clip_dst", None) is None or self._clip_dst.size < cap:
+                self._clip_dst = np.empty(cap, dtype=np.uint8)
+            self._clip_cap = cap
+            if device_ptr is None:
+                r = self._lib.scpr_compress_clip(self._h, _ptr(frames), n, _ptr(keyflags), _ptr(self._clip_dst), cap,
+                                                 _ptr(sizes), _ptr(ftypes))
+            else:
+                r = self._lib.scpr_compress_clip_dev(self._h, device_ptr, n, _ptr(keyflags), _ptr(self._clip_dst), cap,
+                                                     _ptr(sizes), _ptr(ftypes))
+            if r == SCPR_E_DSTSIZE:
+                raise ScprError(r, "destination too small (codec state already advanced): pass a larger capacity via "
+                                   "reserve_clip_output() before the call")
+            self._check(r)
+            return self._clip_dst[:r], sizes, ftypes
+
+    def reserve_clip_output(self, nbytes: int) -> None:
+        self._clip_cap = int(nbytes)
+        self._clip_dst = np.empty(self._clip_cap, dtype=np.uint8)
+
+    def DecompressClip(self, stream: np.ndarray, sizes: np.ndarray, ftypes: np.ndarray, pitch: int | None = None,
+                       device_ptr: int | None = None):
+        """-> ndarray (n, height*pitch) of decoded frames, or None when decoding into device_ptr."""
+        pitch = self.pitch if pitch is None else pitch
+        n = int(sizes.size)
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        ftypes = np.ascontiguousarray(ftypes, dtype=np.uint8)
+        if device_ptr is None:
+            out = np.zeros((n, self.params.height * pitch), dtype=np.uint8)
+            r = self._lib.scpr_decompress_clip(self._h, _ptr(stream), _ptr(sizes), _ptr(ftypes), n, _ptr(out), pitch)
+        else:
+            out = None
+            r = self._lib.scpr_decompress_clip_dev(self._h, _ptr(stream), _ptr(sizes), _ptr(ftypes), n, device_ptr, pitch)
+        if -16 <= r < 0:
+            raise BadVersionException(-r)
+        if r == 0:
+            raise ScprError(0, "P frame before any I frame")
+        self._check(r)
+        return out
+
+    # ---- plumbing / test hooks -------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self._lib.scpr_set_stream(self._h, cuda_stream))
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.scpr_kernel_launches(self._h))
+
+    def debug_events(self, frame: int):
+        n = self._check(self._lib.scpr_debug_events(self._h, frame, None, None, 0))
+        ev = np.zeros(n, dtype=np.uint32)
+        iv = np.zeros(n, dtype=np.uint32)
+        if n:
+            self._check(self._lib.scpr_debug_events(self._h, frame, _ptr(ev), _ptr(iv), n))
+        return ev, iv
+
+    def debug_blocks(self, frame: int):
+        nb = ((self.params.width + 15) // 16) * ((self.params.height + 15) // 16)
+        bts = np.zeros(nb, dtype=np.uint8)
+        sxy = np.zeros((nb, 4), dtype=np.int32)
+        mv = np.zeros((nb, 2), dtype=np.int32)
+        self._check(self._lib.scpr_debug_blocks(self._h, frame, _ptr(bts), _ptr(sxy), _ptr(mv)))
+        return bts, sxy, mv
+
+    def bench_frame_scan(self, device_ptr: int, n: int, reps: int) -> float:
+        ms = float(self._lib.scpr_bench_frame_scan(self._h, device_ptr, n, reps))
+        if ms < 0:
+            raise ScprError(int(ms), self._lib.scpr_last_error().decode())
+        return ms
+
+    def _check(self, r: int) -> int:
+        if r < 0:
+            raise ScprError(int(r), self._lib.scpr_last_error().decode())
+        return int(r)

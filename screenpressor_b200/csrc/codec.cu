@@ -1,0 +1,551 @@
+// codec.cu -- host side of the C ABI (include/scpr_c.h): codec object, frame-type policy, GOP
+// ("chain") bookkeeping, workspace management and kernel orchestration.
+//
+// Mirrors, on the host, only the control decisions of the reference:
+//   ScreenCodec::Init / CompressFrame / DecompressFrame   screencap.cpp:1565-1743
+//   CScreenCapt::CompressFrame (flat / I / P choice)      screencap.cpp:1456-1518
+// All pixel, model and entropy work is done by the kernels in frame_scan.cu, pframe.cu, iframe.cu,
+// models.cu, rans.cu and decode.cu.  There is no CPU implementation of any of it in this library.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/scpr_c.h"
+#include "codec.h"
+
+namespace scpr {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return SCPR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return SCPR_E_CUDA;
+    }
+    cap = want;
+    return SCPR_OK;
+}
+void DBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+}  // namespace scpr
+
+using namespace scpr;
+
+#define CK(call) SCPR_CUDA_CHECK(call)
+#define TRY(expr)                 \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ < 0) return r__;  \
+    } while (0)
+
+static int ensure_states(scpr_codec* c, int n) {
+    if (n <= c->n_states) return SCPR_OK;
+    // keep the open chain's state: allocate a larger pool and copy the live state over
+    DBuf nb;
+    TRY(nb.ensure((size_t)n * model_state_bytes()));
+    if (c->states.p)
+        CK(cudaMemcpyAsync((uint8_t*)nb.p + (size_t)c->cur_state * model_state_bytes(),
+                           (uint8_t*)c->states.p + (size_t)c->cur_state * model_state_bytes(), model_state_bytes(),
+                           cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->states.release();
+    c->states = nb;
+    c->n_states = n;
+    return SCPR_OK;
+}
+
+extern "C" {
+
+const char* scpr_last_error(void) { return g_err; }
+
+size_t scpr_max_compressed_size(const scpr_params* p) { return (size_t)p->width * p->height * 6; }
+
+int scpr_create(const scpr_params* p, int device, scpr_codec** out) {
+    if (!p || !out) return SCPR_E_PARAM;
+    *out = nullptr;
+    if (p->width < 3 || p->height < 2 || p->width > 65535 || p->height > 65535) {
+        set_error("unsupported frame size %ux%u", p->width, p->height);
+        return SCPR_E_PARAM;
+    }
+    if (p->bits_per_pixel != 24 && p->bits_per_pixel != 32) {
+        set_error("bits_per_pixel %d: only 24 and 32 are built", (int)p->bits_per_pixel);
+        return SCPR_E_UNSUPPORTED;
+    }
+    if (p->loss != 0) {
+        set_error("lossy modes are not built yet (loss must be 0)");
+        return SCPR_E_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device: libscpr_b200 has no CPU path");
+        return SCPR_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) return SCPR_E_PARAM;
+    CK(cudaSetDevice(device));
+    scpr_codec* c = new scpr_codec();
+    c->p = *p;
+    c->device = device;
+    Geo& g = c->g;
+    g.X = (int)p->width;
+    g.Y = (int)p->height;
+    g.bpp = p->bits_per_pixel / 8;
+    g.pitch = g.bpp == 4 ? g.X * 4 : ((g.X * 3 + 3) & ~3);
+    g.nbx = (g.X + 15) / 16;
+    g.nby = (g.Y + 15) / 16;
+    g.nb = g.nbx * g.nby;
+    g.frame_bytes = (size_t)g.pitch * g.Y;
+    if (g.nb > 65536) {  // xx1/xx2 are two bytes each (screencap.cpp:1145-1150)
+        delete c;
+        set_error("more than 65536 blocks per frame");
+        return SCPR_E_PARAM;
+    }
+    int r = c->prev.ensure(g.frame_bytes);
+    if (r >= 0) r = c->mvs.ensure((size_t)g.nb * sizeof(int2));
+    if (r >= 0) r = c->dec_mvs.ensure((size_t)g.nb * sizeof(int2));
+    if (r < 0) {
+        scpr_destroy(c);
+        return r;
+    }
+    cudaMemset(c->prev.p, 0, g.frame_bytes);              // prev = calloc (screencap.cpp:89)
+    cudaMemset(c->mvs.p, 0, (size_t)g.nb * sizeof(int2));  // mvs = calloc (screencap.cpp:96-97)
+    *out = c;
+    return SCPR_OK;
+}
+
+void scpr_destroy(scpr_codec* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    DBuf* all[] = {&c->prev, &c->mvs, &c->dec_mvs, &c->states, &c->frames, &c->blkinfo, &c->summary, &c->chg_list, &c->hdr,
+                   &c->ftype, &c->blocks, &c->pframes, &c->runs, &c->bts_rle, &c->ihdr, &c->desc, &c->exit_tab, &c->entry,
+                   &c->starts, &c->chunk_cnt, &c->frame_ev_off, &c->events, &c->intervals, &c->sorted, &c->seg_off,
+                   &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
+                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev};
+    for (DBuf* b : all) b->release();
+    delete c;
+}
+
+int scpr_set_stream(scpr_codec* c, void* cuda_stream) {
+    if (!c) return SCPR_E_PARAM;
+    c->st = (cudaStream_t)cuda_stream;
+    return SCPR_OK;
+}
+
+uint64_t scpr_kernel_launches(const scpr_codec* c) { return c ? c->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// batch encoder: n device-resident frames -> host bitstreams
+// ------------------------------------------------------------------------------------------------
+static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags, uint8_t* dst,
+                            size_t dst_cap, uint32_t* sizes, uint8_t* ftypes_out) {
+    const Geo& g = c->g;
+    cudaStream_t st = c->st;
+    CK(cudaSetDevice(c->device));
+    if (n <= 0) return 0;
+
+    // ---- pass 1: frame scan + changed-block lists for every frame ------------------------------
+    TRY(c->blkinfo.ensure((size_t)n * g.nb * 4));
+    TRY(c->summary.ensure((size_t)n * sizeof(FrameSummary)));
+    TRY(c->chg_list.ensure((size_t)n * g.nb * 4));
+    TRY(c->hdr.ensure((size_t)n * sizeof(PFrameHdr)));
+    TRY(c->ftype.ensure((size_t)n));
+    CK(cudaMemsetAsync(c->summary.p, 0, (size_t)n * sizeof(FrameSummary), st));
+    CK(cudaMemsetAsync(c->ftype.p, FT_P, (size_t)n, st));
+    launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, st,
+                      &c->launches);
+    launch_compact_changed((const uint32_t*)c->blkinfo.p, (const uint8_t*)c->ftype.p, n, g, (uint32_t*)c->chg_list.p,
+                           (PFrameHdr*)c->hdr.p, st, &c->launches);
+    std::vector<FrameSummary> summary(n);
+    std::vector<PFrameHdr> hdr(n);
+    CK(cudaMemcpyAsync(summary.data(), c->summary.p, (size_t)n * sizeof(FrameSummary), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hdr.data(), c->hdr.p, (size_t)n * sizeof(PFrameHdr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- host plan: frame types and chains (CScreenCapt::CompressFrame, screencap.cpp:1456-1518) --
+    std::vector<uint8_t> ftype(n);
+    std::vector<int> pframes, iframes;
+    std::vector<int> chain_of(n, -1);
+    std::vector<ChainDesc> chains;
+    std::vector<int> chain_first(0);
+    int open_chain = -1;  // index into `chains` of the chain coded P frames append to
+    int next_state = 0;
+    auto new_state = [&]() {
+        // any slot except the one holding a live chain of this batch; chain k gets its own
+        int s = next_state++;
+        return s;
+    };
+    // the persistent state (if any) is chain "-1": it is referenced lazily by the first P frame
+    const int persistent_state = c->cur_state;
+    for (int f = 0; f < n; f++) {
+        const bool flat = !summary[f].notflat;
+        const uint8_t clr[3] = {(uint8_t)summary[f].pixel0, (uint8_t)(summary[f].pixel0 >> 8), (uint8_t)(summary[f].pixel0 >> 16)};
+        if (flat) {
+            ftype[f] = FT_FLAT;
+            if (!(c->last_was_flat && !memcmp(clr, c->last_flat_clr, 3))) {
+                memcpy(c->last_flat_clr, clr, 3);
+                ChainDesc cd = {0, 0, -1, 1};  // RenewI with no events of its own (screencap.cpp:1490-1494)
+                chains.push_back(cd);
+                chain_first.push_back(f);
+                open_chain = (int)chains.size() - 1;
+                c->have_models = true;
+            }
+            c->last_was_flat = true;
+            continue;
+        }
+        c->last_was_flat = false;
+        if (c->fn && !keyflags[f]) {
+            c->fn++;
+            if (!summary[f].changed) {
+                ftype[f] = FT_PSAME;
+                continue;
+            }
+            ftype[f] = FT_P;
+            pframes.push_back(f);
+            if (open_chain < 0) {  // continue the chain left open by the previous call
+                ChainDesc cd = {0, 0, -2, 0};
+                chains.push_back(cd);
+                chain_first.push_back(f);
+                open_chain = (int)chains.size() - 1;
+            }
+            chain_of[f] = open_chain;
+        } else {
+            c->fn++;
+            ftype[f] = FT_I;
+            iframes.push_back(f);
+            ChainDesc cd = {0, 0, -1, 1};
+            chains.push_back(cd);
+            chain_first.push_back(f);
+            open_chain = (int)chains.size() - 1;
+            chain_of[f] = open_chain;
+            c->have_models = true;
+        }
+    }
+    // model states: the continued chain keeps the persistent slot, every new chain gets its own
+    {
+        int need = (int)chains.size() + 1;
+        TRY(ensure_states(c, need));
+        for (size_t k = 0; k < chains.size(); k++) {
+            if (chains[k].state == -2)
+                chains[k].state = persistent_state;
+            else {
+                int s = new_state();
+                if (s == persistent_state) s = new_state();
+                chains[k].state = s;
+            }
+        }
+        if (!chains.empty()) c->cur_state = chains.back().state;
+    }
+
+    // ---- stage A --------------------------------------------------------------------------------
+    int total_blocks = 0;
+    for (int f : pframes) {
+        hdr[f].chg_off = total_blocks;
+        total_blocks += hdr[f].n_changed;
+    }
+    const int n_p = (int)pframes.size(), n_i = (int)iframes.size();
+    CK(cudaMemcpyAsync(c->ftype.p, ftype.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->hdr.p, hdr.data(), (size_t)n * sizeof(PFrameHdr), cudaMemcpyHostToDevice, st));
+    TRY(c->frame_ev_off.ensure((size_t)(n + 1) * 4));
+    PWork pw;
+    memset(&pw, 0, sizeof(pw));
+    pw.frames = d_frames; pw.prev0 = (const uint8_t*)c->prev.p; pw.n = n; pw.g = g;
+    pw.ftype = (const uint8_t*)c->ftype.p; pw.blkinfo = (const uint32_t*)c->blkinfo.p; pw.chg_list = (const uint32_t*)c->chg_list.p;
+    pw.hdr = (PFrameHdr*)c->hdr.p; pw.total_blocks = total_blocks; pw.n_pframes = n_p; pw.mvs = (int2*)c->mvs.p;
+    pw.frame_ev_off = (const uint32_t*)c->frame_ev_off.p;
+    if (n_p) {
+        TRY(c->pframes.ensure((size_t)n_p * 4));
+        TRY(c->blocks.ensure((size_t)(total_blocks + 1) * sizeof(ChgBlock)));
+        TRY(c->runs.ensure((size_t)(total_blocks + 1) * 256 * 2));
+        TRY(c->bts_rle.ensure((size_t)n_p * 2 * g.nb * 4));
+        CK(cudaMemcpyAsync(c->pframes.p, pframes.data(), (size_t)n_p * 4, cudaMemcpyHostToDevice, st));
+        pw.blocks = (ChgBlock*)c->blocks.p; pw.pframes = (const int*)c->pframes.p; pw.runs = (uint16_t*)c->runs.p;
+        pw.bts_rle = (uint32_t*)c->bts_rle.p;
+        launch_p_stage_a(pw, st, &c->launches);
+    }
+    IWork iw;
+    memset(&iw, 0, sizeof(iw));
+    std::vector<IFrameHdr> ihdr(n_i);
+    const long total_px = (long)g.X * g.Y;
+    const int nchunks = (int)((total_px - (g.X + 1) + ICHUNK - 1) / ICHUNK);
+    if (n_i) {
+        for (int k = 0; k < n_i; k++) {
+            ihdr[k].frame = iframes[k];
+            ihdr[k].n_hdr_ev = ihdr[k].n_ev = ihdr[k].pad = 0;
+        }
+        TRY(c->ihdr.ensure((size_t)n_i * sizeof(IFrameHdr)));
+        TRY(c->desc.ensure((size_t)n_i * total_px * 2));
+        TRY(c->exit_tab.ensure((size_t)n_i * nchunks * 256));
+        TRY(c->entry.ensure((size_t)n_i * nchunks * 2));
+        TRY(c->starts.ensure((size_t)n_i * nchunks * ICHUNK * 2));
+        TRY(c->chunk_cnt.ensure((size_t)n_i * nchunks * 16));
+        CK(cudaMemcpyAsync(c->ihdr.p, ihdr.data(), (size_t)n_i * sizeof(IFrameHdr), cudaMemcpyHostToDevice, st));
+        iw.frames = d_frames; iw.g = g; iw.hdr = (IFrameHdr*)c->ihdr.p; iw.n_iframes = n_i; iw.nchunks = nchunks;
+        iw.desc = (uint16_t*)c->desc.p; iw.exit_tab = (uint8_t*)c->exit_tab.p; iw.entry = (uint16_t*)c->entry.p;
+        iw.starts = (uint16_t*)c->starts.p; iw.chunk_cnt = (uint32_t*)c->chunk_cnt.p;
+        iw.frame_ev_off = (const uint32_t*)c->frame_ev_off.p;
+        launch_i_stage_a(iw, st, &c->launches);
+    }
+    if (n_p) CK(cudaMemcpyAsync(hdr.data(), c->hdr.p, (size_t)n * sizeof(PFrameHdr), cudaMemcpyDeviceToHost, st));
+    if (n_i) CK(cudaMemcpyAsync(ihdr.data(), c->ihdr.p, (size_t)n_i * sizeof(IFrameHdr), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- event layout, chains, rANS blocks ----------------------------------------------------
+    std::vector<uint32_t> frame_ev_off(n + 1, 0), frame_nev(n, 0);
+    for (int f : pframes) frame_nev[f] = hdr[f].n_ev;
+    for (int k = 0; k < n_i; k++) frame_nev[iframes[k]] = ihdr[k].n_ev;
+    uint64_t tot = 0;
+    for (int f = 0; f < n; f++) {
+        frame_ev_off[f] = (uint32_t)tot;
+        tot += frame_nev[f];
+    }
+    frame_ev_off[n] = (uint32_t)tot;
+    if (tot >= 0xFFFF0000ull) {
+        set_error("batch too large: %llu events", (unsigned long long)tot);
+        return SCPR_E_PARAM;
+    }
+    const uint32_t total_ev = (uint32_t)tot;
+    for (size_t k = 0; k < chains.size(); k++) {
+        const int f0 = chain_first[k];
+        const int f1 = k + 1 < chains.size() ? chain_first[k + 1] : n;
+        chains[k].ev_off = frame_ev_off[f0];
+        chains[k].n_ev = frame_ev_off[f1] - frame_ev_off[f0];
+    }
+    std::vector<RansBlk> rblks;
+    uint64_t scratch_bytes = 0;
+    for (int f = 0; f < n; f++)
+        for (uint32_t b = 0; b < frame_nev[f]; b += RANS_BLOCK) {
+            RansBlk rb;
+            rb.iv_off = frame_ev_off[f] + b;
+            rb.len = frame_nev[f] - b < (uint32_t)RANS_BLOCK ? frame_nev[f] - b : (uint32_t)RANS_BLOCK;
+            rb.scratch = (uint32_t)scratch_bytes;
+            rb.size = 0;
+            rb.frame = (uint32_t)f;
+            rb.out_off = 0;
+            scratch_bytes += 2 * (uint64_t)rb.len + 4;
+            rblks.push_back(rb);
+        }
+    if (scratch_bytes >= 0xFFFF0000ull) {
+        set_error("batch too large: %llu scratch bytes", (unsigned long long)scratch_bytes);
+        return SCPR_E_PARAM;
+    }
+    const int n_chains = (int)chains.size(), n_rb = (int)rblks.size();
+    CK(cudaMemcpyAsync(c->frame_ev_off.p, frame_ev_off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    TRY(c->events.ensure((size_t)(total_ev + 1) * 4));
+    TRY(c->intervals.ensure((size_t)(total_ev + 1) * 4));
+    pw.events = (uint32_t*)c->events.p; pw.intervals = (uint32_t*)c->intervals.p;
+    iw.events = (uint32_t*)c->events.p;
+    if (n_p) launch_p_emit(pw, st, &c->launches);
+    if (n_i) launch_i_emit(iw, st, &c->launches);
+
+    if (n_chains) {
+        TRY(c->sorted.ensure((size_t)(total_ev + 1) * 4));
+        TRY(c->seg_off.ensure((size_t)n_chains * (NUM_CX + 1) * 4));
+        size_t hist_entries = 0;
+        for (auto& cd : chains) hist_entries += replay_hist_entries(cd.n_ev);
+        TRY(c->chunk_hist.ensure((hist_entries + 1) * 4));
+        std::vector<uint32_t> cb(sort_chunk_words(chains.data(), n_chains) + 4);
+        const size_t words = build_sort_chunks(chains.data(), n_chains, cb.data());
+        TRY(c->chunk_base.ensure((words + 1) * 4));
+        TRY(c->chains.ensure((size_t)n_chains * sizeof(ChainDesc)));
+        CK(cudaMemcpyAsync(c->chunk_base.p, cb.data(), words * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->chains.p, chains.data(), (size_t)n_chains * sizeof(ChainDesc), cudaMemcpyHostToDevice, st));
+        ReplayWork rw;
+        memset(&rw, 0, sizeof(rw));
+        rw.events = (const uint32_t*)c->events.p; rw.intervals = (uint32_t*)c->intervals.p;
+        rw.chains = (const ChainDesc*)c->chains.p; rw.n_chains = n_chains; rw.h_chains = chains.data();
+        rw.states = (uint8_t*)c->states.p; rw.f0 = 32;
+        rw.sorted = (uint32_t*)c->sorted.p; rw.seg_off = (uint32_t*)c->seg_off.p; rw.chunk_hist = (uint32_t*)c->chunk_hist.p;
+        rw.chunk_base = (const uint32_t*)c->chunk_base.p; rw.total_events = total_ev;
+        launch_replay(rw, st, &c->launches);
+        CK(cudaStreamSynchronize(st));  // `cb` and `chains` are host vectors read by the async copies above
+    }
+    if (n_rb) {
+        TRY(c->rblks.ensure((size_t)n_rb * sizeof(RansBlk)));
+        TRY(c->scratch.ensure((size_t)scratch_bytes + 16));
+        CK(cudaMemcpyAsync(c->rblks.p, rblks.data(), (size_t)n_rb * sizeof(RansBlk), cudaMemcpyHostToDevice, st));
+        launch_rans((const uint32_t*)c->intervals.p, (RansBlk*)c->rblks.p, n_rb, (uint8_t*)c->scratch.p, st, &c->launches);
+        CK(cudaMemcpyAsync(rblks.data(), c->rblks.p, (size_t)n_rb * sizeof(RansBlk), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+
+    // ---- output layout -----------------------------------------------------------------------------
+    std::vector<uint64_t> frame_out(n + 1, 0);
+    {
+        uint64_t pos = 0;
+        size_t rb = 0;
+        for (int f = 0; f < n; f++) {
+            frame_out[f] = pos;
+            uint64_t sz = 0;
+            switch (ftype[f]) {
+            case FT_FLAT: sz = 4; break;
+            case FT_PSAME: sz = 1; break;
+            default:
+                sz = 1;
+                while (rb < rblks.size() && rblks[rb].frame == (uint32_t)f) {
+                    rblks[rb].out_off = (uint32_t)(pos + sz);
+                    sz += rblks[rb].size;
+                    rb++;
+                }
+            }
+            pos += sz;
+            if (sizes) sizes[f] = (uint32_t)sz;
+            if (ftypes_out) ftypes_out[f] = (ftype[f] == FT_P || ftype[f] == FT_PSAME) ? 1 : 0;
+        }
+        frame_out[n] = pos;
+        if (pos > dst_cap) {
+            set_error("destination too small: need %llu bytes, have %zu", (unsigned long long)pos, dst_cap);
+            return SCPR_E_DSTSIZE;
+        }
+        if (pos >= 0xFFFF0000ull) {
+            set_error("batch output too large");
+            return SCPR_E_PARAM;
+        }
+    }
+    const uint64_t out_bytes = frame_out[n];
+    if (n_rb) {
+        TRY(c->out.ensure((size_t)out_bytes + 16));
+        CK(cudaMemcpyAsync(c->rblks.p, rblks.data(), (size_t)n_rb * sizeof(RansBlk), cudaMemcpyHostToDevice, st));
+        launch_assemble((const RansBlk*)c->rblks.p, n_rb, (const uint8_t*)c->scratch.p, (uint8_t*)c->out.p, st, &c->launches);
+        CK(cudaMemcpyAsync(dst, c->out.p, (size_t)out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    // the last frame of the batch is the next call's previous frame (memcpy(prev, ...) of the reference)
+    CK(cudaMemcpyAsync(c->prev.p, d_frames + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < n; f++) {
+        uint8_t* o = dst + frame_out[f];
+        switch (ftype[f]) {
+        case FT_FLAT:
+            o[0] = 0x31;  // 1 + (version-1)*16, screencap.cpp:1495
+            o[1] = (uint8_t)summary[f].pixel0;
+            o[2] = (uint8_t)(summary[f].pixel0 >> 8);
+            o[3] = (uint8_t)(summary[f].pixel0 >> 16);
+            break;
+        case FT_PSAME: o[0] = 0; break;    // screencap.cpp:1113-1116
+        case FT_P: o[0] = 1; break;        // screencap.cpp:1117
+        case FT_I: o[0] = 0x32; break;     // 2 + (version-1)*16, screencap.cpp:1509
+        }
+    }
+    // keep what the debug hooks need
+    c->dbg_n = n;
+    c->dbg_frame_ev_off = frame_ev_off;
+    c->dbg_ftype = ftype;
+    c->dbg_hdr = hdr;
+    return (int64_t)out_bytes;
+}
+
+extern "C" {
+
+int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags, uint8_t* dst,
+                               size_t dst_cap, uint32_t* sizes, uint8_t* ftypes) {
+    if (!c || !d_frames || !keyflags || !dst || n < 0) return SCPR_E_PARAM;
+    return encode_batch(c, d_frames, n, keyflags, dst, dst_cap, sizes, ftypes);
+}
+
+int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const uint8_t* keyflags, uint8_t* dst, size_t dst_cap,
+                           uint32_t* sizes, uint8_t* ftypes) {
+    if (!c || !frames || !keyflags || !dst || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * c->g.frame_bytes;
+    TRY(c->frames.ensure(bytes));
+    CK(cudaMemcpyAsync(c->frames.p, frames, bytes, cudaMemcpyHostToDevice, c->st));
+    return encode_batch(c, (const uint8_t*)c->frames.p, n, keyflags, dst, dst_cap, sizes, ftypes);
+}
+
+int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss) {
+    if (!c || !src || !dst || !ftype || dst_cap <= 0) return SCPR_E_PARAM;
+    if (loss != 0) {
+        set_error("lossy modes are not built yet (loss must be 0)");
+        return SCPR_E_UNSUPPORTED;
+    }
+    const uint8_t key = *ftype ? 0 : 1;
+    uint32_t size = 0;
+    uint8_t ft = 0;
+    const int64_t r = scpr_compress_clip(c, src, 1, &key, dst, (size_t)dst_cap, &size, &ft);
+    if (r < 0) return (int)r;
+    *ftype = ft;
+    return (int)size;
+}
+
+int64_t scpr_debug_events(scpr_codec* c, int frame, uint32_t* ev, uint32_t* iv, size_t cap) {
+    if (!c || frame < 0 || frame >= c->dbg_n) return SCPR_E_PARAM;
+    const uint32_t off = c->dbg_frame_ev_off[frame], cnt = c->dbg_frame_ev_off[frame + 1] - off;
+    const size_t m = cnt < cap ? cnt : cap;
+    if (m && ev) CK(cudaMemcpy(ev, (const uint32_t*)c->events.p + off, m * 4, cudaMemcpyDeviceToHost));
+    if (m && iv) CK(cudaMemcpy(iv, (const uint32_t*)c->intervals.p + off, m * 4, cudaMemcpyDeviceToHost));
+    return cnt;
+}
+
+int scpr_debug_blocks(scpr_codec* c, int frame, uint8_t* bts, int32_t* sxy4, int32_t* mv2) {
+    if (!c || frame < 0 || frame >= c->dbg_n) return SCPR_E_PARAM;
+    const Geo& g = c->g;
+    memset(bts, 0, (size_t)g.nb);
+    if (c->dbg_ftype[frame] != FT_P) return 0;
+    const PFrameHdr& h = c->dbg_hdr[frame];
+    std::vector<ChgBlock> blocks(h.n_changed);
+    if (h.n_changed)
+        CK(cudaMemcpy(blocks.data(), (const ChgBlock*)c->blocks.p + h.chg_off, (size_t)h.n_changed * sizeof(ChgBlock),
+                      cudaMemcpyDeviceToHost));
+    for (auto& b : blocks) {
+        const int by = (int)b.bi / g.nbx, bx = (int)b.bi - by * g.nbx;
+        bts[b.bi] = b.bt;
+        if (sxy4) {
+            sxy4[4 * b.bi + 0] = bx * 16 + (int)((b.info >> 4) & 15);
+            sxy4[4 * b.bi + 1] = by * 16 + (int)((b.info >> 8) & 15);
+            sxy4[4 * b.bi + 2] = bx * 16 + (int)((b.info >> 12) & 15) + 1;
+            sxy4[4 * b.bi + 3] = by * 16 + (int)((b.info >> 16) & 15) + 1;
+        }
+        if (mv2 && b.bt >= 3) {
+            mv2[2 * b.bi] = b.mx;
+            mv2[2 * b.bi + 1] = b.my;
+        }
+    }
+    return h.n_changed;
+}
+
+float scpr_bench_frame_scan(scpr_codec* c, const uint8_t* d_frames, int n, int reps) {
+    if (!c || !d_frames || n <= 0 || reps <= 0) return (float)SCPR_E_PARAM;
+    const Geo& g = c->g;
+    if (cudaSetDevice(c->device) != cudaSuccess) return (float)SCPR_E_CUDA;
+    if (c->blkinfo.ensure((size_t)n * g.nb * 4) < 0 || c->summary.ensure((size_t)n * sizeof(FrameSummary)) < 0)
+        return (float)SCPR_E_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, c->st,
+                      &c->launches);
+    cudaEventRecord(e0, c->st);
+    for (int r = 0; r < reps; r++)
+        launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p,
+                          c->st, &c->launches);
+    cudaEventRecord(e1, c->st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (cudaGetLastError() != cudaSuccess) return (float)SCPR_E_CUDA;
+    return ms / reps;
+}
+
+}  // extern "C"

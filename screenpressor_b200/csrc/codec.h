@@ -1,0 +1,58 @@
+// codec.h -- the codec object behind the C ABI (host side only).
+#pragma once
+#include <vector>
+
+#include "../../include/scpr_c.h"
+#include "kernels.cuh"
+
+namespace scpr {
+
+// grow-only device buffer
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+};
+
+}  // namespace scpr
+
+struct scpr_codec {
+    scpr_params p;
+    int device = 0;
+    cudaStream_t st = 0;
+    scpr::Geo g;
+    uint64_t launches = 0;
+
+    // ---- encoder state carried between calls (CScreenCapt members, screencap.h:445-463) ----------
+    unsigned fn = 0;                 // coded (non-flat) frames so far
+    bool last_was_flat = false;
+    uint8_t last_flat_clr[3] = {0, 0, 0};
+    bool have_models = false;
+    scpr::DBuf prev;                 // previous frame, native pixel format
+    scpr::DBuf mvs;                  // int2 per block, never cleared
+    scpr::DBuf states;               // pool of ModelState; states[cur_state] belongs to the open chain
+    int n_states = 0, cur_state = 0;
+
+    // ---- encoder workspaces ---------------------------------------------------------------------
+    scpr::DBuf frames, blkinfo, summary, chg_list, hdr, ftype, blocks, pframes, runs, bts_rle;
+    scpr::DBuf ihdr, desc, exit_tab, entry, starts, chunk_cnt;
+    scpr::DBuf frame_ev_off, events, intervals, sorted, seg_off, chunk_hist, chunk_base, chains, rblks, scratch, out;
+
+    // ---- decoder state and workspaces -----------------------------------------------------------
+    bool dec_created = false;        // a codec exists (first I frame seen), screencap.cpp:1698-1702
+    int dec_version = 4;
+    scpr::DBuf dec_state;            // pool of ModelState; dec_state[dec_cur_state] belongs to the open chain
+    int dec_n_states = 0, dec_cur_state = 0;
+    bool dec_last_was_flat = false;
+    uint8_t dec_last_flat_clr[3] = {0, 0, 0};
+    scpr::DBuf dec_prev;             // last decoded frame, output format
+    int dec_prev_pitch = 0;
+    scpr::DBuf dec_mvs, dec_ws, dec_stream, dec_desc, dec_frames;
+
+    // ---- debug hooks -----------------------------------------------------------------------------
+    int dbg_n = 0;
+    std::vector<uint32_t> dbg_frame_ev_off;
+    std::vector<uint8_t> dbg_ftype;
+    std::vector<scpr::PFrameHdr> dbg_hdr;
+};

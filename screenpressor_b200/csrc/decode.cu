@@ -1,0 +1,677 @@
+// decode.cu -- the decoder: one warp per GOP chain for the serial part, a streaming fill kernel for
+// everything that is a copy.
+//
+// Replaces (reference):
+//   ScreenCodec::DecompressFrame                 screencap.cpp:1695-1743 (RGB24 -> RGB32 repack fused away)
+//   CScreenCapt::DecompressFrame / I / P         screencap.cpp:1522-1557, 414-498, 1275-1432
+//   UseANS::decodeC / decodeF / decodeBool       screencap.h:318-359, 411-421
+//   Context::decode / update                     ans_contexts.cpp:52-74
+//   RansDecInit / Get / Advance                  rans_byte.h:105-146
+//
+// A GOP is one dependency chain (model state, rANS state and reconstructed pixels interleave,
+// SURVEY.md 0.4), so the entropy walk of a chain is serial and runs on one warp; chains of a clip
+// run concurrently.  What the reference spends most of a sparse P frame on -- copying unchanged
+// blocks from the previous frame and repacking RGB24 to RGB32 -- is not done by that warp at all:
+// the chain only writes the blocks a frame changes (decoded in a shared-memory tile), tracks for
+// every block which frame holds its current pixels, and k_dec_fill afterwards gathers every
+// untouched block of every frame from that source in one HBM-bound pass.
+#include <string.h>
+
+#include <vector>
+
+#include "codec.h"
+#include "models.cuh"
+
+namespace scpr {
+
+enum : uint8_t { DK_FLAT = 0, DK_I = 1, DK_PSAME = 2, DK_P = 3 };
+
+struct DecFrame {
+    uint32_t src_off;   // offset of the frame's bytes in the device stream copy
+    uint32_t size;
+    uint8_t kind;       // DK_*
+    uint8_t renew;      // flat frame that resets the models (screencap.cpp:1547-1550)
+    uint8_t pad[2];
+    uint32_t flat_clr;  // colour of a flat frame
+};
+
+struct DecChain {
+    int first, count;   // frames [first, first+count) of the clip
+    int state;          // model state slot
+};
+
+struct DecWork {
+    Geo g;              // geometry of the OUTPUT frames (pitch = caller's pitch)
+    const uint8_t* stream;
+    const DecFrame* frames;
+    const DecChain* chains;
+    uint8_t* states;
+    int f0;
+    uint8_t* out;       // n output frames
+    const uint8_t* prev0;   // frame decoded last by the previous call (output format, pitch g.pitch)
+    int* src_cur;       // per chain: nb ints, frame that holds each block's current pixels (-1 = prev0)
+    int* src_prev;      // per chain: same, as of the previous frame
+    int* stamp;         // per chain: frame in which src_cur was last changed
+    uint8_t* upd;       // n * nb flags: block written by the chain kernel in this frame
+    int16_t* fill_src;  // n * nb: source frame of every block (k_dec_sources)
+    int n;
+};
+
+// ---- pixel access through the block-source map ----------------------------------------------------
+struct ChainCtx {
+    const DecWork* w;
+    int* src_cur; int* src_prev; int* stamp;
+    int f;              // frame being decoded
+};
+
+__device__ __forceinline__ uint32_t frame_px(const DecWork& w, int src, int x, int y) {
+    if (src >= 0 && w.frames[src].kind == DK_FLAT) return w.frames[src].flat_clr;
+    const uint8_t* base = src >= 0 ? w.out + (size_t)src * w.g.frame_bytes : w.prev0;
+    return load_px(base, w.g, x, y);
+}
+// pixel of the frame being decoded (only valid for pixels already reconstructed or unchanged)
+__device__ __forceinline__ uint32_t cur_px(const ChainCtx& c, int x, int y) {
+    const int b = (y >> 4) * c.w->g.nbx + (x >> 4);
+    return frame_px(*c.w, c.src_cur[b], x, y);
+}
+// pixel of the previous frame
+__device__ __forceinline__ uint32_t prev_px(const ChainCtx& c, int x, int y) {
+    const int b = (y >> 4) * c.w->g.nbx + (x >> 4);
+    const int s = c.stamp[b] == c.f ? c.src_prev[b] : c.src_cur[b];
+    return frame_px(*c.w, s, x, y);
+}
+__device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, int y, uint32_t v) {
+    uint8_t* p = frame + (size_t)y * g.pitch + (size_t)x * g.bpp;
+    if (g.bpp == 4)
+        *reinterpret_cast<uint32_t*>(p) = v | 0xFF000000u;  // alpha := 255, screencap.cpp:1721
+    else {
+        p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+    }
+}
+
+// ---- serial entropy state (held by lane 0) ---------------------------------------------------------
+struct Ent {
+    const uint8_t* p;
+    uint32_t x;
+    int ndec;
+    uint32_t cx, cx1;
+    ModelState* m;
+    int f0;
+};
+__device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
+    e.x = (uint32_t)e.p[0] | ((uint32_t)e.p[1] << 8) | ((uint32_t)e.p[2] << 16) | ((uint32_t)e.p[3] << 24);
+    e.p += 4;
+}
+__device__ __forceinline__ void rdec_count(Ent& e) {  // re-init every 131072 symbols (screencap.h:327-331)
+    if (++e.ndec == RANS_BLOCK) {
+        rdec_init(e);
+        e.ndec = 0;
+    }
+}
+__device__ __forceinline__ void rdec_advance(Ent& e, uint32_t start, uint32_t freq) {  // RansDecAdvance
+    uint32_t x = e.x;
+    x = freq * (x >> PROB_BITS) + (x & (PROB_SCALE - 1)) - start;
+    while (x < RANS_L) x = (x << 8) | *e.p++;
+    e.x = x;
+}
+__device__ inline int dec_color(Ent& e, int id) {  // decodeC
+    ColorState& x = e.m->color[id];
+    int c;
+    if (x.kind >= 4) {
+        c = cc_find(x, (int)(e.x & (PROB_SCALE - 1)));
+        const uint32_t iv = cc_encode_counted(x, c);
+        rdec_advance(e, iv >> 16, iv & 0xFFFFu);
+    } else {
+        c = *e.p++;
+        cc_update_raw(x, c, e.f0);
+    }
+    rdec_count(e);
+    return c;
+}
+__device__ inline int dec_fixed(Ent& e, int id) {  // decodeF
+    FixedState& f = e.m->fx[id - CX_NTAB];
+    const int c = table_find(f.cum, f.nsym, (int)(e.x & (PROB_SCALE - 1)));
+    const uint32_t freq = f.freq[c], cum = f.cum[c];
+    table_incr(f.cnt, f.freq, f.cum, f.nsym, f.cntsum, c);
+    rdec_advance(e, cum, freq);
+    rdec_count(e);
+    return c;
+}
+__device__ inline int dec_bool(Ent& e) {  // decodeBool
+    const int flag = (e.x & (PROB_SCALE - 1)) >= PROB_SCALE / 2;
+    rdec_advance(e, flag ? PROB_SCALE / 2 : 0, PROB_SCALE / 2);
+    rdec_count(e);
+    return flag;
+}
+__device__ inline uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
+    const uint32_t r = (uint32_t)dec_color(e, 0 * 4096 + (int)(e.cx + e.cx1));
+    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = r >> 2;
+    const uint32_t g = (uint32_t)dec_color(e, 1 * 4096 + (int)(e.cx + e.cx1));
+    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = g >> 2;
+    const uint32_t b = (uint32_t)dec_color(e, 2 * 4096 + (int)(e.cx + e.cx1));
+    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = b >> 2;
+    return r | (g << 8) | (b << 16);
+}
+__device__ __forceinline__ void set_cx_from(Ent& e, uint32_t px) {  // screencap.cpp:488-493, 1417-1419
+    e.cx = ((px >> 8) & 255) >> 2;
+    e.cx1 = (e.cx << 6) & 0xFC0;
+    e.cx = ((px >> 16) & 255) >> 2;
+}
+
+__device__ __forceinline__ uint32_t grad_px(uint32_t l, uint32_t t, uint32_t tl) {  // type 4, truncated to bytes
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int sh = 8 * c;
+        v |= (uint32_t)(((int)((l >> sh) & 255) + (int)((t >> sh) & 255) - (int)((tl >> sh) & 255)) & 255) << sh;
+    }
+    return v;
+}
+
+// ---- I frame (DecompressI, screencap.cpp:414-498) --------------------------------------------------
+// q = raster index; all neighbours are pixels of this frame: left = q-1 (lasti), top = q-X,
+// top-left = q-X-1 (byte offset -stride-3; with row padding the x==0 case reads padding, A.2).
+__device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
+    const Geo& g = w.g;
+    const long total = (long)g.X * g.Y;
+    const int stride24 = (g.X * 3 + 3) & ~3;
+    const bool padded = stride24 != g.X * 3;
+    auto px_at = [&](long q) { return load_px(frame, g, (int)(q % g.X), (int)(q / g.X)); };
+    auto tl_at = [&](long q) -> uint32_t {
+        const int x = (int)(q % g.X), y = (int)(q / g.X);
+        if (!padded || x > 0) return px_at(q - g.X - 1);
+        // bytes (y-1)*stride-3 .. : tail of row y-2 incl. zero padding.  The frame is in output
+        // format, so rebuild the RGB24 view byte by byte.
+        uint32_t v = 0;
+        const long o = (long)y * stride24 - stride24 - 3;
+        for (int k = 0; k < 3; k++) {
+            const long ok = o + k;
+            const int row = (int)(ok / stride24), col = (int)(ok % stride24);
+            uint32_t b = 0;
+            if (col < 3 * g.X) b = (load_px(frame, g, col / 3, row) >> (8 * (col % 3))) & 255;
+            v |= b << (8 * k);
+        }
+        return v;
+    };
+    long q = 0;
+    int ptype = 0;
+    // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
+    while (q < g.X + 1) {
+        uint32_t c = 0;
+        int n = 0;
+        if (lane == 0) {
+            c = dec_rgb(e);
+            n = dec_fixed(e, CX_NTAB + 0);
+        }
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        if (q + n > total) n = (int)(total - q);  // corrupt input guard
+        if (n <= 0) return;
+        for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
+        q += n;
+        __syncwarp();
+    }
+    while (q < total) {
+        uint32_t c = 0;
+        int n = 0;
+        if (lane == 0) {
+            ptype = dec_fixed(e, CX_PTYPE + ptype);
+            if (!ptype) c = dec_rgb(e);
+            n = dec_fixed(e, CX_NTAB + ptype);
+        }
+        ptype = __shfl_sync(0xFFFFFFFFu, ptype, 0);
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        if (q + n > total) n = (int)(total - q);  // corrupt input guard
+        if (n <= 0) return;
+        if (ptype == 0 || ptype == 1) {
+            if (ptype == 1) c = px_at(q - 1);
+            for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
+        } else if (n < g.X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
+            for (int i = lane; i < n; i += 32) {
+                const long qq = q + i;
+                store_px(frame, g, (int)(qq % g.X), (int)(qq / g.X), ptype == 2 ? px_at(qq - g.X) : tl_at(qq));
+            }
+        } else {  // gradient chains through the left pixel; tiny frames may read their own run
+            if (lane == 0)
+                for (int i = 0; i < n; i++) {
+                    const long qq = q + i;
+                    uint32_t v;
+                    if (ptype == 2) v = px_at(qq - g.X);
+                    else if (ptype == 5) v = tl_at(qq);
+                    else v = grad_px(px_at(qq - 1), px_at(qq - g.X), tl_at(qq));
+                    store_px(frame, g, (int)(qq % g.X), (int)(qq / g.X), v);
+                }
+        }
+        __syncwarp();
+        q += n;
+        if (lane == 0) set_cx_from(e, px_at(q - 1));
+    }
+}
+
+// ---- P frame (DecompressP, screencap.cpp:1275-1432) ------------------------------------------------
+__device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame, int f, uint8_t* s_bts, uint32_t (*tile)[17],
+                         int lane) {
+    const Geo& g = w.g;
+    int xx1 = 0, xx2 = 0;
+    if (lane == 0) {
+        int t = dec_fixed(e, CX_XX);
+        xx1 = (dec_fixed(e, CX_XX) << 8) + t;
+        t = dec_fixed(e, CX_XX);
+        xx2 = (dec_fixed(e, CX_XX) << 8) + t;
+        if (xx2 >= g.nb) xx2 = g.nb - 1;  // corrupt input guard
+    }
+    xx1 = __shfl_sync(0xFFFFFFFFu, xx1, 0);
+    xx2 = __shfl_sync(0xFFFFFFFFu, xx2, 0);
+    // block types of [xx1, xx2] as (type, run) pairs (screencap.cpp:1306-1313)
+    for (int i = lane; i < g.nb; i += 32) s_bts[i] = 0;
+    __syncwarp();
+    for (int x = xx1; x <= xx2;) {
+        int c = 0, n = 0;
+        if (lane == 0) {
+            c = dec_fixed(e, CX_BT);
+            n = dec_fixed(e, CX_NTAB2);
+        }
+        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        if (n <= 0) break;
+        for (int i = lane; i < n && x + i < g.nb; i += 32) s_bts[x + i] = (uint8_t)c;
+        x += n;
+    }
+    __syncwarp();
+    if (lane == 0) e.cx = e.cx1 = 0;
+    int lastmx = 0, lastmy = 0;
+    uint8_t* upd = w.upd + (size_t)f * g.nb;
+    for (int bi = xx1; bi <= xx2; bi++) {
+        const int bt = s_bts[bi];
+        if (!bt) continue;
+        const int by = bi / g.nbx, bx = bi - by * g.nbx;
+        const int bx0 = bx * 16, by0 = by * 16;
+        const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
+        int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
+        // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
+        for (int p = lane; p < 17 * 17; p += 32) {
+            const int ty = p / 17, tx = p - ty * 17;
+            const int x = bx0 + tx - 1, y = by0 + ty - 1;
+            uint32_t v = 0;
+            if (x >= 0 && y >= 0 && x < g.X && y < g.Y) {
+                if (tx == 0 || ty == 0) v = cur_px(cc, x, y);
+                else if ((bt - 1) & 1) v = prev_px(cc, x, y);  // partial block: starts as a copy of prev
+            }
+            tile[ty][tx] = v;
+        }
+        __syncwarp();
+        if ((bt - 1) & 1) {
+            int v4[4] = {0, 0, 0, 0};
+            if (lane == 0)
+                for (int k = 0; k < 4; k++) v4[k] = dec_fixed(e, CX_SXY + k);
+            x1 = bx0 + __shfl_sync(0xFFFFFFFFu, v4[0], 0);
+            y1 = by0 + __shfl_sync(0xFFFFFFFFu, v4[1], 0);
+            x2 = bx0 + __shfl_sync(0xFFFFFFFFu, v4[2], 0) + 1;
+            y2 = by0 + __shfl_sync(0xFFFFFFFFu, v4[3], 0) + 1;
+            if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
+            if (y2 > by0 + bh) y2 = by0 + bh;
+            if (x1 >= x2) x1 = x2 - 1;
+            if (y1 >= y2) y1 = y2 - 1;
+        }
+        const int sw = x2 - x1, sh = y2 - y1;
+        if ((bt - 1) & 2) {  // motion vector block
+            int mx = lastmx, my = lastmy;
+            if (lane == 0) {
+                if (!dec_bool(e)) {
+                    mx = dec_fixed(e, CX_MV + 0) - 256;
+                    my = dec_fixed(e, CX_MV + 1) - 256;
+                }
+            }
+            mx = __shfl_sync(0xFFFFFFFFu, mx, 0);
+            my = __shfl_sync(0xFFFFFFFFu, my, 0);
+            lastmx = mx; lastmy = my;
+            for (int p = lane; p < sw * sh; p += 32) {
+                const int xx = p % sw, yy = p / sw;
+                int sx = x1 + xx + mx, sy = y1 + yy + my;
+                sx = min(max(sx, 0), g.X - 1); sy = min(max(sy, 0), g.Y - 1);  // corrupt input guard
+                tile[1 + y1 - by0 + yy][1 + x1 - bx0 + xx] = prev_px(cc, sx, sy);
+            }
+        } else {  // pixel runs over the sub-rect in its own raster order
+            int pos = 0, ptype = 0;
+            const int npx = sw * sh;
+            const int ox = 1 + x1 - bx0, oy = 1 + y1 - by0;
+            while (pos < npx) {
+                uint32_t c = 0;
+                int n = 0;
+                if (lane == 0) {
+                    ptype = dec_fixed(e, CX_PTYPE + ptype);
+                    if (!ptype) c = dec_rgb(e);
+                    n = dec_fixed(e, CX_NTAB + ptype);
+                    if (n > npx - pos) n = npx - pos;
+                    uint32_t v = c;
+                    for (int i = 0; i < n; i++) {
+                        const int xx = (pos + i) % sw, yy = (pos + i) / sw;
+                        uint32_t* t = &tile[oy + yy][ox + xx];
+                        switch (ptype) {
+                        case 1: v = t[-1]; break;
+                        case 2: v = t[-17]; break;
+                        case 3: v = (bt - 1) & 1 ? t[0] : prev_px(cc, x1 + xx, y1 + yy); break;
+                        case 4: v = grad_px(t[-1], t[-17], t[-18]); break;
+                        case 5: v = t[-18]; break;
+                        }
+                        t[0] = v;
+                    }
+                    set_cx_from(e, v);
+                }
+                ptype = __shfl_sync(0xFFFFFFFFu, ptype, 0);
+                n = __shfl_sync(0xFFFFFFFFu, n, 0);
+                if (n <= 0) break;
+                pos += n;
+            }
+        }
+        __syncwarp();
+        // write the whole block and hand its ownership to this frame
+        for (int p = lane; p < bw * bh; p += 32) {
+            const int xx = p % bw, yy = p / bw;
+            store_px(frame, g, bx0 + xx, by0 + yy, tile[1 + yy][1 + xx]);
+        }
+        if (lane == 0) {
+            if (cc.stamp[bi] != f) {
+                cc.src_prev[bi] = cc.src_cur[bi];
+                cc.stamp[bi] = f;
+            }
+            cc.src_cur[bi] = f;
+            upd[bi] = 1;
+        }
+        __syncwarp();
+    }
+}
+
+// one warp per chain
+__global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
+    extern __shared__ uint8_t s_mem[];
+    uint32_t(*tile)[17] = reinterpret_cast<uint32_t(*)[17]>(s_mem);
+    uint8_t* s_bts = s_mem + 17 * 17 * 4;
+    const int lane = threadIdx.x;
+    const DecChain ch = w.chains[blockIdx.x];
+    const Geo& g = w.g;
+    ChainCtx cc;
+    cc.w = &w;
+    cc.src_cur = w.src_cur + (size_t)blockIdx.x * g.nb;
+    cc.src_prev = w.src_prev + (size_t)blockIdx.x * g.nb;
+    cc.stamp = w.stamp + (size_t)blockIdx.x * g.nb;
+    for (int i = lane; i < g.nb; i += 32) {
+        cc.src_cur[i] = -1;
+        cc.src_prev[i] = -1;
+        cc.stamp[i] = -1;
+    }
+    __syncwarp();
+    Ent e;
+    e.m = reinterpret_cast<ModelState*>(w.states + (size_t)ch.state * sizeof(ModelState));
+    e.f0 = w.f0;
+    e.cx = e.cx1 = 0;
+    e.ndec = 0;
+    e.x = 0;
+    e.p = nullptr;
+    for (int f = ch.first; f < ch.first + ch.count; f++) {
+        const DecFrame df = w.frames[f];
+        uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
+        cc.f = f;
+        if (df.kind == DK_PSAME) continue;  // every block keeps its source (memcpy(pDst, prev), screencap.cpp:1288-1291)
+        if (df.kind == DK_FLAT || df.kind == DK_I) {
+            if (df.kind == DK_I || df.renew) {  // RenewI
+                for (int i = lane; i < NUM_COLOR_CX; i += 32) e.m->color[i].kind = 0;
+                if (lane < NUM_FIXED_CX) fixed_renew(e.m->fx[lane], fixed_nsym(CX_NTAB + lane));
+                __syncwarp();
+            }
+            for (int i = lane; i < g.nb; i += 32) {  // the whole frame is new
+                cc.src_prev[i] = cc.src_cur[i];
+                cc.stamp[i] = f;
+                cc.src_cur[i] = f;
+            }
+            __syncwarp();
+            if (df.kind == DK_I) {
+                e.p = w.stream + df.src_off + 1;
+                e.ndec = 0;
+                e.cx = e.cx1 = 0;
+                if (lane == 0) rdec_init(e);
+                decode_i(w, e, frame, lane);
+            }
+            continue;
+        }
+        e.p = w.stream + df.src_off + 1;
+        e.ndec = 0;
+        if (lane == 0) rdec_init(e);
+        decode_p(w, cc, e, frame, f, s_bts, tile, lane);
+        __threadfence_block();
+    }
+}
+
+// source frame of every block of every frame: thread per block, frames in order
+__global__ void k_dec_sources(DecWork w) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.g.nb) return;
+    int last = -1;
+    for (int f = 0; f < w.n; f++) {
+        const uint8_t k = w.frames[f].kind;
+        if (k == DK_I || k == DK_FLAT || w.upd[(size_t)f * w.g.nb + b]) last = f;
+        w.fill_src[(size_t)f * w.g.nb + b] = (int16_t)last;
+    }
+}
+
+// gather every block a frame did not write itself from the frame that holds it (or paint flat
+// frames).  One warp per block row strip of 8 blocks, as in the frame scan; 32 bpp fast path uses
+// 128-bit accesses.
+__global__ void __launch_bounds__(256) k_dec_fill(DecWork w) {
+    const Geo& g = w.g;
+    const int lane = threadIdx.x & 31;
+    const int strips_x = (g.nbx + 7) >> 3;
+    const int strips_per_frame = strips_x * g.nby;
+    const long strip = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (strip >= (long)w.n * strips_per_frame) return;
+    const int f = (int)(strip / strips_per_frame);
+    const int s = (int)(strip - (long)f * strips_per_frame);
+    const int by = s / strips_x, sx = s - by * strips_x;
+    const int bx = sx * 8 + (lane >> 2);
+    if (bx >= g.nbx) return;
+    const int src = w.fill_src[(size_t)f * g.nb + (size_t)by * g.nbx + bx];
+    const bool flat = w.frames[f].kind == DK_FLAT;
+    if (src == f && !flat) return;  // written by the chain kernel
+    uint8_t* dst = w.out + (size_t)f * g.frame_bytes;
+    const int y0 = by * 16, rows = min(16, g.Y - y0);
+    const bool src_flat = flat || (src >= 0 && w.frames[src].kind == DK_FLAT);
+    const uint32_t clr = flat ? w.frames[f].flat_clr : (src >= 0 ? w.frames[src].flat_clr : 0u);
+    const uint8_t* sp = src >= 0 ? w.out + (size_t)src * g.frame_bytes : w.prev0;
+    const int x0 = bx * 16 + (lane & 3) * 4;
+    if (g.bpp == 4 && (g.pitch & 15) == 0 && (g.X & 3) == 0) {
+        if (x0 >= g.X) return;
+        const size_t base = (size_t)y0 * g.pitch + (size_t)x0 * 4;
+        if (src_flat) {
+            const uint32_t v = clr | 0xFF000000u;
+            const uint4 q = make_uint4(v, v, v, v);
+            for (int r = 0; r < rows; r++) *reinterpret_cast<uint4*>(dst + base + (size_t)r * g.pitch) = q;
+        } else {
+            uint4 q[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+                if (r < rows) q[r] = *reinterpret_cast<const uint4*>(sp + base + (size_t)r * g.pitch);
+#pragma unroll
+            for (int r = 0; r < 16; r++)
+                if (r < rows) *reinterpret_cast<uint4*>(dst + base + (size_t)r * g.pitch) = q[r];
+        }
+    } else {
+        for (int r = 0; r < rows; r++)
+            for (int k = 0; k < 4; k++) {
+                const int x = x0 + k;
+                if (x < g.X) store_px(dst, g, x, y0 + r, src_flat ? clr : load_px(sp, g, x, y0 + r));
+            }
+    }
+}
+
+}  // namespace scpr
+
+using namespace scpr;
+#define CK(call) SCPR_CUDA_CHECK(call)
+#define TRY(expr)                 \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ < 0) return r__;  \
+    } while (0)
+
+static int ensure_dec_states(scpr_codec* c, int n) {
+    if (n <= c->dec_n_states) return SCPR_OK;
+    DBuf nb;
+    TRY(nb.ensure((size_t)n * model_state_bytes()));
+    if (c->dec_state.p)
+        CK(cudaMemcpyAsync((uint8_t*)nb.p + (size_t)c->dec_cur_state * model_state_bytes(),
+                           (uint8_t*)c->dec_state.p + (size_t)c->dec_cur_state * model_state_bytes(), model_state_bytes(),
+                           cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->dec_state.release();
+    c->dec_state = nb;
+    c->dec_n_states = n;
+    return SCPR_OK;
+}
+
+// n frames, bitstreams on the host, decoded frames to device memory `d_out` (pitch bytes per row)
+static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
+                        int pitch) {
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->st;
+    if (n <= 0) return 1;
+    Geo g = c->g;
+    g.pitch = pitch;
+    g.frame_bytes = (size_t)pitch * g.Y;
+    if (pitch < g.X * g.bpp) return SCPR_E_PARAM;
+    // ---- host plan: frame kinds, versions, chains (DecompressFrame, screencap.cpp:1695-1702, 1522-1557)
+    std::vector<DecFrame> frames(n);
+    std::vector<DecChain> chains;
+    uint64_t off = 0;
+    for (int f = 0; f < n; f++) {
+        DecFrame& d = frames[f];
+        memset(&d, 0, sizeof(d));
+        d.src_off = (uint32_t)off;
+        d.size = sizes[f];
+        const uint8_t* s = stream + off;
+        off += sizes[f];
+        if (sizes[f] < 1) return SCPR_E_PARAM;
+        if (!c->dec_created) {
+            if (ftypes[f] > 0) return 0;  // P frame before any I frame
+            const int version = (s[0] >> 4) + 1;
+            if (version != 3 && version != 4) return -version;  // BadVersionException; v2 = range coder, out of scope
+            c->dec_version = version;
+            c->dec_created = true;
+        }
+        if (ftypes[f]) {
+            c->dec_last_was_flat = false;
+            d.kind = (s[0] & 1) ? DK_P : DK_PSAME;
+            if (chains.empty()) chains.push_back(DecChain{f, 0, -2});  // continues the previous call's chain
+        } else if ((s[0] & 0x0F) == 1) {
+            if (sizes[f] < 4) return SCPR_E_PARAM;
+            d.kind = DK_FLAT;
+            d.flat_clr = (uint32_t)s[1] | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 16);
+            d.renew = !(c->dec_last_was_flat && !memcmp(c->dec_last_flat_clr, s + 1, 3));
+            c->dec_last_was_flat = true;
+            memcpy(c->dec_last_flat_clr, s + 1, 3);
+            if (d.renew || chains.empty()) chains.push_back(DecChain{f, 0, d.renew ? -1 : -2});
+        } else {
+            c->dec_last_was_flat = false;
+            d.kind = DK_I;
+            chains.push_back(DecChain{f, 0, -1});
+        }
+        chains.back().count = f - chains.back().first + 1;
+    }
+    if (off >= 0xFFFF0000ull) return SCPR_E_PARAM;
+    const int n_chains = (int)chains.size();
+    TRY(ensure_dec_states(c, n_chains + 1));
+    {
+        int next = 0;
+        for (auto& ch : chains) {
+            if (ch.state == -2)
+                ch.state = c->dec_cur_state;
+            else {
+                if (next == c->dec_cur_state) next++;
+                ch.state = next++;
+            }
+        }
+        // note: states of new chains must differ from the persistent one only while it is in use by chain 0
+        c->dec_cur_state = chains.back().state;
+    }
+    // ---- device buffers ---------------------------------------------------------------------------
+    TRY(c->dec_stream.ensure((size_t)off + 64));
+    TRY(c->dec_desc.ensure((size_t)n * sizeof(DecFrame) + (size_t)n_chains * sizeof(DecChain)));
+    const size_t map_bytes = (size_t)n_chains * g.nb * 4;
+    TRY(c->dec_ws.ensure(3 * map_bytes + (size_t)n * g.nb * 3 + 64));
+    if (c->dec_prev_pitch != pitch) {  // previous frame is kept in output format
+        TRY(c->dec_prev.ensure(g.frame_bytes));
+        if (c->dec_prev_pitch == 0) CK(cudaMemsetAsync(c->dec_prev.p, 0, g.frame_bytes, st));
+        else {
+            set_error("output pitch changed between calls");
+            return SCPR_E_PARAM;
+        }
+        c->dec_prev_pitch = pitch;
+    }
+    CK(cudaMemcpyAsync(c->dec_stream.p, stream, (size_t)off, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync((uint8_t*)c->dec_stream.p + off, 0, 64, st));
+    CK(cudaMemcpyAsync(c->dec_desc.p, frames.data(), (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, st));
+    DecChain* d_chains = reinterpret_cast<DecChain*>((uint8_t*)c->dec_desc.p + (size_t)n * sizeof(DecFrame));
+    CK(cudaMemcpyAsync(d_chains, chains.data(), (size_t)n_chains * sizeof(DecChain), cudaMemcpyHostToDevice, st));
+    DecWork w;
+    memset(&w, 0, sizeof(w));
+    w.g = g;
+    w.stream = (const uint8_t*)c->dec_stream.p;
+    w.frames = (const DecFrame*)c->dec_desc.p;
+    w.chains = d_chains;
+    w.states = (uint8_t*)c->dec_state.p;
+    w.f0 = c->dec_version == 3 ? 64 : 32;  // setCx6f0, screencap.cpp:1613-1614
+    w.out = d_out;
+    w.prev0 = (const uint8_t*)c->dec_prev.p;
+    uint8_t* ws = (uint8_t*)c->dec_ws.p;
+    w.src_cur = (int*)ws;
+    w.src_prev = (int*)(ws + map_bytes);
+    w.stamp = (int*)(ws + 2 * map_bytes);
+    w.upd = ws + 3 * map_bytes;
+    w.fill_src = (int16_t*)(ws + 3 * map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
+    w.n = n;
+    CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
+    const size_t smem = 17 * 17 * 4 + (size_t)g.nb + 16;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_dec_chain<<<n_chains, 32, smem, st>>>(w);
+    k_dec_sources<<<(g.nb + 127) / 128, 128, 0, st>>>(w);
+    const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
+    k_dec_fill<<<(unsigned)((strips + 7) / 8), 256, 0, st>>>(w);
+    c->launches += 3;
+    CK(cudaMemcpyAsync(c->dec_prev.p, d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 1;
+}
+
+extern "C" {
+
+int scpr_decompress_clip_dev(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n,
+                             uint8_t* d_frames, int pitch) {
+    if (!c || !stream || !sizes || !ftypes || !d_frames || n < 0) return SCPR_E_PARAM;
+    return decode_batch(c, stream, sizes, ftypes, n, d_frames, pitch);
+}
+
+int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* frames,
+                         int pitch) {
+    if (!c || !stream || !sizes || !ftypes || !frames || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 1;
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * pitch * c->g.Y;
+    TRY(c->dec_frames.ensure(bytes));
+    // row padding of the caller's buffer is not produced by the kernels: start from zeros
+    if (pitch != c->g.X * c->g.bpp) CK(cudaMemsetAsync(c->dec_frames.p, 0, bytes, c->st));
+    const int r = decode_batch(c, stream, sizes, ftypes, n, (uint8_t*)c->dec_frames.p, pitch);
+    if (r != 1) return r;
+    CK(cudaMemcpyAsync(frames, c->dec_frames.p, bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 1;
+}
+
+int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_t* dst, int pitch, int ftype) {
+    if (!c || !src || !dst || src_len <= 0) return SCPR_E_PARAM;
+    const uint32_t size = (uint32_t)src_len;
+    const uint8_t ft = ftype ? 1 : 0;
+    return scpr_decompress_clip(c, src, &size, &ft, 1, dst, pitch);
+}
+
+}  // extern "C"

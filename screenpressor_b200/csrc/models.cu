@@ -1,0 +1,301 @@
+// models.cu -- stage B: replay of the adaptive models over a GOP's events, parallel across contexts.
+//
+// Replaces the serial main-thread walk ec.encodeX(...) -> model.encode() of the reference
+// (screencap.h:311-317, 339-344; ans_contexts.cpp:34-50; ans_contexts.h:1063-1091).  Which context a
+// symbol is coded in never depends on model state, so the events of a chain (one
+// GOP = everything between two RenewI) are stably partitioned by context id and each context's
+// subsequence is replayed on its own:
+//   * the 21 fixed tables: one warp per table, epoch-wise -- the interval table is frozen between
+//     rescales and the rescale instant depends only on the event count, so an epoch is parallel
+//     table look-ups + a shared-memory histogram + one table rebuild (warp scan);
+//   * the 12288 colour contexts: one thread per context walking the Cx1..Cx7 state machine.
+// Intervals are scattered back to bitstream order for the rANS stage.
+#include "kernels.cuh"
+#include "models.cuh"
+
+namespace scpr {
+
+constexpr int SORT_CHUNK = 8192;
+
+size_t model_state_bytes() { return sizeof(ModelState); }
+size_t replay_hist_entries(uint32_t n_ev) { return (size_t)((n_ev + SORT_CHUNK - 1) / SORT_CHUNK) * NUM_CX; }
+
+// ---- stable partition by context id ----------------------------------------------------------------
+// per chain: chunks of SORT_CHUNK events; hist[chunk][ctx] (u32) -> exclusive prefix over chunks;
+// seg_off[ctx] = exclusive prefix over contexts; rank inside a chunk by in-order warp match.
+struct SortChunkDesc {
+    uint32_t ev_begin, len;   // batch-wide event range
+    uint32_t hist_off;        // row offset (in u32 entries) of this chunk's histogram
+    uint32_t chain;
+};
+
+__global__ void __launch_bounds__(256) k_sort_hist(const uint32_t* __restrict__ events, const SortChunkDesc* __restrict__ chunks,
+                                                   uint32_t* __restrict__ hist) {
+    // two 16-bit counters per word (a chunk holds <= 8192 events, so a half never carries over)
+    __shared__ uint32_t s_h[NUM_CX / 2];
+    const SortChunkDesc cd = chunks[blockIdx.x];
+    for (int i = threadIdx.x; i < NUM_CX / 2; i += 256) s_h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cd.len; i += 256) {
+        const uint32_t ctx = events[cd.ev_begin + i] >> 16;
+        atomicAdd(&s_h[ctx >> 1], 1u << (16 * (ctx & 1)));
+    }
+    __syncthreads();
+    uint32_t* row = hist + cd.hist_off;
+    for (int i = threadIdx.x; i < NUM_CX; i += 256) row[i] = (s_h[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+}
+
+// column scan: thread per (context, chain).  hist rows of a chain are contiguous.
+__global__ void k_sort_scan_cols(uint32_t* __restrict__ hist, const ChainDesc* __restrict__ chains,
+                                 const uint32_t* __restrict__ chain_hist_off, uint32_t* __restrict__ totals) {
+    const int ctx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (ctx >= NUM_CX) return;
+    const uint32_t nchunks = (chains[ch].n_ev + SORT_CHUNK - 1) / SORT_CHUNK;
+    uint32_t* col = hist + chain_hist_off[ch] + ctx;
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t v = col[(size_t)k * NUM_CX];
+        col[(size_t)k * NUM_CX] = run;
+        run += v;
+    }
+    totals[(size_t)ch * (NUM_CX + 1) + ctx] = run;
+}
+
+// exclusive scan over contexts -> seg_off[chain][0..NUM_CX]; one CTA per chain
+__global__ void __launch_bounds__(256) k_sort_scan_ctx(uint32_t* __restrict__ seg_off) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    uint32_t* row = seg_off + (size_t)blockIdx.x * (NUM_CX + 1);
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < NUM_CX + 1; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const uint32_t v = i < NUM_CX ? row[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[wi] = inc;
+        __syncthreads();
+        uint32_t off = s_base;
+        for (int j = 0; j < wi; j++) off += s_warp[j];
+        if (i < NUM_CX + 1) row[i] = off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int j = 0; j < 8; j++) t += s_warp[j];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+}
+
+// placement: one warp per chunk, events taken 32 at a time in order; equal contexts inside a
+// warp step are ranked with match_any, across steps with a shared-memory running count.
+__global__ void __launch_bounds__(32) k_sort_place(const uint32_t* __restrict__ events, const SortChunkDesc* __restrict__ chunks,
+                                                   const uint32_t* __restrict__ hist, const uint32_t* __restrict__ seg_off,
+                                                   const ChainDesc* __restrict__ chains, uint32_t* __restrict__ sorted) {
+    extern __shared__ uint16_t s_cnt[];  // NUM_CX
+    const SortChunkDesc cd = chunks[blockIdx.x];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < NUM_CX; i += 32) s_cnt[i] = 0;
+    __syncwarp();
+    const uint32_t* row = hist + cd.hist_off;
+    const uint32_t* seg = seg_off + (size_t)cd.chain * (NUM_CX + 1);
+    uint32_t* out = sorted + chains[cd.chain].ev_off;
+    for (uint32_t i0 = 0; i0 < cd.len; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool ok = i < cd.len;
+        const uint32_t ctx = ok ? events[cd.ev_begin + i] >> 16 : 0xFFFFu;
+        const uint32_t m = __match_any_sync(0xFFFFFFFFu, ctx);
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (ok && lane == leader) {
+            base = s_cnt[ctx];
+            s_cnt[ctx] = (uint16_t)(base + __popc(m));
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (ok) out[seg[ctx] + row[ctx] + base + __popc(m & ((1u << lane) - 1))] = cd.ev_begin + i;
+        __syncwarp();
+    }
+}
+
+// ---- RenewI ------------------------------------------------------------------------------------------
+__global__ void k_renew(ModelState* st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NUM_COLOR_CX) st->color[i].kind = 0;
+    if (i < NUM_FIXED_CX) fixed_renew(st->fx[i], fixed_nsym(CX_NTAB + i));
+}
+
+void launch_renew_state(uint8_t* state, cudaStream_t st, uint64_t* launches) {
+    k_renew<<<(NUM_COLOR_CX + 255) / 256, 256, 0, st>>>(reinterpret_cast<ModelState*>(state));
+    ++*launches;
+}
+
+// ---- fixed tables: one warp per (table, chain), epoch-wise -----------------------------------------------
+__global__ void __launch_bounds__(32) k_replay_fixed(ReplayWork w, const uint32_t* __restrict__ seg_off) {
+    __shared__ uint32_t s_cnt[512];
+    __shared__ uint16_t s_freq[512], s_cum[512];
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x, ch = blockIdx.y;
+    const ChainDesc cd = w.chains[ch];
+    const uint32_t* seg = seg_off + (size_t)ch * (NUM_CX + 1);
+    const uint32_t pos0 = cd.ev_off + seg[CX_NTAB + t];
+    uint32_t m = seg[CX_NTAB + t + 1] - seg[CX_NTAB + t];
+    if (m == 0 && !cd.renew) return;
+    FixedState& fs = reinterpret_cast<ModelState*>(w.states + (size_t)cd.state * sizeof(ModelState))->fx[t];
+    const int nsym = fixed_nsym(CX_NTAB + t);
+    int cntsum;
+    if (cd.renew) {  // FixedSizeRansCtx::renew, ans_contexts.h:1114-1131
+        const int fr = PROB_SCALE / nsym, c0 = fr - (fr >> 1);
+        for (int i = lane; i < nsym; i += 32) {
+            s_cnt[i] = c0;
+            s_freq[i] = (uint16_t)fr;
+            s_cum[i] = (uint16_t)(fr * i);
+        }
+        cntsum = c0 * nsym;
+    } else {
+        for (int i = lane; i < nsym; i += 32) {
+            s_cnt[i] = fs.cnt[i];
+            s_freq[i] = fs.freq[i];
+            s_cum[i] = fs.cum[i];
+        }
+        cntsum = fs.cntsum;
+    }
+    __syncwarp();
+    const int per = (nsym + 31) / 32;  // table entries per lane at a rebuild
+    uint32_t pos = pos0;
+    while (m > 0) {
+        // events until the rescale fires: cntsum + 16k + 16 > 4096 (ans_contexts.h:1074-1075)
+        const uint32_t epoch = (uint32_t)((PROB_SCALE - 16 - cntsum) / 16 + 1);
+        const uint32_t L = min(m, epoch);
+        for (uint32_t i = lane; i < L; i += 32) {
+            const uint32_t idx = w.sorted[pos + i];
+            const uint32_t sym = w.events[idx] & 0xFFFFu;
+            w.intervals[idx] = make_iv(s_freq[sym], s_cum[sym]);
+            atomicAdd(&s_cnt[sym], 16u);
+        }
+        __syncwarp();
+        cntsum += 16 * (int)L;
+        pos += L;
+        m -= L;
+        if (cntsum + 16 > PROB_SCALE) {  // rebuild: freq = cnt, cum = prefix, cnt -= freq >> 1
+            uint32_t sum = 0;
+            const int b = lane * per;
+            for (int j = 0; j < per; j++)
+                if (b + j < nsym) sum += s_cnt[b + j];
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            uint32_t cf = inc - sum, ns = 0;
+            for (int j = 0; j < per; j++)
+                if (b + j < nsym) {
+                    const uint32_t fr = s_cnt[b + j];
+                    s_cum[b + j] = (uint16_t)cf;
+                    s_freq[b + j] = (uint16_t)fr;
+                    cf += fr;
+                    const uint32_t nc = fr - (fr >> 1);
+                    s_cnt[b + j] = nc;
+                    ns += nc;
+                }
+            cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < nsym; i += 32) {
+        fs.cnt[i] = (uint16_t)s_cnt[i];
+        fs.freq[i] = s_freq[i];
+        fs.cum[i] = s_cum[i];
+    }
+    if (lane == 0) {
+        fs.cntsum = cntsum;
+        fs.nsym = nsym;
+    }
+}
+
+// ---- colour contexts: one thread per (context, chain) ---------------------------------------------------
+__global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32_t* __restrict__ seg_off) {
+    const int ctx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (ctx >= NUM_COLOR_CX) return;
+    const ChainDesc cd = w.chains[ch];
+    const uint32_t* seg = seg_off + (size_t)ch * (NUM_CX + 1);
+    const uint32_t m = seg[ctx + 1] - seg[ctx];
+    ColorState& x = reinterpret_cast<ModelState*>(w.states + (size_t)cd.state * sizeof(ModelState))->color[ctx];
+    if (cd.renew) x.kind = 0;  // Context::renew, ans_contexts.h:1050
+    const uint32_t pos = cd.ev_off + seg[ctx];
+    for (uint32_t i = 0; i < m; i++) {
+        const uint32_t idx = w.sorted[pos + i];
+        const int c = (int)(w.events[idx] & 0xFFu);
+        uint32_t iv;
+        if (x.kind < 4) {  // no statistics yet: the byte goes out raw (screencap.h:313-315)
+            cc_update_raw(x, c, w.f0);
+            iv = make_iv(0, (uint32_t)c);
+        } else
+            iv = cc_encode_counted(x, c);
+        w.intervals[idx] = iv;
+    }
+}
+
+// host-side driver -------------------------------------------------------------------------------------
+void launch_replay(const ReplayWork& w, cudaStream_t st, uint64_t* launches) {
+    if (w.n_chains == 0) return;
+    // chunk descriptors live at the front of chunk_base (host-built, already uploaded by the caller):
+    //   chunk_base layout: [n_chunks_total SortChunkDesc][n_chains u32 chain_hist_off]
+    uint32_t n_chunks = 0;
+    for (int c = 0; c < w.n_chains; c++) n_chunks += (w.h_chains[c].n_ev + SORT_CHUNK - 1) / SORT_CHUNK;
+    const SortChunkDesc* chunks = reinterpret_cast<const SortChunkDesc*>(w.chunk_base);
+    const uint32_t* chain_hist_off = w.chunk_base + (size_t)n_chunks * (sizeof(SortChunkDesc) / 4);
+    uint32_t* hist = w.chunk_hist;
+    if (n_chunks) {
+        k_sort_hist<<<n_chunks, 256, 0, st>>>(w.events, chunks, hist);
+        ++*launches;
+    }
+    dim3 g1((NUM_CX + 255) / 256, w.n_chains);
+    k_sort_scan_cols<<<g1, 256, 0, st>>>(hist, w.chains, chain_hist_off, w.seg_off);
+    k_sort_scan_ctx<<<w.n_chains, 256, 0, st>>>(w.seg_off);
+    *launches += 2;
+    if (n_chunks) {
+        k_sort_place<<<n_chunks, 32, NUM_CX * sizeof(uint16_t), st>>>(w.events, chunks, hist, w.seg_off, w.chains, w.sorted);
+        ++*launches;
+    }
+    k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, st>>>(w, w.seg_off);
+    k_replay_color<<<dim3(NUM_COLOR_CX / 128, w.n_chains), 128, 0, st>>>(w, w.seg_off);
+    *launches += 2;
+}
+
+size_t sort_chunk_words(const ChainDesc* chains, int n_chains) {
+    size_t n_chunks = 0;
+    for (int c = 0; c < n_chains; c++) n_chunks += (chains[c].n_ev + SORT_CHUNK - 1) / SORT_CHUNK;
+    return n_chunks * (sizeof(SortChunkDesc) / 4) + (size_t)n_chains;
+}
+
+// Builds the host image of chunk_base for launch_replay.  Returns the number of u32 words written.
+size_t build_sort_chunks(const ChainDesc* chains, int n_chains, uint32_t* out) {
+    size_t n_chunks = 0;
+    for (int c = 0; c < n_chains; c++) n_chunks += (chains[c].n_ev + SORT_CHUNK - 1) / SORT_CHUNK;
+    SortChunkDesc* cd = reinterpret_cast<SortChunkDesc*>(out);
+    uint32_t* hist_off = out + n_chunks * (sizeof(SortChunkDesc) / 4);
+    size_t k = 0, row = 0;
+    for (int c = 0; c < n_chains; c++) {
+        hist_off[c] = (uint32_t)(row * NUM_CX);
+        for (uint32_t b = 0; b < chains[c].n_ev; b += SORT_CHUNK) {
+            cd[k].ev_begin = chains[c].ev_off + b;
+            cd[k].len = chains[c].n_ev - b < (uint32_t)SORT_CHUNK ? chains[c].n_ev - b : (uint32_t)SORT_CHUNK;
+            cd[k].hist_off = (uint32_t)(row * NUM_CX);
+            cd[k].chain = (uint32_t)c;
+            k++;
+            row++;
+        }
+    }
+    return n_chunks * (sizeof(SortChunkDesc) / 4) + (size_t)n_chains;
+}
+
+}  // namespace scpr

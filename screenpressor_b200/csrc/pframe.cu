@@ -1,0 +1,535 @@
+// pframe.cu -- stage A for P frames: motion search, in-order MV resolve, pixel typing + run-length
+// coding of the changed sub-rects, and event emission.
+//
+// Replaces (reference, 1-thread canonical order):
+//   FindMV / SameBlocks            screencap.cpp:684-825
+//   DecideBlockTypes (typing part) screencap.cpp:1041-1069
+//   GetPixelTypeP/P0, PixelTypeFitsP/P0  screencap.cpp:525-556, 578-604
+//   CompressP's serialisation      screencap.cpp:1144-1248, WritePixel :609-627
+//
+// The reference's motion search is serial through `last_mv` and the persistent mvs[] array
+// (SURVEY.md A.3).  Here F(b) = "first hit of the fixed candidate order" is computed for every
+// changed block of every frame in parallel (k_mv_search, 32 candidates per warp step, first hit by
+// ballot), and only the two state-dependent shortcut candidates are evaluated in frame/raster order
+// (k_mv_resolve); a shortcut whose vector equals F(b) needs no compare at all.
+#include "kernels.cuh"
+
+namespace scpr {
+
+struct SubRect {
+    int bx, by, x1, y1, x2, y2, w, h;
+    bool partial;
+};
+
+__device__ __forceinline__ SubRect subrect_of(uint32_t bi, uint32_t info, const Geo& g) {
+    SubRect r;
+    r.by = (int)bi / g.nbx;
+    r.bx = (int)bi - r.by * g.nbx;
+    r.x1 = r.bx * 16 + (int)((info >> 4) & 15);
+    r.y1 = r.by * 16 + (int)((info >> 8) & 15);
+    r.x2 = r.bx * 16 + (int)((info >> 12) & 15) + 1;
+    r.y2 = r.by * 16 + (int)((info >> 16) & 15) + 1;
+    r.w = r.x2 - r.x1;
+    r.h = r.y2 - r.y1;
+    r.partial = (info & BI_PARTIAL) != 0;
+    return r;
+}
+
+// search windows of FindMV (screencap.cpp:691-709)
+struct Windows {
+    int fx1, fx2, fy1, fy2, rx1, rx2, ry1, ry2;
+};
+__device__ __forceinline__ Windows windows_of(const SubRect& r, const Geo& g) {
+    Windows w;
+    w.rx1 = max(0, r.x1 - 8);
+    w.ry1 = max(0, r.y1 - 8);
+    w.rx2 = r.x1 + 8;
+    w.ry2 = r.y1 + 8;
+    if (w.rx2 + r.w > g.X) w.rx2 = g.X - r.w + 1;
+    if (w.ry2 + r.h > g.Y) w.ry2 = g.Y - r.h + 1;
+    w.fx1 = max(0, r.x1 - 256);
+    w.fy1 = max(0, r.y1 - 256);
+    w.fx2 = r.x1 + 256;
+    w.fy2 = r.y1 + 256;
+    if (w.fx2 + r.w > g.X) w.fx2 = g.X - r.w + 1;
+    if (w.fy2 + r.h > g.Y) w.fy2 = g.Y - r.h + 1;
+    return w;
+}
+
+__device__ __forceinline__ int find_pframe(const PFrameHdr* hdr, const int* pframes, int n_pframes, int slot) {
+    int lo = 0, hi = n_pframes - 1;
+    while (lo < hi) {  // largest i with chg_off <= slot
+        const int mid = (lo + hi + 1) >> 1;
+        if (hdr[pframes[mid]].chg_off <= slot) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mv_search: F(b) for every changed block.  One warp per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mv_search(PWork w) {
+    __shared__ uint32_t s_cur[4][256];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int slot = blockIdx.x * 4 + wi;
+    if (slot >= w.total_blocks) return;
+    const int pi = find_pframe(w.hdr, w.pframes, w.n_pframes, slot);
+    const int f = w.pframes[pi];
+    const int k = slot - w.hdr[f].chg_off;
+    const Geo& g = w.g;
+    const uint32_t bi = w.chg_list[(size_t)f * g.nb + k];
+    const uint32_t info = w.blkinfo[(size_t)f * g.nb + bi];
+    const SubRect r = subrect_of(bi, info, g);
+    const Windows win = windows_of(r, g);
+    const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+    const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
+
+    const int npx = r.w * r.h;
+    for (int p = lane; p < npx; p += 32) s_cur[wi][p] = load_px(cur, g, r.x1 + p % r.w, r.y1 + p / r.w);
+    __syncwarp();
+
+    // candidate segments in the reference's order (screencap.cpp:737-811)
+    const int common = min(r.y1 - win.fy1, win.fy2 - r.y1 - 1);
+    const int nA = 2 * common;
+    const int nB = max(0, (r.y1 - 1 - common) - win.fy1 + 1);
+    const int nC = max(0, win.fy2 - (r.y1 + 1 + common));
+    const int nD = r.x1 - win.fx1 + 1;
+    const int nE = win.fx2 - r.x1;
+    const int nyu = r.y1 - win.ry1 + 1, nyd = win.ry2 - r.y1 - 1, ny = nyu + nyd;
+    const int nxl = r.x1 - win.rx1 + 1, nxr = max(0, win.rx2 - r.x1 - 1);
+    const int total = nA + nB + nC + nD + nE + (nxl + nxr) * ny;
+
+    int hit = -1, hx = 0, hy = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        int t = t0 + lane;
+        bool ok = t < total;
+        int cx = r.x1, cy = r.y1;
+        if (ok) {
+            if (t < nA) {
+                const int j = t >> 1;
+                cy = (t & 1) ? r.y1 + 1 + j : r.y1 - 1 - j;
+            } else if ((t -= nA) < nB) {
+                cy = r.y1 - 1 - common - t;
+            } else if ((t -= nB) < nC) {
+                cy = r.y1 + 1 + common + t;
+            } else if ((t -= nC) < nD) {
+                cx = r.x1 - t;
+            } else if ((t -= nD) < nE) {
+                cx = r.x1 + t;
+            } else {
+                t -= nE;
+                const int xi = t / ny, yi = t - xi * ny;
+                cx = xi < nxl ? r.x1 - xi : r.x1 + 1 + (xi - nxl);
+                cy = yi < nyu ? r.y1 - yi : r.y1 + 1 + (yi - nyu);
+            }
+            // SameBlocks (screencap.cpp:817-825), early exit on the first differing pixel
+            for (int yy = 0; yy < r.h && ok; yy++)
+                for (int xx = 0; xx < r.w; xx++)
+                    if (load_px(prv, g, cx + xx, cy + yy) != s_cur[wi][yy * r.w + xx]) {
+                        ok = false;
+                        break;
+                    }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) {
+            const int src = __ffs(m) - 1;
+            hit = t0 + src;
+            hx = __shfl_sync(0xFFFFFFFFu, cx, src);
+            hy = __shfl_sync(0xFFFFFFFFu, cy, src);
+            break;
+        }
+    }
+    if (lane == 0) {
+        ChgBlock& b = w.blocks[slot];
+        b.bi = bi;
+        b.info = info;
+        b.has_f = hit >= 0;
+        b.fmx = (int16_t)(hx - r.x1);
+        b.fmy = (int16_t)(hy - r.y1);
+    }
+}
+
+// warp-cooperative SameBlocks: sub-rect of cur at (x1,y1) vs prev at (x1+mx, y1+my)
+__device__ __forceinline__ bool warp_match(const uint8_t* cur, const uint8_t* prv, const Geo& g, const SubRect& r, int mx,
+                                           int my, int lane) {
+    bool same = true;
+    const int npx = r.w * r.h;
+    for (int p = lane; p < npx; p += 32) {
+        const int xx = p % r.w, yy = p / r.w;
+        if (load_px(cur, g, r.x1 + xx, r.y1 + yy) != load_px(prv, g, r.x1 + mx + xx, r.y1 + my + yy)) same = false;
+    }
+    return __all_sync(0xFFFFFFFFu, same);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mv_resolve: the serial part of FindMV, one warp walking P frames and their changed blocks in
+// order.  Candidate 1 = last_mv, candidate 2 = persistent MV of the block above
+// (screencap.cpp:715-735); search hits (= F) update last_mv, shortcut hits do not.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
+    const int lane = threadIdx.x;
+    const Geo& g = w.g;
+    for (int pi = 0; pi < w.n_pframes; pi++) {
+        const int f = w.pframes[pi];
+        const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
+        const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+        const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
+        int lmx = 0, lmy = 0;      // last_mv
+        int cmx = 0, cmy = 0;      // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
+        int prev_nonmv = -1;
+        for (int k = 0; k < nchg; k++) {
+            ChgBlock& b = w.blocks[off + k];
+            const uint32_t bi = b.bi;
+            const SubRect r = subrect_of(bi, b.info, g);
+            const Windows win = windows_of(r, g);
+            const bool has_f = b.has_f;
+            const int fmx = b.fmx, fmy = b.fmy;
+            bool found = false;
+            int mx = 0, my = 0;
+            {   // candidate 1: last_mv
+                const int sx = r.x1 + lmx, sy = r.y1 + lmy;
+                if (sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2) {
+                    if ((has_f && fmx == lmx && fmy == lmy) || warp_match(cur, prv, g, r, lmx, lmy, lane)) {
+                        found = true; mx = lmx; my = lmy;
+                    }
+                }
+            }
+            if (!found && r.by > 0) {  // candidate 2: MV stored for the block above, if it differs
+                const int2 u = w.mvs[bi - g.nbx];
+                if (u.x != lmx || u.y != lmy) {
+                    const int sx = r.x1 + u.x, sy = r.y1 + u.y;
+                    if (sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2) {
+                        if ((has_f && fmx == u.x && fmy == u.y) || warp_match(cur, prv, g, r, u.x, u.y, lane)) {
+                            found = true; mx = u.x; my = u.y;
+                        }
+                    }
+                }
+            }
+            if (!found && has_f) {  // the fixed-order search: first hit wins and becomes last_mv
+                found = true; mx = fmx; my = fmy;
+                lmx = mx; lmy = my;
+            }
+            if (lane == 0) {
+                uint8_t bt = r.partial ? 2 : 1;
+                if (found) {
+                    bt += 2;
+                    w.mvs[bi] = make_int2(mx, my);
+                    const bool rep = bi > 0 && mx == cmx && my == cmy;  // screencap.cpp:1202
+                    b.rep = rep;
+                    b.mx = (int16_t)mx; b.my = (int16_t)my;
+                    b.prev_nonmv = -1;
+                } else {
+                    b.rep = 0;
+                    b.prev_nonmv = prev_nonmv;
+                }
+                b.bt = bt;
+            }
+            if (found) {
+                if (!(bi > 0 && mx == cmx && my == cmy)) { cmx = mx; cmy = my; }
+            } else
+                prev_nonmv = k;
+            __syncwarp();
+        }
+        __threadfence();  // mvs[] of this frame visible before the next frame reads it
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_p_runs: pixel typing + run segmentation of pixel-coded blocks; per-block event counts.
+// One warp per changed block.  runs[slot*256 + r] = (ptype << 8) | n.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grad_ok(uint32_t p, uint32_t l, uint32_t t, uint32_t tl) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int sh = 8 * c;
+        const int v = (int)((l >> sh) & 255) + (int)((t >> sh) & 255) - (int)((tl >> sh) & 255);
+        ok = ok && ((int)((p >> sh) & 255) == v);
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(128) k_p_runs(PWork w) {
+    __shared__ uint16_t s_px[4][256];  // per pixel: best type (bits 0-2) | fit mask for types 0..5 (bits 4-9)
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int slot = blockIdx.x * 4 + wi;
+    if (slot >= w.total_blocks) return;
+    ChgBlock& b = w.blocks[slot];
+    const Geo& g = w.g;
+    const SubRect r = subrect_of(b.bi, b.info, g);
+    const uint32_t sxy_ev = r.partial ? 4u : 0u;
+    if (b.bt >= 3) {  // MV block: [SXY x4] BOOL [MX MY]
+        if (lane == 0) {
+            b.n_runs = 0;
+            b.n_ev = sxy_ev + (b.rep ? 1u : 3u);
+        }
+        return;
+    }
+    const int pi = find_pframe(w.hdr, w.pframes, w.n_pframes, slot);
+    const int f = w.pframes[pi];
+    const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+    const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
+    const int npx = r.w * r.h;
+    for (int p = lane; p < npx; p += 32) {
+        const int xx = p % r.w, yy = p / r.w, x = r.x1 + xx, y = r.y1 + yy;
+        const uint32_t c = load_px(cur, g, x, y);
+        const uint32_t pr = load_px(prv, g, x, y);
+        // previous pixel in the sub-rect's raster order (lasti, screencap.cpp:1045-1061)
+        uint32_t last = 0;
+        if (p > 0) {
+            const int q = p - 1;
+            last = load_px(cur, g, r.x1 + q % r.w, r.y1 + q / r.w);
+        }
+        uint32_t fit = (p > 0 && c == last) ? 1u : 0u;  // type 0 continues on "equals last pixel"
+        int best;
+        if (x > 0 && y > 0) {
+            const uint32_t l = load_px(cur, g, x - 1, y), t = load_px(cur, g, x, y - 1), tl = load_px(cur, g, x - 1, y - 1);
+            const bool e1 = c == l, e3 = c == pr, e5 = c == tl, e2 = c == t, e4 = grad_ok(c, l, t, tl);
+            fit |= (e1 ? 2u : 0u) | (e2 ? 4u : 0u) | (e3 ? 8u : 0u) | (e4 ? 16u : 0u) | (e5 ? 32u : 0u);
+            best = e1 ? 1 : e3 ? 3 : e5 ? 5 : e2 ? 2 : e4 ? 4 : 0;  // GetPixelTypeP priority
+        } else {
+            const bool e3 = c == pr;
+            fit |= e3 ? 8u : 0u;
+            best = e3 ? 3 : 0;  // GetPixelTypeP0
+        }
+        s_px[wi][p] = (uint16_t)(best | (fit << 4));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint16_t* runs = w.runs + (size_t)slot * 256;
+        int nr = 0, type = s_px[wi][0] & 7, n = 1;
+        uint32_t nev = sxy_ev;
+        for (int p = 1; p < npx; p++) {
+            const uint32_t v = s_px[wi][p];
+            if (n < 255 && ((v >> (4 + type)) & 1))
+                n++;
+            else {
+                runs[nr++] = (uint16_t)((type << 8) | n);
+                nev += type ? 2u : 5u;
+                type = v & 7;
+                n = 1;
+            }
+        }
+        runs[nr++] = (uint16_t)((type << 8) | n);
+        nev += type ? 2u : 5u;
+        b.n_runs = nr;
+        b.n_ev = nev;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_p_count: per P frame -- block-type RLE (screencap.cpp:1155-1169) into scratch, exclusive scan
+// of the per-block event counts, frame totals.  One CTA per P frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_p_count(PWork w) {
+    const int f = w.pframes[blockIdx.x];
+    const Geo& g = w.g;
+    PFrameHdr& h = w.hdr[f];
+    ChgBlock* blocks = w.blocks + h.chg_off;
+    const int nchg = h.n_changed;
+    __shared__ uint32_t s_hdr_ev;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    // dense block types of the coded range [xx1, xx2] live in the upper half of the scratch
+    uint32_t* rle = w.bts_rle + (size_t)blockIdx.x * 2 * g.nb;
+    uint8_t* dense = reinterpret_cast<uint8_t*>(rle + g.nb);
+    for (int i = threadIdx.x; i < g.nb; i += 256) dense[i] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nchg; k += 256) dense[blocks[k].bi] = blocks[k].bt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int oldt = -1, n = -1, np = 0;
+        for (int x = h.xx1; x <= h.xx2; x++) {
+            const int t = dense[x];
+            if (t == oldt && n < 255)
+                n++;
+            else {
+                if (n > 0) rle[np++] = ((uint32_t)oldt << 8) | (uint32_t)n;
+                oldt = t;
+                n = 1;
+            }
+        }
+        rle[np++] = ((uint32_t)oldt << 8) | (uint32_t)n;
+        s_hdr_ev = 4u + 2u * (uint32_t)np;
+        s_base = 4u + 2u * (uint32_t)np;
+        h.n_hdr_ev = s_hdr_ev;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < nchg; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        const uint32_t v = k < nchg ? blocks[k].n_ev : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[wi] = inc;
+        __syncthreads();
+        uint32_t woff = s_base;
+        for (int j = 0; j < wi; j++) woff += s_warp[j];
+        if (k < nchg) blocks[k].ev_off = woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int j = 0; j < 8; j++) t += s_warp[j];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) h.n_ev = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_p_emit_hdr: XX bytes + (BT, BN) pairs.  One CTA per P frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_p_emit_hdr(PWork w) {
+    const int f = w.pframes[blockIdx.x];
+    const Geo& g = w.g;
+    const PFrameHdr& h = w.hdr[f];
+    uint32_t* ev = w.events + w.frame_ev_off[f];
+    const uint32_t* rle = w.bts_rle + (size_t)blockIdx.x * 2 * g.nb;
+    if (threadIdx.x == 0) {
+        ev[0] = make_ev(CX_XX, h.xx1 & 255);
+        ev[1] = make_ev(CX_XX, (h.xx1 >> 8) & 255);
+        ev[2] = make_ev(CX_XX, h.xx2 & 255);
+        ev[3] = make_ev(CX_XX, (h.xx2 >> 8) & 255);
+    }
+    const int np = (int)(h.n_hdr_ev - 4) / 2;
+    for (int i = threadIdx.x; i < np; i += 256) {
+        ev[4 + 2 * i] = make_ev(CX_BT, rle[i] >> 8);
+        ev[5 + 2 * i] = make_ev(CX_NTAB2, rle[i] & 255);
+    }
+}
+
+// colour context ids of a literal pixel `c` that follows pixel `last` (WritePixel / MAKECX1,
+// screencap.cpp:609-627, screencap.h:36); has_last == false -> cx = cx1 = 0 (frame start)
+__device__ __forceinline__ void emit_literal(uint32_t* ev, uint32_t c, uint32_t last, bool has_last) {
+    const uint32_t r = c & 255, gg = (c >> 8) & 255, bb = (c >> 16) & 255;
+    const uint32_t lg = has_last ? ((last >> 8) & 255) >> 2 : 0, lb = has_last ? ((last >> 16) & 255) >> 2 : 0;
+    ev[0] = make_ev(CX_COLOR + 0 * 4096 + (int)(lb + (lg << 6)), r);
+    ev[1] = make_ev(CX_COLOR + 1 * 4096 + (int)((r >> 2) + (lb << 6)), gg);
+    ev[2] = make_ev(CX_COLOR + 2 * 4096 + (int)((gg >> 2) + ((r >> 2) << 6)), bb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_p_emit: events of every changed block.  One warp per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_p_emit(PWork w) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int slot = blockIdx.x * 4 + wi;
+    if (slot >= w.total_blocks) return;
+    const ChgBlock& b = w.blocks[slot];
+    const Geo& g = w.g;
+    const int pi = find_pframe(w.hdr, w.pframes, w.n_pframes, slot);
+    const int f = w.pframes[pi];
+    const SubRect r = subrect_of(b.bi, b.info, g);
+    uint32_t* ev = w.events + w.frame_ev_off[f] + b.ev_off;
+    if (r.partial) {
+        if (lane == 0) {
+            ev[0] = make_ev(CX_SXY + 0, r.x1 - r.bx * 16);
+            ev[1] = make_ev(CX_SXY + 1, r.y1 - r.by * 16);
+            ev[2] = make_ev(CX_SXY + 2, r.x2 - 1 - r.bx * 16);
+            ev[3] = make_ev(CX_SXY + 3, r.y2 - 1 - r.by * 16);
+        }
+        ev += 4;
+    }
+    if (b.bt >= 3) {
+        if (lane == 0) {
+            uint32_t* iv = w.intervals + (ev - w.events);
+            ev[0] = make_ev(CX_BOOL, b.rep);
+            iv[0] = make_iv(PROB_SCALE / 2, b.rep ? PROB_SCALE / 2 : 0);  // encodeBool, screencap.h:407-410
+            if (!b.rep) {
+                ev[1] = make_ev(CX_MV + 0, b.mx + 256);
+                ev[2] = make_ev(CX_MV + 1, b.my + 256);
+            }
+        }
+        return;
+    }
+    const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+    const uint16_t* runs = w.runs + (size_t)slot * 256;
+    const int nr = (int)b.n_runs;
+    // context pixel for the first run: bottom-right pixel of the previous pixel-coded block
+    uint32_t first_last = 0;
+    bool first_has = false;
+    if (b.prev_nonmv >= 0) {
+        const ChgBlock& pb = w.blocks[w.hdr[f].chg_off + b.prev_nonmv];
+        const SubRect pr = subrect_of(pb.bi, pb.info, g);
+        first_last = load_px(cur, g, pr.x2 - 1, pr.y2 - 1);
+        first_has = true;
+    }
+    // each lane owns 8 consecutive runs; prefix sums of pixel counts and event counts
+    uint32_t rv[8];
+    uint32_t npx = 0, nev = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int ri = lane * 8 + j;
+        rv[j] = ri < nr ? runs[ri] : 0u;
+        if (ri < nr) {
+            npx += rv[j] & 255;
+            nev += (rv[j] >> 8) ? 2u : 5u;
+        }
+    }
+    uint32_t ipx = npx, iev = nev;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, ipx, d), c = __shfl_up_sync(0xFFFFFFFFu, iev, d);
+        if (lane >= d) { ipx += a; iev += c; }
+    }
+    uint32_t px = ipx - npx, eo = iev - nev;
+    // type of the run just before this lane's first run
+    uint32_t prev_type = __shfl_up_sync(0xFFFFFFFFu, rv[7] >> 8, 1);
+    if (lane == 0) prev_type = 0;  // lastptype restarts at 0 per block (screencap.cpp:1218)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int ri = lane * 8 + j;
+        if (ri < nr) {
+            const uint32_t type = rv[j] >> 8, n = rv[j] & 255;
+            uint32_t* e = ev + eo;
+            *e++ = make_ev(CX_PTYPE + (int)prev_type, type);
+            if (type == 0) {
+                const uint32_t c = load_px(cur, g, r.x1 + (int)(px % r.w), r.y1 + (int)(px / r.w));
+                uint32_t last = first_last;
+                bool has = first_has;
+                if (px > 0) {
+                    const uint32_t q = px - 1;
+                    last = load_px(cur, g, r.x1 + (int)(q % r.w), r.y1 + (int)(q / r.w));
+                    has = true;
+                }
+                emit_literal(e, c, last, has);
+                e += 3;
+            }
+            *e = make_ev(CX_NTAB + (int)type, n);
+            eo += type ? 2u : 5u;
+            px += n;
+            prev_type = type;
+        }
+    }
+}
+
+void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
+    if (w.total_blocks > 0) {
+        k_mv_search<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        k_mv_resolve<<<1, 32, 0, st>>>(w);
+        k_p_runs<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        *launches += 3;
+    }
+    if (w.n_pframes > 0) {
+        k_p_count<<<w.n_pframes, 256, 0, st>>>(w);
+        ++*launches;
+    }
+}
+
+void launch_p_emit(const PWork& w, cudaStream_t st, uint64_t* launches) {
+    if (w.n_pframes > 0) {
+        k_p_emit_hdr<<<w.n_pframes, 256, 0, st>>>(w);
+        ++*launches;
+    }
+    if (w.total_blocks > 0) {
+        k_p_emit<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        ++*launches;
+    }
+}
+
+}  // namespace scpr
