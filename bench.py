@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: 1080p RGB32 encode+decode frames/s (bit-exact).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference codec core on the host CPU
+
+Workload (config.workload): BASELINE.json configs[1], 1920x1080 RGB32 synthetic desktop capture,
+600 frames, keyframes at 0 and 500 (the VfW default interval).  One *step* = encoding all 600
+frames and decoding them again.  `value` = frames / second with the input frames already resident
+in HBM when the timed region starts (bitstreams still travel to the host and back, they are tiny);
+`e2e` = the same through the host-buffer API (pinned host frames in, pinned host frames out), which
+is what a drop-in user of the reference's ScreenCodec sees.  Inputs (5 GB per step) exceed the
+126 MB L2, so no explicit L2 flush is needed between steps.
+
+Multi-GPU: clips are independent, so each rank encodes+decodes its own clip (seed + rank); there is
+no data-path collective (weak scaling).  torch.distributed is only used for the timing barrier.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from screenpressor_b200 import synth  # noqa: E402
+
+WORKLOAD = "cfg2_1080p_rgb32"
+METRIC = "1080p_rgb32_encode_decode_frames_per_s"
+
+
+def make_workload(rank: int, frames: int):
+    cfg = synth.CONFIGS[WORKLOAD]
+    if rank:
+        cfg = synth.ClipConfig(cfg.name, cfg.width, cfg.height, cfg.bpp, cfg.frames, cfg.key_interval, cfg.seed + 100 * rank, cfg.kind)
+    clip = synth.make_clip(cfg, frames)
+    keys = synth.keyframe_flags(frames, cfg.key_interval)
+    return cfg, clip, keys
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_reference(clip, keys, cfg, threads: int):
+    """encode+decode `clip` with the compiled reference core (oracle/_ref); returns (seconds enc, seconds dec, kind)."""
+    from oracle import pyref  # the one place bench.py may execute oracle/: the CPU baseline
+
+    kind = "reference" if pyref.have_ref() else "port"
+    Codec = pyref.RefCodec if kind == "reference" else pyref.OracleCodec
+    if kind == "port":
+        pyref.build()
+    enc, dec = Codec(cfg.width, cfg.height, cfg.bpp, threads=threads), Codec(cfg.width, cfg.height, cfg.bpp, threads=1)
+    n = len(clip)
+    flat = clip.reshape(n, -1)
+    te = td = 0.0
+    for i in range(n):
+        fr = flat[i].copy()
+        t0 = time.perf_counter()
+        data, ft = enc.compress(fr, not keys[i])
+        t1 = time.perf_counter()
+        out = dec.decompress(data, ft)
+        t2 = time.perf_counter()
+        te += t1 - t0
+        td += t2 - t1
+        if i % 97 == 0:
+            assert np.array_equal(out, flat[i]), "reference round trip failed"
+    enc.close()
+    dec.close()
+    return te, td, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    sample = min(args.ref_frames, synth.CONFIGS[WORKLOAD].frames)
+    cfg, clip, keys = make_workload(0, sample)
+    nby = (cfg.height + 15) // 16
+    nthr = max(1, min(os.cpu_count() or 1, nby))  # cap: the reference's tls[] overflows past nby threads
+    results = {}
+    for thr in sorted({1, nthr}):
+        for _ in range(args.warmup if thr == 1 else 0):
+            time_reference(clip, keys, cfg, thr)
+        ts = [time_reference(clip, keys, cfg, thr) for _ in range(args.steps)]
+        best = min(t[0] + t[1] for t in ts)
+        results[thr] = {"fps": sample / best, "enc_fps": sample / min(t[0] for t in ts), "dec_fps": sample / min(t[1] for t in ts),
+                        "kind": ts[0][2]}
+    thr_best = max(results, key=lambda k: results[k]["fps"])
+    r = results[thr_best]
+    per_step = sample / r["fps"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 1920x1080 RGB32, keyframe interval 500, first {sample} of 600 frames per step, encode+decode"},
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": thr_best, "kind": r["kind"],
+                         "sample": f"first {sample} frames of the 600-frame clip, encode then decode each frame, best of {args.steps}",
+                         "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
+                         "by_threads": {str(k): v["fps"] for k, v in results.items()}},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from screenpressor_b200.codec import CodecParameters, ScreenCodec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    frames = args.frames
+    cfg, clip, keys = make_workload(rank, frames)
+    W, H = cfg.width, cfg.height
+    fb = W * H * 4
+    # pinned host copies for the end-to-end leg, device-resident copy for `value`
+    h_in = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
+    h_in.numpy()[:] = clip.reshape(-1)
+    h_out = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
+    d_in = h_in.cuda(non_blocking=True)
+    d_out = torch.empty(frames * fb, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    enc, dec = ScreenCodec(local), ScreenCodec(local)
+
+    def fresh():
+        for c in (enc, dec):
+            c.Init(CodecParameters(W, H, 32))
+            c.set_stream(stream.cuda_stream)
+        enc.reserve_clip_output(64 << 20)
+
+    def step_device():
+        fresh()
+        s, sizes, fts = enc.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=frames)
+        dec.DecompressClip(s, sizes, fts, device_ptr=d_out.data_ptr())
+        return s, sizes
+
+    def step_host():
+        fresh()
+        s, sizes, fts = enc.CompressClip(h_in.numpy(), keys)
+        out = dec._lib.scpr_decompress_clip(dec._h, s.ctypes.data, sizes.ctypes.data, fts.ctypes.data, frames, h_out.data_ptr(), W * 4)
+        assert out == 1, out
+        return s, sizes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            res = fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res
+
+    # correctness gate before timing: decode(encode(clip)) must reproduce the clip bit for bit
+    step_device()
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_in), "decode(encode(x)) != x on the device path"
+    for _ in range(max(0, args.warmup - 1)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = enc.kernel_launches() + dec.kernel_launches()
+    # launches are counted per codec object and fresh() re-creates them: accumulate manually
+    launches = 0
+
+    def counted_device():
+        nonlocal launches
+        r = step_device()
+        launches += enc.kernel_launches() + dec.kernel_launches()
+        return r
+
+    ms, (s, sizes) = timed(counted_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * frames * args.steps / (ms / 1e3)
+
+    # end-to-end leg
+    step_host()
+    torch.cuda.synchronize()
+    assert np.array_equal(h_out.numpy(), h_in.numpy()), "decode(encode(x)) != x on the host-buffer path"
+    ms_e2e, (s2, sizes2) = timed(step_host, args.steps)
+    e2e = world * frames * args.steps / (ms_e2e / 1e3)
+    stream_bytes = int(sizes.sum())
+
+    # roofline leg: the frame-scan kernel (stage A pass 1), timed alone with CUDA events on its stream
+    fresh()
+    scan_ms = enc.bench_frame_scan(d_in.data_ptr(), frames, 5)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = frames * W * H * 8  # cur + prev, 4 B/px each
+    achieved = alg_bytes / (scan_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "frame_scan_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_600f")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = min(args.ref_frames, frames)
+        te, td, kind = time_reference(clip[:sample], keys[:sample], cfg, 1)
+        cpu = {"value": sample / (te + td), "unit": "frames/s", "cores": 1, "kind": kind,
+               "sample": f"first {sample} frames of the same clip, encode then decode each frame, 1 thread (canonical bitstream)",
+               "encode_fps": sample / te, "decode_fps": sample / td}
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 1920x1080 RGB32, {frames} frames per clip per GPU, keyframe interval 500, encode+decode, "
+                               "bit-exact round trip asserted", "l2": "inputs (5 GB/step) exceed L2; no flush needed",
+                   "gops_per_clip": int(keys.sum()), "stream_bytes_per_clip": stream_bytes},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
+                "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "k_frame_scan32", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--frames", type=int, default=synth.CONFIGS[WORKLOAD].frames)
+    ap.add_argument("--ref-frames", type=int, default=200, help="bounded sample for the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

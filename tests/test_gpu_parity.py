@@ -1,0 +1,210 @@
+"""GPU: the CUDA path, called through the C ABI, against (a) the golden bitstreams generated from the
+unmodified reference, (b) the plain-C oracle on seeded fuzz clips (bytes, events, intervals, block
+tables), (c) size-independent properties at BASELINE.json's full sizes (encode -> decode round trip)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import _golden
+from _clips import fuzz_clip
+
+pytestmark = pytest.mark.gpu
+
+DIGESTS = _golden.digests()
+
+
+@pytest.fixture(scope="module")
+def scpr():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from screenpressor_b200 import codec
+
+    return codec
+
+
+def _new(scpr, w, h, bpp):
+    sc = scpr.ScreenCodec(0)
+    sc.Init(scpr.CodecParameters(w, h, bpp))
+    return sc
+
+
+def _split(stream, sizes, ftypes):
+    out, pos = [], 0
+    for sz, ft in zip(sizes, ftypes):
+        out.append((bytes(stream[pos:pos + int(sz)]), int(ft)))
+        pos += int(sz)
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS))
+def test_encode_matches_reference_golden_clip_api(scpr, name):
+    """whole clip in one call; bytes must equal the reference's, frame by frame"""
+    entry = DIGESTS[name]
+    clip, keys, w, h, bpp = _golden.load_case(entry)
+    enc = _new(scpr, w, h, bpp)
+    produced = _split(*enc.CompressClip(clip, keys))
+    _golden.check_frames(name, entry["frames"], produced)
+    dec = _new(scpr, w, h, bpp)
+    stream = np.frombuffer(b"".join(p[0] for p in produced), dtype=np.uint8)
+    out = dec.DecompressClip(stream, np.array([len(p[0]) for p in produced], np.uint32), np.array([p[1] for p in produced], np.uint8))
+    assert np.array_equal(out.reshape(len(clip), -1), clip.reshape(len(clip), -1)), f"{name}: decode is not bit-exact"
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(DIGESTS) if n.startswith("fuzz") or n.startswith("cfg1")])
+def test_encode_matches_reference_golden_frame_api(scpr, name):
+    """the drop-in calls: one CompressFrame / DecompressFrame per frame, state carried across calls"""
+    entry = DIGESTS[name]
+    clip, keys, w, h, bpp = _golden.load_case(entry)
+    enc, dec = _new(scpr, w, h, bpp), _new(scpr, w, h, bpp)
+    produced = []
+    for i in range(len(clip)):
+        data, ft = enc.CompressFrame(clip[i], 0 if keys[i] else 1)
+        produced.append((data, ft))
+        out = dec.DecompressFrame(data, None, ft)
+        assert np.array_equal(out, clip[i].reshape(-1)), f"{name} frame {i}: decode is not bit-exact"
+    _golden.check_frames(name, entry["frames"], produced)
+
+
+def test_decodes_reference_streams(scpr):
+    st = _golden.streams()
+    for name in sorted({k.split("/")[0] for k in st.files}):
+        clip, keys, w, h, bpp = _golden.load_case(DIGESTS[name])
+        dec = _new(scpr, w, h, bpp)
+        out = dec.DecompressClip(st[name + "/data"], st[name + "/sizes"].astype(np.uint32), st[name + "/types"])
+        assert np.array_equal(out.reshape(len(clip), -1), clip.reshape(len(clip), -1)), name
+
+
+def test_mixed_batch_sizes_equal_single_calls(scpr):
+    """splitting a clip into arbitrary batches must not change a byte (model / prev / mvs carry-over)"""
+    clip, keys = fuzz_clip(200, 120, 40, 21, 32, 16)
+    a = _new(scpr, 200, 120, 32)
+    whole = _split(*a.CompressClip(clip, keys))
+    b = _new(scpr, 200, 120, 32)
+    parts = []
+    for lo, hi in [(0, 1), (1, 2), (2, 9), (9, 10), (10, 27), (27, 40)]:
+        parts += _split(*b.CompressClip(clip[lo:hi], keys[lo:hi]))
+    assert parts == whole
+    d = _new(scpr, 200, 120, 32)
+    outs = []
+    for lo, hi in [(0, 3), (3, 4), (4, 30), (30, 40)]:
+        p = whole[lo:hi]
+        outs.append(d.DecompressClip(np.frombuffer(b"".join(x[0] for x in p), np.uint8), np.array([len(x[0]) for x in p], np.uint32),
+                                     np.array([x[1] for x in p], np.uint8)))
+    assert np.array_equal(np.concatenate(outs).reshape(clip.shape), clip)
+
+
+@pytest.mark.parametrize("size", [(97, 45), (1001, 37), (33, 17), (16, 16), (255, 31), (18, 2), (3, 40), (5, 5), (4, 3), (130, 130)])
+@pytest.mark.parametrize("bpp", [32, 24])
+def test_fuzz_against_oracle(scpr, oracle_built, size, bpp):
+    """odd widths (row padding), tiny frames, noise levels that drive every model promotion"""
+    w, h = size
+    for levels in (256, 16, 4):
+        clip, keys = fuzz_clip(w, h, 24, w * 5 + levels, bpp, levels)
+        orc = oracle_built.OracleCodec(w, h, bpp)
+        want = [orc.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), not keys[i]) for i in range(len(clip))]
+        enc = _new(scpr, w, h, bpp)
+        got = _split(*enc.CompressClip(clip, keys))
+        assert got == want, (size, bpp, levels, [i for i in range(len(got)) if got[i] != want[i]][:5])
+        dec = _new(scpr, w, h, bpp)
+        out = dec.DecompressClip(np.frombuffer(b"".join(x[0] for x in want), np.uint8), np.array([len(x[0]) for x in want], np.uint32),
+                                 np.array([x[1] for x in want], np.uint8))
+        assert np.array_equal(out.reshape(len(clip), -1), clip.reshape(len(clip), -1)), (size, bpp, levels)
+
+
+def test_stage_outputs_match_oracle(scpr, oracle_built):
+    """per-stage differential: event list (stage A), intervals (stage B), block tables"""
+    w, h = 320, 200
+    clip, keys = fuzz_clip(w, h, 16, 31, 32, 16)
+    orc = oracle_built.OracleCodec(w, h, 32)
+    lib = orc.lib
+    lib.orc_last_events.restype = C.c_size_t
+    lib.orc_last_events.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
+    lib.orc_last_freqs.restype = C.c_size_t
+    lib.orc_last_freqs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
+    lib.orc_last_bts.restype = C.POINTER(C.c_uint8)
+    lib.orc_last_bts.argtypes = [C.c_void_p]
+    enc = _new(scpr, w, h, 32)
+    nb = ((w + 15) // 16) * ((h + 15) // 16)
+    for i in range(len(clip)):
+        data, ft = orc.compress(clip[i].reshape(-1).copy(), not keys[i])
+        p = C.POINTER(C.c_uint32)()
+        n = lib.orc_last_events(orc.h_, C.byref(p))
+        oev = np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        lib.orc_last_freqs(orc.h_, C.byref(p))
+        ofq = np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        got, gft = enc.CompressFrame(clip[i], 0 if keys[i] else 1)
+        ev, iv = enc.debug_events(0)
+        assert np.array_equal(ev, oev), f"frame {i}: event list differs"
+        assert np.array_equal(iv, ofq), f"frame {i}: intervals differ"
+        assert (got, gft) == (data, ft)
+        if ft == 1 and data[0] == 1:
+            bts, sxy, mv = enc.debug_blocks(0)
+            obts = np.ctypeslib.as_array(lib.orc_last_bts(orc.h_), shape=(nb,))
+            assert np.array_equal(bts, obts), f"frame {i}: block types differ"
+
+
+def test_full_size_round_trip_properties(scpr):
+    """BASELINE configs at full resolution, more frames than the oracle could check in seconds:
+    decode(encode(x)) == x, duplicate frames cost one byte, flat frames four."""
+    from screenpressor_b200 import synth
+
+    for cname, n in [("cfg2_1080p_rgb32", 150), ("cfg5_5120x1440", 60), ("cfg3_2160p_rgb32", 12), ("cfg4_1440p_intra", 4)]:
+        cfg = synth.CONFIGS[cname]
+        clip = synth.make_clip(cfg, n)
+        keys = synth.keyframe_flags(n, min(cfg.key_interval, 64))
+        enc, dec = _new(scpr, cfg.width, cfg.height, 32), _new(scpr, cfg.width, cfg.height, 32)
+        stream, sizes, fts = enc.CompressClip(clip, keys)
+        out = dec.DecompressClip(stream, sizes, fts)
+        assert np.array_equal(out.reshape(n, -1), clip.reshape(n, -1)), cname
+        for i in range(1, n):
+            if np.array_equal(clip[i], clip[i - 1]) and not keys[i]:
+                assert sizes[i] == 1
+        assert hashlib.md5(stream.tobytes()).hexdigest()  # stream is materialised
+
+
+def test_flat_and_duplicate_frames(scpr, oracle_built):
+    w, h = 64, 48
+    frames = np.zeros((8, h, w, 4), np.uint8)
+    frames[..., 3] = 255
+    frames[0, ..., :3] = (10, 20, 30)          # flat
+    frames[1] = frames[0]                      # same flat colour again
+    frames[2, ..., :3] = (10, 20, 31)          # another flat colour -> renew
+    frames[3] = frames[2]; frames[3, 5, 7, 1] = 99   # first non-flat frame: forced I
+    frames[4] = frames[3]                      # duplicate -> 1 byte
+    frames[5] = frames[3]; frames[5, 40:44, 10:30, :3] = 200
+    frames[6, ..., :3] = (1, 2, 3)             # flat in the middle of a GOP
+    frames[7] = frames[5]
+    keys = np.array([1, 0, 0, 0, 0, 0, 0, 0], np.uint8)
+    orc = oracle_built.OracleCodec(w, h, 32)
+    want = [orc.compress(frames[i].reshape(-1).copy(), not keys[i]) for i in range(8)]
+    enc = _new(scpr, w, h, 32)
+    got = _split(*enc.CompressClip(frames, keys))
+    assert got == want
+    assert [len(g[0]) for g in got][:3] == [4, 4, 4] and len(got[4][0]) == 1
+    dec = _new(scpr, w, h, 32)
+    for i in range(8):
+        assert np.array_equal(dec.DecompressFrame(got[i][0], None, got[i][1]), frames[i].reshape(-1)), i
+
+
+def test_error_behaviour(scpr):
+    dec = _new(scpr, 64, 48, 32)
+    with pytest.raises(scpr.ScprError):          # P before any I: the reference returns 0 (screencap.cpp:1699)
+        dec.DecompressFrame(b"\x01abcdefgh", None, 1)
+    with pytest.raises(scpr.BadVersionException) as e:   # version nibble 7 -> BadVersionException(8)
+        dec.DecompressFrame(b"\x72abcdefgh", None, 0)
+    assert e.value.version == 8
+    with pytest.raises(scpr.BadVersionException) as e:   # v2 range-coder stream: out of scope here
+        dec.DecompressFrame(b"\x12abcdefgh", None, 0)
+    assert e.value.version == 2
+    sc = scpr.ScreenCodec(0)
+    with pytest.raises(scpr.ScprError):
+        sc.Init(scpr.CodecParameters(64, 48, 16))
+
+
+def test_smoke_entry(scpr):
+    import __graft_entry__ as ge
+
+    ge.smoke()

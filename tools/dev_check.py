@@ -69,7 +69,29 @@ def check(name, clip, keys, w, h, bpp, mode):
             else:
                 print("  events and intervals equal -> rANS/assembly differs")
     sc.Deinit()
-    return not bad
+    # decoder: reference-exact streams in, source frames out
+    dec = ScreenCodec(); dec.Init(CodecParameters(w, h, bpp))
+    flat = [np.ascontiguousarray(clip[i]).reshape(-1) for i in range(n)]
+    t0 = time.time()
+    dbad = []
+    if mode == "frame":
+        for i in range(n):
+            out = dec.DecompressFrame(exp[i][0], None, exp[i][1])
+            if not np.array_equal(out, flat[i]): dbad.append(i)
+    else:
+        stream = np.frombuffer(b"".join(e[0] for e in exp), dtype=np.uint8)
+        sizes = np.array([len(e[0]) for e in exp], dtype=np.uint32); fts = np.array([e[1] for e in exp], dtype=np.uint8)
+        outs = dec.DecompressClip(stream, sizes, fts)
+        for i in range(n):
+            if not np.array_equal(outs[i], flat[i]): dbad.append(i)
+    dt = time.time() - t0
+    print(f"   decode [{mode}]: {'OK' if not dbad else 'MISMATCH at ' + str(dbad[:8])}  ({dt*1e3:.1f} ms)")
+    if dbad and mode == "clip":
+        i = dbad[0]; d = np.nonzero(outs[i] != flat[i])[0]
+        pitch = flat[i].size // h
+        print("    frame", i, "type", exp[i][1], "hdr", exp[i][0][0], "ndiff", len(d), "first (y,xbyte)", divmod(int(d[0]), pitch), "last", divmod(int(d[-1]), pitch))
+    dec.Deinit()
+    return not bad and not dbad
 
 
 ok = True
