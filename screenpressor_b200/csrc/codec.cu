@@ -8,6 +8,7 @@
 // models.cu, rans.cu and decode.cu.  There is no CPU implementation of any of it in this library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -23,6 +24,31 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+StageTimer::StageTimer(cudaStream_t s) : on(getenv("SCPR_TIMING") != nullptr), st(s) { mark("start"); }
+void StageTimer::mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    names.push_back(name);
+}
+void StageTimer::report(const char* what) {
+    if (!on) return;
+    cudaEventSynchronize(ev.back());
+    float tot = 0;
+    cudaEventElapsedTime(&tot, ev.front(), ev.back());
+    fprintf(stderr, "[scpr timing] %s total %.3f ms:", what, tot);
+    for (size_t i = 1; i < ev.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+        fprintf(stderr, " %s=%.3f", names[i], ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
 }
 
 int DBuf::ensure(size_t bytes) {
@@ -138,7 +164,7 @@ void scpr_destroy(scpr_codec* c) {
                    &c->ftype, &c->blocks, &c->pframes, &c->runs, &c->bts_rle, &c->ihdr, &c->desc, &c->exit_tab, &c->entry,
                    &c->starts, &c->chunk_cnt, &c->frame_ev_off, &c->events, &c->intervals, &c->sorted, &c->seg_off,
                    &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
-                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev};
+                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands};
     for (DBuf* b : all) b->release();
     delete c;
 }
@@ -162,6 +188,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     cudaStream_t st = c->st;
     CK(cudaSetDevice(c->device));
     if (n <= 0) return 0;
+    StageTimer tm(st);
 
     // ---- pass 1: frame scan + changed-block lists for every frame ------------------------------
     TRY(c->blkinfo.ensure((size_t)n * g.nb * 4));
@@ -173,8 +200,10 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     CK(cudaMemsetAsync(c->ftype.p, FT_P, (size_t)n, st));
     launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, st,
                       &c->launches);
+    tm.mark("scan");
     launch_compact_changed((const uint32_t*)c->blkinfo.p, (const uint8_t*)c->ftype.p, n, g, (uint32_t*)c->chg_list.p,
                            (PFrameHdr*)c->hdr.p, st, &c->launches);
+    tm.mark("compact");
     std::vector<FrameSummary> summary(n);
     std::vector<PFrameHdr> hdr(n);
     CK(cudaMemcpyAsync(summary.data(), c->summary.p, (size_t)n * sizeof(FrameSummary), cudaMemcpyDeviceToHost, st));
@@ -272,15 +301,19 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     pw.ftype = (const uint8_t*)c->ftype.p; pw.blkinfo = (const uint32_t*)c->blkinfo.p; pw.chg_list = (const uint32_t*)c->chg_list.p;
     pw.hdr = (PFrameHdr*)c->hdr.p; pw.total_blocks = total_blocks; pw.n_pframes = n_p; pw.mvs = (int2*)c->mvs.p;
     pw.frame_ev_off = (const uint32_t*)c->frame_ev_off.p;
+    pw.tm = &tm;
     if (n_p) {
         TRY(c->pframes.ensure((size_t)n_p * 4));
         TRY(c->blocks.ensure((size_t)(total_blocks + 1) * sizeof(ChgBlock)));
         TRY(c->runs.ensure((size_t)(total_blocks + 1) * 256 * 2));
         TRY(c->bts_rle.ensure((size_t)n_p * 2 * g.nb * 4));
+        TRY(c->cands.ensure((size_t)n_p * 17 * 4));
         CK(cudaMemcpyAsync(c->pframes.p, pframes.data(), (size_t)n_p * 4, cudaMemcpyHostToDevice, st));
         pw.blocks = (ChgBlock*)c->blocks.p; pw.pframes = (const int*)c->pframes.p; pw.runs = (uint16_t*)c->runs.p;
         pw.bts_rle = (uint32_t*)c->bts_rle.p;
+        pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * 16;
         launch_p_stage_a(pw, st, &c->launches);
+        tm.mark("p_stage_a");
     }
     IWork iw;
     memset(&iw, 0, sizeof(iw));
@@ -303,7 +336,9 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         iw.desc = (uint16_t*)c->desc.p; iw.exit_tab = (uint8_t*)c->exit_tab.p; iw.entry = (uint16_t*)c->entry.p;
         iw.starts = (uint16_t*)c->starts.p; iw.chunk_cnt = (uint32_t*)c->chunk_cnt.p;
         iw.frame_ev_off = (const uint32_t*)c->frame_ev_off.p;
+        iw.tm = &tm;
         launch_i_stage_a(iw, st, &c->launches);
+        tm.mark("i_stage_a");
     }
     if (n_p) CK(cudaMemcpyAsync(hdr.data(), c->hdr.p, (size_t)n * sizeof(PFrameHdr), cudaMemcpyDeviceToHost, st));
     if (n_i) CK(cudaMemcpyAsync(ihdr.data(), c->ihdr.p, (size_t)n_i * sizeof(IFrameHdr), cudaMemcpyDeviceToHost, st));
@@ -354,8 +389,10 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     TRY(c->intervals.ensure((size_t)(total_ev + 1) * 4));
     pw.events = (uint32_t*)c->events.p; pw.intervals = (uint32_t*)c->intervals.p;
     iw.events = (uint32_t*)c->events.p;
+    tm.mark("plan2");
     if (n_p) launch_p_emit(pw, st, &c->launches);
     if (n_i) launch_i_emit(iw, st, &c->launches);
+    tm.mark("emit");
 
     if (n_chains) {
         TRY(c->sorted.ensure((size_t)(total_ev + 1) * 4));
@@ -375,8 +412,9 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         rw.chains = (const ChainDesc*)c->chains.p; rw.n_chains = n_chains; rw.h_chains = chains.data();
         rw.states = (uint8_t*)c->states.p; rw.f0 = 32;
         rw.sorted = (uint32_t*)c->sorted.p; rw.seg_off = (uint32_t*)c->seg_off.p; rw.chunk_hist = (uint32_t*)c->chunk_hist.p;
-        rw.chunk_base = (const uint32_t*)c->chunk_base.p; rw.total_events = total_ev;
+        rw.chunk_base = (const uint32_t*)c->chunk_base.p; rw.total_events = total_ev; rw.tm = &tm;
         launch_replay(rw, st, &c->launches);
+        tm.mark("replay");
         CK(cudaStreamSynchronize(st));  // `cb` and `chains` are host vectors read by the async copies above
     }
     if (n_rb) {
@@ -384,6 +422,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         TRY(c->scratch.ensure((size_t)scratch_bytes + 16));
         CK(cudaMemcpyAsync(c->rblks.p, rblks.data(), (size_t)n_rb * sizeof(RansBlk), cudaMemcpyHostToDevice, st));
         launch_rans((const uint32_t*)c->intervals.p, (RansBlk*)c->rblks.p, n_rb, (uint8_t*)c->scratch.p, st, &c->launches);
+        tm.mark("rans");
         CK(cudaMemcpyAsync(rblks.data(), c->rblks.p, (size_t)n_rb * sizeof(RansBlk), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
@@ -430,7 +469,9 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     }
     // the last frame of the batch is the next call's previous frame (memcpy(prev, ...) of the reference)
     CK(cudaMemcpyAsync(c->prev.p, d_frames + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
+    tm.mark("assemble+d2h");
     CK(cudaStreamSynchronize(st));
+    tm.report("encode_batch");
     for (int f = 0; f < n; f++) {
         uint8_t* o = dst + frame_out[f];
         switch (ftype[f]) {

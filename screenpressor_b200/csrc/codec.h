@@ -7,6 +7,17 @@
 
 namespace scpr {
 
+// optional per-stage timing (SCPR_TIMING=1): CUDA events on the codec's stream, printed to stderr
+struct StageTimer {
+    bool on;
+    cudaStream_t st;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    explicit StageTimer(cudaStream_t s);
+    void mark(const char* name);
+    void report(const char* what);
+};
+
 // grow-only device buffer
 struct DBuf {
     void* p = nullptr;
@@ -35,7 +46,7 @@ struct scpr_codec {
     int n_states = 0, cur_state = 0;
 
     // ---- encoder workspaces ---------------------------------------------------------------------
-    scpr::DBuf frames, blkinfo, summary, chg_list, hdr, ftype, blocks, pframes, runs, bts_rle;
+    scpr::DBuf frames, blkinfo, summary, chg_list, hdr, ftype, blocks, pframes, runs, bts_rle, cands;
     scpr::DBuf ihdr, desc, exit_tab, entry, starts, chunk_cnt;
     scpr::DBuf frame_ev_off, events, intervals, sorted, seg_off, chunk_hist, chunk_base, chains, rblks, scratch, out;
 

@@ -15,6 +15,7 @@
 // the chain only writes the blocks a frame changes (decoded in a shared-memory tile), tracks for
 // every block which frame holds its current pixels, and k_dec_fill afterwards gathers every
 // untouched block of every frame from that source in one HBM-bound pass.
+#include <stdio.h>
 #include <string.h>
 
 #include <vector>
@@ -89,14 +90,47 @@ __device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, in
     }
 }
 
-// ---- serial entropy state (held by lane 0) ---------------------------------------------------------
+// ---- entropy state ------------------------------------------------------------------------------------
+// The rANS state, the byte cursor and the colour-context registers are held identically by all 32
+// lanes (every lane executes the same arithmetic on the same values), so no broadcast is needed
+// between symbols; only model *stores* are done by one lane.
+//
+// The 21 fixed tables live in shared memory for the whole chain (3192 u16 entries x 3).  A symbol
+// search is warp-parallel: each lane compares its 8 (or 16) cumulative frequencies against the rANS
+// slot with one 128-bit shared load + SIMD halfword compares, a REDUX adds the counts.  A table
+// rebuild (every ~128 symbols of that table, ans_contexts.h:1075-1090) is a warp scan.
+constexpr int FX_TOTAL = 3192;
+__host__ __device__ constexpr int fx_off(int t) {
+    return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
+}
+struct FixedSmem {
+    uint16_t cnt[FX_TOTAL], freq[FX_TOTAL], cum[FX_TOTAL];
+};
+
+#ifdef SCPR_PROF
+#define PROF_T0 const long long t0__ = clock64();
+#define PROF_ADD(field) e.field += clock64() - t0__;
+#define PROF_CNT(field) e.field++;
+#else
+#define PROF_T0
+#define PROF_ADD(field)
+#define PROF_CNT(field)
+#endif
+
 struct Ent {
+#ifdef SCPR_PROF
+    long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
+              c_hdr = 0, c_total = 0;
+#endif
     const uint8_t* p;
     uint32_t x;
     int ndec;
     uint32_t cx, cx1;
     ModelState* m;
+    FixedSmem* fs;
+    int cs;  // lane t < 21 holds cntsum of fixed table t
     int f0;
+    int lane;
 };
 __device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
     e.x = (uint32_t)e.p[0] | ((uint32_t)e.p[1] << 8) | ((uint32_t)e.p[2] << 16) | ((uint32_t)e.p[3] << 24);
@@ -114,27 +148,99 @@ __device__ __forceinline__ void rdec_advance(Ent& e, uint32_t start, uint32_t fr
     while (x < RANS_L) x = (x << 8) | *e.p++;
     e.x = x;
 }
-__device__ inline int dec_color(Ent& e, int id) {  // decodeC
+
+// number of the 8 packed u16 in q that are <= v
+__device__ __forceinline__ int count_le8(uint4 q, uint32_t vv) {
+    return (__popc(__vcmpleu2(q.x, vv)) + __popc(__vcmpleu2(q.y, vv)) + __popc(__vcmpleu2(q.z, vv)) + __popc(__vcmpleu2(q.w, vv))) >> 4;
+}
+
+__device__ __forceinline__ void fixed_rebuild_smem(FixedSmem& fs, int off, int nsym, int lane, int& cntsum) {
+    const int per = (nsym + 31) >> 5;
+    const int b = lane * per;
+    uint32_t sum = 0;
+    for (int j = 0; j < per; j++)
+        if (b + j < nsym) sum += fs.cnt[off + b + j];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    uint32_t cf = inc - sum, ns = 0;
+    for (int j = 0; j < per; j++)
+        if (b + j < nsym) {
+            const uint32_t fr = fs.cnt[off + b + j];
+            fs.cum[off + b + j] = (uint16_t)cf;
+            fs.freq[off + b + j] = (uint16_t)fr;
+            cf += fr;
+            const uint32_t nc = fr - (fr >> 1);
+            fs.cnt[off + b + j] = (uint16_t)nc;
+            ns += nc;
+        }
+    cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
+}
+
+__device__ inline int dec_fixed(Ent& e, int id) {  // decodeF, screencap.h:346-359
+    PROF_T0
+    const int t = id - CX_NTAB, off = fx_off(t), nsym = fixed_nsym(id), lane = e.lane;
+    FixedSmem& fs = *e.fs;
+    const uint32_t v = e.x & (PROB_SCALE - 1), vv = v | (v << 16);
+    int j;
+    if (nsym == 256) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 8]);
+        j = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)count_le8(q, vv)) - 1;
+    } else if (nsym == 512) {
+        const uint4 q0 = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 16]);
+        const uint4 q1 = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 16 + 8]);
+        j = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(count_le8(q0, vv) + count_le8(q1, vv))) - 1;
+    } else {
+        const bool le = lane < nsym && fs.cum[off + lane] <= v;
+        j = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
+    }
+    const uint32_t freq = fs.freq[off + j], cum = fs.cum[off + j];
+    int cs = __shfl_sync(0xFFFFFFFFu, e.cs, t) + 16;
+    if (lane == 0) fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
+    if (cs + 16 > PROB_SCALE) {
+        __syncwarp();
+        fixed_rebuild_smem(fs, off, nsym, lane, cs);
+        __syncwarp();
+    }
+    if (lane == t) e.cs = cs;
+    rdec_advance(e, cum, freq);
+    rdec_count(e);
+    PROF_ADD(c_fixed) PROF_CNT(n_fixed)
+    return j;
+}
+
+__device__ inline int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
+    PROF_T0
     ColorState& x = e.m->color[id];
+    const int kind = x.kind;
     int c;
-    if (x.kind >= 4) {
-        c = cc_find(x, (int)(e.x & (PROB_SCALE - 1)));
-        const uint32_t iv = cc_encode_counted(x, c);
+    if (kind >= 4) {
+        const uint32_t v = e.x & (PROB_SCALE - 1);
+        uint32_t iv = 0;
+        if (kind >= 6) {  // flat table: warp-parallel search, 8 cumulative frequencies per lane
+            const uint4 q = *reinterpret_cast<const uint4*>(&x.cum[e.lane * 8]);
+            c = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)count_le8(q, v | (v << 16))) - 1;
+            if (e.lane == 0) iv = cc_encode_counted(x, c);
+        } else {
+            c = 0;
+            if (e.lane == 0) {
+                c = cc_find(x, (int)v);
+                iv = cc_encode_counted(x, c);
+            }
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        }
+        iv = __shfl_sync(0xFFFFFFFFu, iv, 0);
         rdec_advance(e, iv >> 16, iv & 0xFFFFu);
     } else {
         c = *e.p++;
-        cc_update_raw(x, c, e.f0);
+        if (e.lane == 0) cc_update_raw(x, c, e.f0);
     }
+    __syncwarp();  // lane 0's model stores are visible to the whole warp before the next symbol
     rdec_count(e);
-    return c;
-}
-__device__ inline int dec_fixed(Ent& e, int id) {  // decodeF
-    FixedState& f = e.m->fx[id - CX_NTAB];
-    const int c = table_find(f.cum, f.nsym, (int)(e.x & (PROB_SCALE - 1)));
-    const uint32_t freq = f.freq[c], cum = f.cum[c];
-    table_incr(f.cnt, f.freq, f.cum, f.nsym, f.cntsum, c);
-    rdec_advance(e, cum, freq);
-    rdec_count(e);
+    PROF_ADD(c_color) PROF_CNT(n_color)
     return c;
 }
 __device__ inline int dec_bool(Ent& e) {  // decodeBool
@@ -197,14 +303,8 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     int ptype = 0;
     // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
     while (q < g.X + 1) {
-        uint32_t c = 0;
-        int n = 0;
-        if (lane == 0) {
-            c = dec_rgb(e);
-            n = dec_fixed(e, CX_NTAB + 0);
-        }
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        uint32_t c = dec_rgb(e);
+        int n = dec_fixed(e, CX_NTAB + 0);
         if (q + n > total) n = (int)(total - q);  // corrupt input guard
         if (n <= 0) return;
         for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
@@ -213,17 +313,12 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     }
     while (q < total) {
         uint32_t c = 0;
-        int n = 0;
-        if (lane == 0) {
-            ptype = dec_fixed(e, CX_PTYPE + ptype);
-            if (!ptype) c = dec_rgb(e);
-            n = dec_fixed(e, CX_NTAB + ptype);
-        }
-        ptype = __shfl_sync(0xFFFFFFFFu, ptype, 0);
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        ptype = dec_fixed(e, CX_PTYPE + ptype);
+        if (!ptype) c = dec_rgb(e);
+        int n = dec_fixed(e, CX_NTAB + ptype);
         if (q + n > total) n = (int)(total - q);  // corrupt input guard
         if (n <= 0) return;
+        PROF_T0
         if (ptype == 0 || ptype == 1) {
             if (ptype == 1) c = px_at(q - 1);
             for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
@@ -245,7 +340,8 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
         }
         __syncwarp();
         q += n;
-        if (lane == 0) set_cx_from(e, px_at(q - 1));
+        set_cx_from(e, px_at(q - 1));
+        PROF_ADD(c_ifill)
     }
 }
 
@@ -253,43 +349,42 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
 __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame, int f, uint8_t* s_bts, uint32_t (*tile)[17],
                          int lane) {
     const Geo& g = w.g;
-    int xx1 = 0, xx2 = 0;
-    if (lane == 0) {
-        int t = dec_fixed(e, CX_XX);
-        xx1 = (dec_fixed(e, CX_XX) << 8) + t;
-        t = dec_fixed(e, CX_XX);
-        xx2 = (dec_fixed(e, CX_XX) << 8) + t;
-        if (xx2 >= g.nb) xx2 = g.nb - 1;  // corrupt input guard
-    }
-    xx1 = __shfl_sync(0xFFFFFFFFu, xx1, 0);
-    xx2 = __shfl_sync(0xFFFFFFFFu, xx2, 0);
+    const long long thdr__ = clock64();
+    int t0 = dec_fixed(e, CX_XX);
+    const int xx1 = (dec_fixed(e, CX_XX) << 8) + t0;
+    t0 = dec_fixed(e, CX_XX);
+    int xx2 = (dec_fixed(e, CX_XX) << 8) + t0;
+    if (xx2 >= g.nb) xx2 = g.nb - 1;  // corrupt input guard
     // block types of [xx1, xx2] as (type, run) pairs (screencap.cpp:1306-1313)
-    for (int i = lane; i < g.nb; i += 32) s_bts[i] = 0;
-    __syncwarp();
     for (int x = xx1; x <= xx2;) {
-        int c = 0, n = 0;
-        if (lane == 0) {
-            c = dec_fixed(e, CX_BT);
-            n = dec_fixed(e, CX_NTAB2);
-        }
-        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+        const int c = dec_fixed(e, CX_BT);
+        const int n = dec_fixed(e, CX_NTAB2);
         if (n <= 0) break;
         for (int i = lane; i < n && x + i < g.nb; i += 32) s_bts[x + i] = (uint8_t)c;
         x += n;
     }
     __syncwarp();
-    if (lane == 0) e.cx = e.cx1 = 0;
+#ifdef SCPR_PROF
+    e.c_hdr += clock64() - thdr__;
+#endif
+    e.cx = e.cx1 = 0;
     int lastmx = 0, lastmy = 0;
     uint8_t* upd = w.upd + (size_t)f * g.nb;
-    for (int bi = xx1; bi <= xx2; bi++) {
+    // visit changed blocks only: 32 block types per step, ballot, iterate the set bits
+    for (int b0 = xx1 & ~31; b0 <= xx2; b0 += 32) {
+      const int myb = b0 + lane;
+      uint32_t chm = __ballot_sync(0xFFFFFFFFu, myb >= xx1 && myb <= xx2 && s_bts[myb] != 0);
+      while (chm) {
+        const int bi = b0 + __ffs(chm) - 1;
+        chm &= chm - 1;
         const int bt = s_bts[bi];
-        if (!bt) continue;
         const int by = bi / g.nbx, bx = bi - by * g.nbx;
         const int bx0 = bx * 16, by0 = by * 16;
         const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
         int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
         // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
+        PROF_CNT(n_blocks)
+        { PROF_T0
         for (int p = lane; p < 17 * 17; p += 32) {
             const int ty = p / 17, tx = p - ty * 17;
             const int x = bx0 + tx - 1, y = by0 + ty - 1;
@@ -301,14 +396,12 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             tile[ty][tx] = v;
         }
         __syncwarp();
+        PROF_ADD(c_tile) }
         if ((bt - 1) & 1) {
-            int v4[4] = {0, 0, 0, 0};
-            if (lane == 0)
-                for (int k = 0; k < 4; k++) v4[k] = dec_fixed(e, CX_SXY + k);
-            x1 = bx0 + __shfl_sync(0xFFFFFFFFu, v4[0], 0);
-            y1 = by0 + __shfl_sync(0xFFFFFFFFu, v4[1], 0);
-            x2 = bx0 + __shfl_sync(0xFFFFFFFFu, v4[2], 0) + 1;
-            y2 = by0 + __shfl_sync(0xFFFFFFFFu, v4[3], 0) + 1;
+            x1 = bx0 + dec_fixed(e, CX_SXY + 0);
+            y1 = by0 + dec_fixed(e, CX_SXY + 1);
+            x2 = bx0 + dec_fixed(e, CX_SXY + 2) + 1;
+            y2 = by0 + dec_fixed(e, CX_SXY + 3) + 1;
             if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
             if (y2 > by0 + bh) y2 = by0 + bh;
             if (x1 >= x2) x1 = x2 - 1;
@@ -316,15 +409,12 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         }
         const int sw = x2 - x1, sh = y2 - y1;
         if ((bt - 1) & 2) {  // motion vector block
+            PROF_T0
             int mx = lastmx, my = lastmy;
-            if (lane == 0) {
-                if (!dec_bool(e)) {
-                    mx = dec_fixed(e, CX_MV + 0) - 256;
-                    my = dec_fixed(e, CX_MV + 1) - 256;
-                }
+            if (!dec_bool(e)) {
+                mx = dec_fixed(e, CX_MV + 0) - 256;
+                my = dec_fixed(e, CX_MV + 1) - 256;
             }
-            mx = __shfl_sync(0xFFFFFFFFu, mx, 0);
-            my = __shfl_sync(0xFFFFFFFFu, my, 0);
             lastmx = mx; lastmy = my;
             for (int p = lane; p < sw * sh; p += 32) {
                 const int xx = p % sw, yy = p / sw;
@@ -332,41 +422,55 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                 sx = min(max(sx, 0), g.X - 1); sy = min(max(sy, 0), g.Y - 1);  // corrupt input guard
                 tile[1 + y1 - by0 + yy][1 + x1 - bx0 + xx] = prev_px(cc, sx, sy);
             }
+            PROF_ADD(c_mv)
         } else {  // pixel runs over the sub-rect in its own raster order
+            PROF_T0
             int pos = 0, ptype = 0;
             const int npx = sw * sh;
             const int ox = 1 + x1 - bx0, oy = 1 + y1 - by0;
             while (pos < npx) {
                 uint32_t c = 0;
-                int n = 0;
-                if (lane == 0) {
-                    ptype = dec_fixed(e, CX_PTYPE + ptype);
-                    if (!ptype) c = dec_rgb(e);
-                    n = dec_fixed(e, CX_NTAB + ptype);
-                    if (n > npx - pos) n = npx - pos;
-                    uint32_t v = c;
-                    for (int i = 0; i < n; i++) {
+                ptype = dec_fixed(e, CX_PTYPE + ptype);
+                if (!ptype) c = dec_rgb(e);
+                int n = dec_fixed(e, CX_NTAB + ptype);
+                if (n > npx - pos) n = npx - pos;
+                if (n <= 0) break;
+                uint32_t v = c;
+                if (ptype == 0 || ptype == 3) {  // no dependence on pixels of this run: lanes fill in parallel
+                    for (int i = lane; i < n; i += 32) {
                         const int xx = (pos + i) % sw, yy = (pos + i) / sw;
                         uint32_t* t = &tile[oy + yy][ox + xx];
-                        switch (ptype) {
-                        case 1: v = t[-1]; break;
-                        case 2: v = t[-17]; break;
-                        case 3: v = (bt - 1) & 1 ? t[0] : prev_px(cc, x1 + xx, y1 + yy); break;
-                        case 4: v = grad_px(t[-1], t[-17], t[-18]); break;
-                        case 5: v = t[-18]; break;
-                        }
-                        t[0] = v;
+                        if (ptype == 3) t[0] = (bt - 1) & 1 ? t[0] : prev_px(cc, x1 + xx, y1 + yy);
+                        else t[0] = c;
                     }
-                    set_cx_from(e, v);
+                    __syncwarp();
+                    const int li = pos + n - 1;
+                    v = tile[oy + li / sw][ox + li % sw];
+                } else {
+                    if (lane == 0)
+                        for (int i = 0; i < n; i++) {
+                            const int xx = (pos + i) % sw, yy = (pos + i) / sw;
+                            uint32_t* t = &tile[oy + yy][ox + xx];
+                            switch (ptype) {
+                            case 1: v = t[-1]; break;
+                            case 2: v = t[-17]; break;
+                            case 4: v = grad_px(t[-1], t[-17], t[-18]); break;
+                            case 5: v = t[-18]; break;
+                            }
+                            t[0] = v;
+                        }
+                    __syncwarp();
+                    const int li = pos + n - 1;
+                    v = tile[oy + li / sw][ox + li % sw];
                 }
-                ptype = __shfl_sync(0xFFFFFFFFu, ptype, 0);
-                n = __shfl_sync(0xFFFFFFFFu, n, 0);
-                if (n <= 0) break;
+                set_cx_from(e, v);
                 pos += n;
             }
+            PROF_ADD(c_runs)
         }
         __syncwarp();
         // write the whole block and hand its ownership to this frame
+        { PROF_T0
         for (int p = lane; p < bw * bh; p += 32) {
             const int xx = p % bw, yy = p / bw;
             store_px(frame, g, bx0 + xx, by0 + yy, tile[1 + yy][1 + xx]);
@@ -380,14 +484,17 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             upd[bi] = 1;
         }
         __syncwarp();
+        PROF_ADD(c_blkwr) }
+      }
     }
 }
 
 // one warp per chain
 __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
-    extern __shared__ uint8_t s_mem[];
-    uint32_t(*tile)[17] = reinterpret_cast<uint32_t(*)[17]>(s_mem);
-    uint8_t* s_bts = s_mem + 17 * 17 * 4;
+    extern __shared__ __align__(16) uint8_t s_mem[];
+    FixedSmem* fs = reinterpret_cast<FixedSmem*>(s_mem);
+    uint32_t(*tile)[17] = reinterpret_cast<uint32_t(*)[17]>(s_mem + sizeof(FixedSmem));
+    uint8_t* s_bts = s_mem + sizeof(FixedSmem) + 17 * 17 * 4;
     const int lane = threadIdx.x;
     const DecChain ch = w.chains[blockIdx.x];
     const Geo& g = w.g;
@@ -409,6 +516,24 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     e.ndec = 0;
     e.x = 0;
     e.p = nullptr;
+    e.fs = fs;
+    e.lane = lane;
+    e.cs = 0;
+#ifdef SCPR_PROF
+    const long long tk0 = clock64();
+#endif
+    // fixed tables of the chain's model state -> shared memory (a renewing first frame overwrites them)
+    for (int t = 0; t < NUM_FIXED_CX; t++) {
+        const FixedState& g0 = e.m->fx[t];
+        const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+        for (int i = lane; i < nsym; i += 32) {
+            fs->cnt[off + i] = g0.cnt[i];
+            fs->freq[off + i] = g0.freq[i];
+            fs->cum[off + i] = g0.cum[i];
+        }
+        if (lane == t) e.cs = g0.cntsum;
+    }
+    __syncwarp();
     for (int f = ch.first; f < ch.first + ch.count; f++) {
         const DecFrame df = w.frames[f];
         uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
@@ -417,7 +542,16 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
         if (df.kind == DK_FLAT || df.kind == DK_I) {
             if (df.kind == DK_I || df.renew) {  // RenewI
                 for (int i = lane; i < NUM_COLOR_CX; i += 32) e.m->color[i].kind = 0;
-                if (lane < NUM_FIXED_CX) fixed_renew(e.m->fx[lane], fixed_nsym(CX_NTAB + lane));
+                for (int t = 0; t < NUM_FIXED_CX; t++) {  // FixedSizeRansCtx::renew, ans_contexts.h:1114-1131
+                    const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+                    const int fr = PROB_SCALE / nsym, c0 = fr - (fr >> 1);
+                    for (int i = lane; i < nsym; i += 32) {
+                        fs->cnt[off + i] = (uint16_t)c0;
+                        fs->freq[off + i] = (uint16_t)fr;
+                        fs->cum[off + i] = (uint16_t)(fr * i);
+                    }
+                    if (lane == t) e.cs = c0 * nsym;
+                }
                 __syncwarp();
             }
             for (int i = lane; i < g.nb; i += 32) {  // the whole frame is new
@@ -430,16 +564,39 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
                 e.p = w.stream + df.src_off + 1;
                 e.ndec = 0;
                 e.cx = e.cx1 = 0;
-                if (lane == 0) rdec_init(e);
+                rdec_init(e);
                 decode_i(w, e, frame, lane);
             }
             continue;
         }
         e.p = w.stream + df.src_off + 1;
         e.ndec = 0;
-        if (lane == 0) rdec_init(e);
+        rdec_init(e);
         decode_p(w, cc, e, frame, f, s_bts, tile, lane);
         __threadfence_block();
+    }
+#ifdef SCPR_PROF
+    if (lane == 0)
+        printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc) | "
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f\n",
+               (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
+               e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.c_hdr * 1e-6, e.c_tile * 1e-6, e.n_blocks,
+               e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6);
+#endif
+    // leave the fixed tables behind for the next call
+    __syncwarp();
+    for (int t = 0; t < NUM_FIXED_CX; t++) {
+        FixedState& g0 = e.m->fx[t];
+        const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+        for (int i = lane; i < nsym; i += 32) {
+            g0.cnt[i] = fs->cnt[off + i];
+            g0.freq[i] = fs->freq[off + i];
+            g0.cum[i] = fs->cum[off + i];
+        }
+        if (lane == t) {
+            g0.cntsum = e.cs;
+            g0.nsym = nsym;
+        }
     }
 }
 
@@ -630,13 +787,17 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.fill_src = (int16_t*)(ws + 3 * map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
     w.n = n;
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
-    const size_t smem = 17 * 17 * 4 + (size_t)g.nb + 16;
+    const size_t smem = sizeof(FixedSmem) + 17 * 17 * 4 + (size_t)g.nb + 16;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageTimer tm(st);
     k_dec_chain<<<n_chains, 32, smem, st>>>(w);
+    tm.mark("chain");
     k_dec_sources<<<(g.nb + 127) / 128, 128, 0, st>>>(w);
     const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
     k_dec_fill<<<(unsigned)((strips + 7) / 8), 256, 0, st>>>(w);
     c->launches += 3;
+    tm.mark("sources+fill");
+    tm.report("decode_batch");
     CK(cudaMemcpyAsync(c->dec_prev.p, d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

@@ -13,7 +13,7 @@
 // q -> q + len(q).  That orbit is resolved per 2048-pixel chunk: pointer doubling in shared memory
 // gives each chunk a 255-entry table "entry offset -> entry offset of the next chunk", a short
 // serial pass chains the tables, and then chunks mark their run starts and emit independently.
-#include "kernels.cuh"
+#include "codec.h"
 
 namespace scpr {
 
@@ -323,8 +323,11 @@ void launch_i_stage_a(const IWork& w, cudaStream_t st, uint64_t* launches) {
     if (w.n_iframes == 0) return;
     dim3 grid(w.nchunks, w.n_iframes);
     k_i_classify<<<grid, 256, 0, st>>>(w);
+    if (w.tm) w.tm->mark("i_classify");
     k_i_entries<<<(w.n_iframes + 31) / 32, 32, 0, st>>>(w);
+    if (w.tm) w.tm->mark("i_entries");
     k_i_mark<<<grid, 256, 0, st>>>(w);
+    if (w.tm) w.tm->mark("i_mark");
     k_i_offsets<<<w.n_iframes, 32, 0, st>>>(w);
     *launches += 4;
 }

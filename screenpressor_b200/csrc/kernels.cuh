@@ -4,6 +4,8 @@
 
 namespace scpr {
 
+struct StageTimer;
+
 // frame types decided by the host plan (CScreenCapt::CompressFrame, reference screencap.cpp:1456-1518)
 enum : uint8_t {
     FT_FLAT = 0,   // 0x31 + colour, 4 bytes
@@ -31,7 +33,9 @@ struct ChgBlock {
     uint8_t has_f;      // F(bi) exists
     uint8_t bt;         // final block type 1..4 (reference bts[])
     uint8_t rep;        // MV equals the previously coded MV of this frame (encodeBool(true))
-    uint8_t pad;
+    uint8_t fidx;       // index of F(bi) in the frame's candidate list, 0xFF = not listed (k_mv_cands)
+    uint16_t mmask;     // bit k: candidate k of the frame reproduces this block (k_mv_prematch)
+    uint16_t pad;
     int32_t prev_nonmv; // previous pixel-coded changed block of the frame (slot index), -1 if none
     uint32_t n_runs;    // pixel runs of a pixel-coded block
     uint32_t n_ev;      // events this block contributes
@@ -71,10 +75,12 @@ struct PWork {
     PFrameHdr* hdr; ChgBlock* blocks; int total_blocks;
     const int* pframes; int n_pframes;     // batch indices of P-coded frames, ascending
     int2* mvs;                             // persistent per-block MV array (reference mvs[], never cleared)
+    int* cands; int* ncands;               // per P frame: up to 16 distinct F vectors (packed x | y<<16) and their count
     uint16_t* runs;                        // per changed block: 256 x (ptype<<8 | n)
     uint32_t* bts_rle;                     // per P frame: scratch for the block-type RLE, 2*nb entries
     const uint32_t* frame_ev_off;          // per batch frame: first event (batch-wide index)
     uint32_t* events; uint32_t* intervals;
+    struct StageTimer* tm;
 };
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches);   // search, resolve, runs, counts
 void launch_p_emit(const PWork& w, cudaStream_t st, uint64_t* launches);      // events
@@ -90,6 +96,7 @@ struct IWork {
     uint32_t* chunk_cnt;   // per chunk: {n_runs, n_ev, last_type, ev_off}
     const uint32_t* frame_ev_off;
     uint32_t* events;
+    struct StageTimer* tm;
 };
 void launch_i_stage_a(const IWork& w, cudaStream_t st, uint64_t* launches);
 void launch_i_emit(const IWork& w, cudaStream_t st, uint64_t* launches);
@@ -111,6 +118,7 @@ struct ReplayWork {
     // sort workspace
     uint32_t* sorted; uint32_t* seg_off; uint32_t* chunk_hist; const uint32_t* chunk_base;
     uint32_t total_events;
+    struct StageTimer* tm;
 };
 size_t replay_hist_entries(uint32_t n_ev);     // u32 entries of chunk_hist needed for a chain of n_ev events
 size_t build_sort_chunks(const ChainDesc* chains, int n_chains, uint32_t* out);  // host image of chunk_base; returns words

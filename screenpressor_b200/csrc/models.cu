@@ -10,7 +10,7 @@
 //     table look-ups + a shared-memory histogram + one table rebuild (warp scan);
 //   * the 12288 colour contexts: one thread per context walking the Cx1..Cx7 state machine.
 // Intervals are scattered back to bitstream order for the rANS stage.
-#include "kernels.cuh"
+#include "codec.h"
 #include "models.cuh"
 
 namespace scpr {
@@ -266,7 +266,9 @@ void launch_replay(const ReplayWork& w, cudaStream_t st, uint64_t* launches) {
         k_sort_place<<<n_chunks, 32, NUM_CX * sizeof(uint16_t), st>>>(w.events, chunks, hist, w.seg_off, w.chains, w.sorted);
         ++*launches;
     }
+    if (w.tm) w.tm->mark("sort");
     k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, st>>>(w, w.seg_off);
+    if (w.tm) w.tm->mark("fixed");
     k_replay_color<<<dim3(NUM_COLOR_CX / 128, w.n_chains), 128, 0, st>>>(w, w.seg_off);
     *launches += 2;
 }

@@ -17,7 +17,8 @@ struct FixedState {  // FixedSizeRansCtx<N>, ans_contexts.h:1053-1132
     uint16_t cnt[512], freq[512], cum[512];
 };
 
-struct ColorState {
+struct alignas(16) ColorState {
+    uint16_t cnt[256], freq[256], cum[256];  // kinds 6/7 (16-byte aligned for 128-bit table scans)
     uint8_t kind;    // 0 empty, 1..3 "every symbol met once" sets, 4/5 SmallContext, 6 Cx6, 7 Cx7
     uint8_t fshift;  // kind 6
     uint8_t maxpos;  // kinds 4/5
@@ -28,7 +29,6 @@ struct ColorState {
     uint32_t seen[8];     // kinds 1..3: bitmap of symbols met
     uint8_t ssym[16];     // kinds 4/5: sorted symbols ...
     uint16_t sfreq[16];   // ... and their frequencies
-    uint16_t cnt[256], freq[256], cum[256];
 };
 
 struct ModelState {

@@ -12,7 +12,7 @@
 // changed block of every frame in parallel (k_mv_search, 32 candidates per warp step, first hit by
 // ballot), and only the two state-dependent shortcut candidates are evaluated in frame/raster order
 // (k_mv_resolve); a shortcut whose vector equals F(b) needs no compare at all.
-#include "kernels.cuh"
+#include "codec.h"
 
 namespace scpr {
 
@@ -149,22 +149,106 @@ __global__ void __launch_bounds__(128) k_mv_search(PWork w) {
     }
 }
 
-// warp-cooperative SameBlocks: sub-rect of cur at (x1,y1) vs prev at (x1+mx, y1+my)
+// warp-cooperative SameBlocks: sub-rect of cur at (x1,y1) vs prev at (x1+mx, y1+my); 32 pixels per
+// step, stops at the first step that differs
 __device__ __forceinline__ bool warp_match(const uint8_t* cur, const uint8_t* prv, const Geo& g, const SubRect& r, int mx,
                                            int my, int lane) {
-    bool same = true;
     const int npx = r.w * r.h;
-    for (int p = lane; p < npx; p += 32) {
-        const int xx = p % r.w, yy = p / r.w;
-        if (load_px(cur, g, r.x1 + xx, r.y1 + yy) != load_px(prv, g, r.x1 + mx + xx, r.y1 + my + yy)) same = false;
+    for (int p0 = 0; p0 < npx; p0 += 32) {
+        const int p = p0 + lane;
+        bool same = true;
+        if (p < npx) {
+            const int xx = p % r.w, yy = p / r.w;
+            same = load_px(cur, g, r.x1 + xx, r.y1 + yy) == load_px(prv, g, r.x1 + mx + xx, r.y1 + my + yy);
+        }
+        if (!__all_sync(0xFFFFFFFFu, same)) return false;
     }
-    return __all_sync(0xFFFFFFFFu, same);
+    return true;
+}
+__device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& win, int mx, int my) {
+    const int sx = r.x1 + mx, sy = r.y1 + my;
+    return sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_mv_resolve: the serial part of FindMV, one warp walking P frames and their changed blocks in
-// order.  Candidate 1 = last_mv, candidate 2 = persistent MV of the block above
-// (screencap.cpp:715-735); search hits (= F) update last_mv, shortcut hits do not.
+// k_mv_cands: per P frame, the distinct F vectors of its blocks (first MAXC of them, in order of
+// appearance) -- the only values last_mv can take in this frame besides (0,0).  One warp per frame;
+// lane k keeps candidate k.  Also records each block's index into that list (fidx, 0xFF = none).
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXC = 16;
+__global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
+    const int lane = threadIdx.x;
+    const int f = w.pframes[blockIdx.x];
+    const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
+    int cand = 0x7FFFFFFF;  // packed (mx & 0xFFFF) | (my << 16)
+    int ncand = 0;
+    for (int k0 = 0; k0 < nchg; k0 += 32) {
+        const int k = k0 + lane;
+        int fv = 0x7FFFFFFF;
+        if (k < nchg && w.blocks[off + k].has_f)
+            fv = ((int)w.blocks[off + k].fmx & 0xFFFF) | ((int)w.blocks[off + k].fmy << 16);
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, fv != 0x7FFFFFFF);
+        int myidx = 0xFF;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            const int v = __shfl_sync(0xFFFFFFFFu, fv, src);
+            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < ncand && cand == v);
+            int idx;
+            if (hit)
+                idx = __ffs(hit) - 1;
+            else if (ncand < MAXC) {
+                if (lane == ncand) cand = v;
+                idx = ncand++;
+            } else
+                idx = 0xFF;
+            // every block of this step with the same vector gets the same answer
+            const uint32_t same = __ballot_sync(0xFFFFFFFFu, fv == v);
+            if (fv == v) myidx = idx;
+            todo &= ~same;
+        }
+        if (k < nchg) w.blocks[off + k].fidx = (uint8_t)myidx;
+    }
+    if (lane < MAXC) w.cands[(size_t)blockIdx.x * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
+    if (lane == 0) w.ncands[blockIdx.x] = ncand;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mv_prematch: for every changed block, which of its frame's candidate vectors reproduce the
+// block from the previous frame (window test included).  One warp per block -> 16-bit mask.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int slot = blockIdx.x * 4 + wi;
+    if (slot >= w.total_blocks) return;
+    const int pi = find_pframe(w.hdr, w.pframes, w.n_pframes, slot);
+    const int f = w.pframes[pi];
+    const Geo& g = w.g;
+    ChgBlock& b = w.blocks[slot];
+    const SubRect r = subrect_of(b.bi, b.info, g);
+    const Windows win = windows_of(r, g);
+    const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+    const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
+    const int nc = w.ncands[pi];
+    const int fidx = b.fidx;
+    uint32_t mask = 0;
+    for (int k = 0; k < nc; k++) {
+        if (k == fidx) {  // F(b) matches by construction and lies inside the far window
+            mask |= 1u << k;
+            continue;
+        }
+        const int cv = w.cands[(size_t)pi * MAXC + k];
+        const int mx = (int)(int16_t)(cv & 0xFFFF), my = cv >> 16;
+        if (in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane)) mask |= 1u << k;
+    }
+    if (lane == 0) b.mmask = (uint16_t)mask;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mv_resolve: the serial part of FindMV (screencap.cpp:715-735), one warp walking P frames and
+// their changed blocks in order.  Candidate 1 = last_mv, candidate 2 = persistent MV of the block
+// above; search hits (= F) update last_mv, shortcut hits do not.  With the prematch masks the walk
+// is table look-ups: blocks are taken 32 at a time (one per lane, fields exchanged by shuffles),
+// and a direct compare is only needed for a vector outside the frame's candidate list.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
     const int lane = threadIdx.x;
@@ -174,61 +258,89 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
         const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
         const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
-        int lmx = 0, lmy = 0;      // last_mv
-        int cmx = 0, cmy = 0;      // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
+        const int nc = w.ncands[pi];
+        const int cand = lane < MAXC ? w.cands[(size_t)pi * MAXC + lane] : 0x7FFFFFFF;  // lane k: candidate k
+        int lv = 0, lidx = -1;   // last_mv (packed) and its index in the candidate list (-1: (0,0), -2: not listed)
+        int cv = 0;              // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
         int prev_nonmv = -1;
-        for (int k = 0; k < nchg; k++) {
-            ChgBlock& b = w.blocks[off + k];
-            const uint32_t bi = b.bi;
-            const SubRect r = subrect_of(bi, b.info, g);
-            const Windows win = windows_of(r, g);
-            const bool has_f = b.has_f;
-            const int fmx = b.fmx, fmy = b.fmy;
-            bool found = false;
-            int mx = 0, my = 0;
-            {   // candidate 1: last_mv
-                const int sx = r.x1 + lmx, sy = r.y1 + lmy;
-                if (sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2) {
-                    if ((has_f && fmx == lmx && fmy == lmy) || warp_match(cur, prv, g, r, lmx, lmy, lane)) {
-                        found = true; mx = lmx; my = lmy;
-                    }
+        int k0 = 0;
+        while (k0 < nchg) {
+            // one block per lane; the step ends before a block whose upper neighbour is inside the step
+            const int k = k0 + lane;
+            uint32_t bi = 0, info = 0;
+            int mmask = 0, fidx = 0xFF, fv = 0, uv = 0;
+            if (k < nchg) {
+                const ChgBlock& b = w.blocks[off + k];
+                bi = b.bi; info = b.info; mmask = b.mmask; fidx = b.has_f ? b.fidx : 0x100;
+                fv = ((int)b.fmx & 0xFFFF) | ((int)b.fmy << 16);
+                if (bi >= (uint32_t)g.nbx) {
+                    const int2 u = w.mvs[bi - g.nbx];
+                    uv = (u.x & 0xFFFF) | (u.y << 16);
                 }
             }
-            if (!found && r.by > 0) {  // candidate 2: MV stored for the block above, if it differs
-                const int2 u = w.mvs[bi - g.nbx];
-                if (u.x != lmx || u.y != lmy) {
-                    const int sx = r.x1 + u.x, sy = r.y1 + u.y;
-                    if (sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2) {
-                        if ((has_f && fmx == u.x && fmy == u.y) || warp_match(cur, prv, g, r, u.x, u.y, lane)) {
-                            found = true; mx = u.x; my = u.y;
-                        }
-                    }
+            const uint32_t bi0 = __shfl_sync(0xFFFFFFFFu, bi, 0);
+            const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, k < nchg && bi - bi0 < (uint32_t)g.nbx));
+            int out_v = 0, out_flags = 0, out_prev = -1;  // per-lane results, written after the step
+            for (int i = 0; i < cnt; i++) {
+                const int b_mask = __shfl_sync(0xFFFFFFFFu, mmask, i), b_fidx = __shfl_sync(0xFFFFFFFFu, fidx, i);
+                const int b_fv = __shfl_sync(0xFFFFFFFFu, fv, i), b_uv = __shfl_sync(0xFFFFFFFFu, uv, i);
+                const uint32_t b_bi = __shfl_sync(0xFFFFFFFFu, bi, i), b_info = __shfl_sync(0xFFFFFFFFu, info, i);
+                bool found = false;
+                int mv = 0;
+                // candidate 1: last_mv
+                if (lidx >= 0)
+                    found = (b_mask >> lidx) & 1;
+                else if (lidx == -2) {
+                    const SubRect r = subrect_of(b_bi, b_info, g);
+                    const Windows win = windows_of(r, g);
+                    const int mx = (int)(int16_t)(lv & 0xFFFF), my = lv >> 16;
+                    found = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
                 }
-            }
-            if (!found && has_f) {  // the fixed-order search: first hit wins and becomes last_mv
-                found = true; mx = fmx; my = fmy;
-                lmx = mx; lmy = my;
-            }
-            if (lane == 0) {
-                uint8_t bt = r.partial ? 2 : 1;
+                if (found) mv = lv;
+                // candidate 2: the vector stored for the block above, if it differs from last_mv
+                if (!found && b_bi >= (uint32_t)g.nbx && b_uv != lv && b_uv != 0) {
+                    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < nc && cand == b_uv);
+                    if (hit)
+                        found = (b_mask >> (__ffs(hit) - 1)) & 1;
+                    else {
+                        const SubRect r = subrect_of(b_bi, b_info, g);
+                        const Windows win = windows_of(r, g);
+                        const int mx = (int)(int16_t)(b_uv & 0xFFFF), my = b_uv >> 16;
+                        found = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                    }
+                    if (found) mv = b_uv;
+                }
+                // the fixed-order search: first hit wins and becomes last_mv
+                if (!found && b_fidx != 0x100) {
+                    found = true;
+                    mv = b_fv;
+                    lv = b_fv;
+                    lidx = b_fidx == 0xFF ? -2 : b_fidx;
+                }
+                int flags = (b_info & BI_PARTIAL) ? 2 : 1;
                 if (found) {
-                    bt += 2;
-                    w.mvs[bi] = make_int2(mx, my);
-                    const bool rep = bi > 0 && mx == cmx && my == cmy;  // screencap.cpp:1202
-                    b.rep = rep;
-                    b.mx = (int16_t)mx; b.my = (int16_t)my;
-                    b.prev_nonmv = -1;
-                } else {
-                    b.rep = 0;
-                    b.prev_nonmv = prev_nonmv;
+                    flags += 2;
+                    const bool rep = b_bi > 0 && mv == cv;  // screencap.cpp:1202
+                    if (rep) flags |= 0x100; else cv = mv;
+                    if (lane == 0) w.mvs[b_bi] = make_int2((int)(int16_t)(mv & 0xFFFF), mv >> 16);
                 }
-                b.bt = bt;
+                if (lane == i) {
+                    out_v = mv;
+                    out_flags = flags;
+                    out_prev = found ? -1 : prev_nonmv;
+                }
+                if (!found) prev_nonmv = k0 + i;
             }
-            if (found) {
-                if (!(bi > 0 && mx == cmx && my == cmy)) { cmx = mx; cmy = my; }
-            } else
-                prev_nonmv = k;
+            if (lane < cnt) {
+                ChgBlock& b = w.blocks[off + k];
+                b.bt = (uint8_t)(out_flags & 0xFF);
+                b.rep = (uint8_t)(out_flags >> 8);
+                b.mx = (int16_t)(out_v & 0xFFFF);
+                b.my = (int16_t)(out_v >> 16);
+                b.prev_nonmv = out_prev;
+            }
             __syncwarp();
+            k0 += cnt;
         }
         __threadfence();  // mvs[] of this frame visible before the next frame reads it
     }
@@ -511,8 +623,15 @@ __global__ void __launch_bounds__(128) k_p_emit(PWork w) {
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
     if (w.total_blocks > 0) {
         k_mv_search<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        if (w.tm) w.tm->mark("mv_search");
+        k_mv_cands<<<w.n_pframes, 32, 0, st>>>(w);
+        k_mv_prematch<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        *launches += 2;
+        if (w.tm) w.tm->mark("mv_prematch");
         k_mv_resolve<<<1, 32, 0, st>>>(w);
+        if (w.tm) w.tm->mark("mv_resolve");
         k_p_runs<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
+        if (w.tm) w.tm->mark("p_runs");
         *launches += 3;
     }
     if (w.n_pframes > 0) {
