@@ -70,6 +70,19 @@ __device__ __forceinline__ uint32_t frame_px(const DecWork& w, int src, int x, i
     const uint8_t* base = src >= 0 ? w.out + (size_t)src * w.g.frame_bytes : w.prev0;
     return load_px(base, w.g, x, y);
 }
+struct PixSrc {
+    const uint8_t* base;
+    uint32_t clr;
+    bool flat;
+};
+__device__ __forceinline__ PixSrc resolve_src(const DecWork& w, int src) {
+    PixSrc s;
+    s.flat = src >= 0 && w.frames[src].kind == DK_FLAT;
+    s.clr = s.flat ? w.frames[src].flat_clr : 0u;
+    s.base = src >= 0 ? w.out + (size_t)src * w.g.frame_bytes : w.prev0;
+    return s;
+}
+__device__ __forceinline__ uint32_t src_px(const PixSrc& s, const Geo& g, int x, int y) { return s.flat ? s.clr : load_px(s.base, g, x, y); }
 // pixel of the frame being decoded (only valid for pixels already reconstructed or unchanged)
 __device__ __forceinline__ uint32_t cur_px(const ChainCtx& c, int x, int y) {
     const int b = (y >> 4) * c.w->g.nbx + (x >> 4);
@@ -82,7 +95,7 @@ __device__ __forceinline__ uint32_t prev_px(const ChainCtx& c, int x, int y) {
     return frame_px(*c.w, s, x, y);
 }
 __device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, int y, uint32_t v) {
-    uint8_t* p = frame + (size_t)y * g.pitch + (size_t)x * g.bpp;
+    uint8_t* p = frame + (uint32_t)(y * g.pitch + x * g.bpp);
     if (g.bpp == 4)
         *reinterpret_cast<uint32_t*>(p) = v | 0xFF000000u;  // alpha := 255, screencap.cpp:1721
     else {
@@ -95,16 +108,27 @@ __device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, in
 // lanes (every lane executes the same arithmetic on the same values), so no broadcast is needed
 // between symbols; only model *stores* are done by one lane.
 //
-// The 21 fixed tables live in shared memory for the whole chain (3192 u16 entries x 3).  A symbol
-// search is warp-parallel: each lane compares its 8 (or 16) cumulative frequencies against the rANS
-// slot with one 128-bit shared load + SIMD halfword compares, a REDUX adds the counts.  A table
-// rebuild (every ~128 symbols of that table, ans_contexts.h:1075-1090) is a warp scan.
+// With one resident warp per chain the decoder is bound by the latency of its dependent
+// instruction chain, so the per-symbol path is kept to two shared-memory loads:
+//   * the 21 fixed tables live in shared memory for the whole chain: fc[] = freq<<16|cum per symbol,
+//     cnt[] the adaptive counters, and -- because a table's intervals are frozen between rescales
+//     (ans_contexts.h:1070-1091) -- a direct slot -> symbol map lut[4096] per table that is rebuilt
+//     together with the table (every ~128 symbols of that table, by the whole warp).  A symbol is
+//     then  v = x & 4095;  sym = lut[v];  fc = fc[sym];  x = freq*(x>>12) + v - cum.
+//   * "events until the next rescale" is a countdown per table (the rescale instant depends only on
+//     the number of events, each adds 16 to cntsum).
 constexpr int FX_TOTAL = 3192;
+constexpr int LUT_ROW = 32 * 132;  // 128 slots per lane + 4 bytes padding: conflict-free fills
+constexpr int N_LUT = 19;          // every table except the two 512-symbol MV tables
 __host__ __device__ constexpr int fx_off(int t) {
     return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
 }
+__host__ __device__ constexpr int fx_lut(int t) { return t < 13 ? t : t - 2; }
 struct FixedSmem {
-    uint16_t cnt[FX_TOTAL], freq[FX_TOTAL], cum[FX_TOTAL];
+    uint32_t fc[FX_TOTAL];
+    uint16_t cnt[FX_TOTAL];
+    int left[24];
+    uint8_t lut[N_LUT][LUT_ROW];
 };
 
 #ifdef SCPR_PROF
@@ -128,7 +152,6 @@ struct Ent {
     uint32_t cx, cx1;
     ModelState* m;
     FixedSmem* fs;
-    int cs;  // lane t < 21 holds cntsum of fixed table t
     int f0;
     int lane;
 };
@@ -149,91 +172,171 @@ __device__ __forceinline__ void rdec_advance(Ent& e, uint32_t start, uint32_t fr
     e.x = x;
 }
 
-// number of the 8 packed u16 in q that are <= v
-__device__ __forceinline__ int count_le8(uint4 q, uint32_t vv) {
-    return (__popc(__vcmpleu2(q.x, vv)) + __popc(__vcmpleu2(q.y, vv)) + __popc(__vcmpleu2(q.z, vv)) + __popc(__vcmpleu2(q.w, vv))) >> 4;
-}
-
-__device__ __forceinline__ void fixed_rebuild_smem(FixedSmem& fs, int off, int nsym, int lane, int& cntsum) {
-    const int per = (nsym + 31) >> 5;
-    const int b = lane * per;
-    uint32_t sum = 0;
-    for (int j = 0; j < per; j++)
-        if (b + j < nsym) sum += fs.cnt[off + b + j];
-    uint32_t inc = sum;
+// (Re)build the derived data of fixed table t from its counters: `rescale` applies the
+// FixedSizeRansCtx rescale (freq := cnt, cum := prefix, cnt -= freq>>1, ans_contexts.h:1075-1090);
+// without it the intervals in fc[] are kept (table just loaded).  Then the countdown and the
+// slot -> symbol map.  Whole warp.
+__device__ __noinline__ void fixed_rebuild(FixedSmem& fs, int t, int lane, bool rescale) {
+    const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+    const int per = (nsym + 31) >> 5, b = lane * per;
+    uint32_t ns = 0;
+    if (rescale) {
+        uint32_t sum = 0;
+        for (int j = 0; j < per; j++)
+            if (b + j < nsym) sum += fs.cnt[off + b + j];
+        uint32_t inc = sum;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    uint32_t cf = inc - sum, ns = 0;
-    for (int j = 0; j < per; j++)
-        if (b + j < nsym) {
-            const uint32_t fr = fs.cnt[off + b + j];
-            fs.cum[off + b + j] = (uint16_t)cf;
-            fs.freq[off + b + j] = (uint16_t)fr;
-            cf += fr;
-            const uint32_t nc = fr - (fr >> 1);
-            fs.cnt[off + b + j] = (uint16_t)nc;
-            ns += nc;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += u;
         }
-    cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
+        uint32_t cf = inc - sum;
+        for (int j = 0; j < per; j++)
+            if (b + j < nsym) {
+                const uint32_t fr = fs.cnt[off + b + j];
+                fs.fc[off + b + j] = (fr << 16) | cf;
+                cf += fr;
+                const uint32_t nc = fr - (fr >> 1);
+                fs.cnt[off + b + j] = (uint16_t)nc;
+                ns += nc;
+            }
+    } else {
+        for (int j = 0; j < per; j++)
+            if (b + j < nsym) ns += fs.cnt[off + b + j];
+    }
+    const int cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
+    if (lane == 0) fs.left[t] = (PROB_SCALE - 16 - cntsum) / 16 + 1;  // events until cntsum + 16 > 4096
+    __syncwarp();
+    if (nsym > 256) return;
+    // slot -> symbol map: lane owns slots [128*lane, 128*lane + 128)
+    uint8_t* row = fs.lut[fx_lut(t)] + lane * 132;
+    const int s0 = lane * 128;
+    int lo = 0, hi = nsym - 1;  // last symbol whose cum <= s0
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)(fs.fc[off + mid] & 0xFFFFu) <= s0) lo = mid; else hi = mid - 1;
+    }
+    int j = lo;
+    uint32_t fcj = fs.fc[off + j];
+    int endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
+    for (int wd = 0; wd < 32; wd++) {
+        const int s = s0 + 4 * wd;
+        uint32_t word;
+        if (s + 4 <= endj || j == nsym - 1)
+            word = (uint32_t)j * 0x01010101u;
+        else {
+            word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                while (s + k >= endj && j < nsym - 1) {
+                    j++;
+                    fcj = fs.fc[off + j];
+                    endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
+                }
+                word |= (uint32_t)j << (8 * k);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(row + 4 * wd) = word;
+    }
+    __syncwarp();
 }
 
-__device__ inline int dec_fixed(Ent& e, int id) {  // decodeF, screencap.h:346-359
+// decodeF (screencap.h:346-359) for table t (0..20) with NSYM symbols; off = fx_off(t), row = fx_lut(t)
+template <int NSYM>
+__device__ __forceinline__ int dec_fx(Ent& e, int t, int off, int row) {
     PROF_T0
-    const int t = id - CX_NTAB, off = fx_off(t), nsym = fixed_nsym(id), lane = e.lane;
     FixedSmem& fs = *e.fs;
-    const uint32_t v = e.x & (PROB_SCALE - 1), vv = v | (v << 16);
+    const uint32_t v = e.x & (PROB_SCALE - 1);
     int j;
-    if (nsym == 256) {
-        const uint4 q = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 8]);
-        j = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)count_le8(q, vv)) - 1;
-    } else if (nsym == 512) {
-        const uint4 q0 = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 16]);
-        const uint4 q1 = *reinterpret_cast<const uint4*>(&fs.cum[off + lane * 16 + 8]);
-        j = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(count_le8(q0, vv) + count_le8(q1, vv))) - 1;
-    } else {
-        const bool le = lane < nsym && fs.cum[off + lane] <= v;
-        j = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
+    if (NSYM <= 256) {
+        j = fs.lut[row][v + ((v >> 7) << 2)];
+    } else {  // 512 symbols: two ballot levels over the cumulative frequencies
+        const bool le = (fs.fc[off + e.lane * 16] & 0xFFFFu) <= v;
+        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
+        const bool le2 = e.lane < 16 && (fs.fc[off + L * 16 + (e.lane & 15)] & 0xFFFFu) <= v;
+        j = L * 16 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
     }
-    const uint32_t freq = fs.freq[off + j], cum = fs.cum[off + j];
-    int cs = __shfl_sync(0xFFFFFFFFu, e.cs, t) + 16;
-    if (lane == 0) fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
-    if (cs + 16 > PROB_SCALE) {
-        __syncwarp();
-        fixed_rebuild_smem(fs, off, nsym, lane, cs);
-        __syncwarp();
+    const uint32_t fc = fs.fc[off + j];
+    const int left = fs.left[t] - 1;
+    if (e.lane == 0) {
+        fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
+        fs.left[t] = left;
     }
-    if (lane == t) e.cs = cs;
-    rdec_advance(e, cum, freq);
+    rdec_advance(e, fc & 0xFFFFu, fc >> 16);
     rdec_count(e);
+    __syncwarp();
+    if (left == 0) fixed_rebuild(fs, t, e.lane, true);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return j;
 }
+template <int NSYM, int T>
+__device__ __forceinline__ int dec_fxc(Ent& e) { return dec_fx<NSYM>(e, T, fx_off(T), fx_lut(T)); }
+__device__ __forceinline__ int dec_n(Ent& e, int ptype) { return dec_fx<256>(e, ptype, ptype << 8, ptype); }
+__device__ __forceinline__ int dec_ptype(Ent& e, int last) { return dec_fx<6>(e, 15 + last, 3144 + 8 * last, 13 + last); }
 
-__device__ inline int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
+// ---- colour contexts (global memory, L1 resident working set) --------------------------------------------
+// find: uniform (all lanes); update: lane 0.
+__device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
     PROF_T0
     ColorState& x = e.m->color[id];
     const int kind = x.kind;
     int c;
-    if (kind >= 4) {
+    if (kind >= 6) {  // flat table: two ballot levels over cum[256], then lane 0 updates
         const uint32_t v = e.x & (PROB_SCALE - 1);
-        uint32_t iv = 0;
-        if (kind >= 6) {  // flat table: warp-parallel search, 8 cumulative frequencies per lane
-            const uint4 q = *reinterpret_cast<const uint4*>(&x.cum[e.lane * 8]);
-            c = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)count_le8(q, v | (v << 16))) - 1;
-            if (e.lane == 0) iv = cc_encode_counted(x, c);
-        } else {
-            c = 0;
-            if (e.lane == 0) {
-                c = cc_find(x, (int)v);
-                iv = cc_encode_counted(x, c);
-            }
-            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+        const bool le = x.cum[e.lane * 8] <= v;
+        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
+        const bool le2 = e.lane < 8 && x.cum[L * 8 + (e.lane & 7)] <= v;
+        c = L * 8 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
+        const uint32_t freq = x.freq[c], cum = x.cum[c];
+        if (e.lane == 0) cc_encode_counted(x, c);
+        rdec_advance(e, cum, freq);
+    } else if (kind >= 4) {  // SmallContext: walk the (<= 16) sorted symbols, ans_contexts.h:238-283
+        const uint32_t v0 = e.x & (PROB_SCALE - 1);
+        const int d = x.d, maxpos = x.maxpos;
+        int totFr = x.cntsum;
+        if (kind == 4) {
+            totFr = 256 - d;
+            for (int i = 0; i < 4; i++) totFr += x.sfreq[i];
         }
-        iv = __shfl_sync(0xFFFFFFFFu, iv, 0);
-        rdec_advance(e, iv >> 16, iv & 0xFFFFu);
+        int shift = 0, tot = totFr;
+        while (tot <= PROB_SCALE / 2) {
+            tot <<= 1;
+            shift++;
+        }
+        const int v = (int)(v0 >> shift);
+        const int bonus = (PROB_SCALE - tot) >> shift;
+        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1;
+        bool found = false;
+        c = -1;
+        for (; pos < d; pos++) {
+            const int sy = x.ssym[pos];
+            const int startFr = cumFr + sy - lastSymb;
+            if (v < startFr) break;
+            fr = (x.sfreq[pos] + (pos == maxpos ? bonus : 0)) & 0xFFFF;
+            if (startFr + fr > v) {
+                c = sy;
+                cumFr = startFr;
+                found = true;
+                break;
+            }
+            cumFr = startFr + fr;
+            lastSymb = sy + 1;
+        }
+        if (!found) {  // a symbol not met yet: width 1
+            c = lastSymb + v - cumFr;
+            cumFr = v;
+            fr = 1;
+        }
+        if (e.lane == 0) {
+            if (found && totFr + 100 <= PROB_SCALE) {  // hot path: count, no rescale (ans_contexts.h:211-214)
+                const int nf = x.sfreq[pos] + 50;
+                x.sfreq[pos] = (uint16_t)nf;
+                if (kind == 5) x.cntsum = totFr + 50;
+                if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;
+            } else
+                cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
+        }
+        rdec_advance(e, (uint32_t)(cumFr << shift) & 0xFFFFu, (uint32_t)(fr << shift) & 0xFFFFu);
     } else {
         c = *e.p++;
         if (e.lane == 0) cc_update_raw(x, c, e.f0);
@@ -249,14 +352,16 @@ __device__ inline int dec_bool(Ent& e) {  // decodeBool
     rdec_count(e);
     return flag;
 }
-__device__ inline uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
-    const uint32_t r = (uint32_t)dec_color(e, 0 * 4096 + (int)(e.cx + e.cx1));
-    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = r >> 2;
-    const uint32_t g = (uint32_t)dec_color(e, 1 * 4096 + (int)(e.cx + e.cx1));
-    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = g >> 2;
-    const uint32_t b = (uint32_t)dec_color(e, 2 * 4096 + (int)(e.cx + e.cx1));
-    e.cx1 = (e.cx << 6) & 0xFC0; e.cx = b >> 2;
-    return r | (g << 8) | (b << 16);
+__device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
+    uint32_t px = 0;
+#pragma unroll 1
+    for (int ch = 0; ch < 3; ch++) {  // one copy of the colour decoder in the instruction stream
+        const uint32_t v = (uint32_t)dec_color(e, ch * 4096 + (int)(e.cx + e.cx1));
+        e.cx1 = (e.cx << 6) & 0xFC0;
+        e.cx = v >> 2;
+        px |= v << (8 * ch);
+    }
+    return px;
 }
 __device__ __forceinline__ void set_cx_from(Ent& e, uint32_t px) {  // screencap.cpp:488-493, 1417-1419
     e.cx = ((px >> 8) & 255) >> 2;
@@ -275,72 +380,105 @@ __device__ __forceinline__ uint32_t grad_px(uint32_t l, uint32_t t, uint32_t tl)
 }
 
 // ---- I frame (DecompressI, screencap.cpp:414-498) --------------------------------------------------
-// q = raster index; all neighbours are pixels of this frame: left = q-1 (lasti), top = q-X,
-// top-left = q-X-1 (byte offset -stride-3; with row padding the x==0 case reads padding, A.2).
+// Runs are laid along the raster; all neighbours are pixels of this frame: left = the previous
+// pixel in raster order (lasti), top = (x, y-1), top-left = byte offset -stride-3, i.e. (x-1, y-1),
+// which for x == 0 is the tail of row y-2 (with row padding it straddles padding bytes, A.2).
+struct IPos {
+    int x, y;
+};
+__device__ __forceinline__ IPos ipos_add(IPos p, int i, int X) {
+    p.x += i;
+    while (p.x >= X) {
+        p.x -= X;
+        p.y++;
+    }
+    return p;
+}
+__device__ __forceinline__ IPos ipos_prev(IPos p, int X) {
+    if (p.x > 0) return IPos{p.x - 1, p.y};
+    return IPos{X - 1, p.y - 1};
+}
+__device__ __noinline__ uint32_t tl_padded(const uint8_t* frame, const Geo& g, int y) {
+    // x == 0 with row padding: bytes (y-1)*stride24 - 3 .. of the RGB24 view, padding reads as 0
+    const int stride24 = (g.X * 3 + 3) & ~3;
+    uint32_t v = 0;
+    const int o = y * stride24 - stride24 - 3;
+    for (int k = 0; k < 3; k++) {
+        const int ok = o + k;
+        const int row = ok / stride24, col = ok % stride24;
+        uint32_t b = 0;
+        if (col < 3 * g.X) b = (load_px(frame, g, col / 3, row) >> (8 * (col % 3))) & 255;
+        v |= b << (8 * k);
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t tl_at(const uint8_t* frame, const Geo& g, IPos p, bool padded) {
+    if (p.x > 0) return load_px(frame, g, p.x - 1, p.y - 1);
+    if (!padded) return load_px(frame, g, g.X - 1, p.y - 2);
+    return tl_padded(frame, g, p.y);
+}
+
 __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     const Geo& g = w.g;
-    const long total = (long)g.X * g.Y;
-    const int stride24 = (g.X * 3 + 3) & ~3;
-    const bool padded = stride24 != g.X * 3;
-    auto px_at = [&](long q) { return load_px(frame, g, (int)(q % g.X), (int)(q / g.X)); };
-    auto tl_at = [&](long q) -> uint32_t {
-        const int x = (int)(q % g.X), y = (int)(q / g.X);
-        if (!padded || x > 0) return px_at(q - g.X - 1);
-        // bytes (y-1)*stride-3 .. : tail of row y-2 incl. zero padding.  The frame is in output
-        // format, so rebuild the RGB24 view byte by byte.
-        uint32_t v = 0;
-        const long o = (long)y * stride24 - stride24 - 3;
-        for (int k = 0; k < 3; k++) {
-            const long ok = o + k;
-            const int row = (int)(ok / stride24), col = (int)(ok % stride24);
-            uint32_t b = 0;
-            if (col < 3 * g.X) b = (load_px(frame, g, col / 3, row) >> (8 * (col % 3))) & 255;
-            v |= b << (8 * k);
-        }
-        return v;
-    };
-    long q = 0;
+    const int X = g.X, Y = g.Y;
+    const bool padded = ((X * 3 + 3) & ~3) != X * 3;
+    IPos p{0, 0};
     int ptype = 0;
+    int hdr = X + 1;
     // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
-    while (q < g.X + 1) {
-        uint32_t c = dec_rgb(e);
-        int n = dec_fixed(e, CX_NTAB + 0);
-        if (q + n > total) n = (int)(total - q);  // corrupt input guard
+    while (hdr > 0) {
+        const uint32_t c = dec_rgb(e);
+        const int n = dec_n(e, 0);
         if (n <= 0) return;
-        for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
-        q += n;
+        for (int i = lane; i < n; i += 32) {
+            const IPos q = ipos_add(p, i, X);
+            if (q.y < Y) store_px(frame, g, q.x, q.y, c);
+        }
+        p = ipos_add(p, n, X);
+        hdr -= n;
         __syncwarp();
     }
-    while (q < total) {
+    while (p.y < Y) {
         uint32_t c = 0;
-        ptype = dec_fixed(e, CX_PTYPE + ptype);
+        ptype = dec_ptype(e, ptype);
         if (!ptype) c = dec_rgb(e);
-        int n = dec_fixed(e, CX_NTAB + ptype);
-        if (q + n > total) n = (int)(total - q);  // corrupt input guard
+        const int n = dec_n(e, ptype);
         if (n <= 0) return;
         PROF_T0
         if (ptype == 0 || ptype == 1) {
-            if (ptype == 1) c = px_at(q - 1);
-            for (int i = lane; i < n; i += 32) store_px(frame, g, (int)((q + i) % g.X), (int)((q + i) / g.X), c);
-        } else if (n < g.X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
+            if (ptype == 1) {
+                const IPos l = ipos_prev(p, X);
+                c = load_px(frame, g, l.x, l.y);
+            }
             for (int i = lane; i < n; i += 32) {
-                const long qq = q + i;
-                store_px(frame, g, (int)(qq % g.X), (int)(qq / g.X), ptype == 2 ? px_at(qq - g.X) : tl_at(qq));
+                const IPos q = ipos_add(p, i, X);
+                if (q.y < Y) store_px(frame, g, q.x, q.y, c);
+            }
+        } else if (n < X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
+            for (int i = lane; i < n; i += 32) {
+                const IPos q = ipos_add(p, i, X);
+                if (q.y < Y) store_px(frame, g, q.x, q.y, ptype == 2 ? load_px(frame, g, q.x, q.y - 1) : tl_at(frame, g, q, padded));
             }
         } else {  // gradient chains through the left pixel; tiny frames may read their own run
-            if (lane == 0)
-                for (int i = 0; i < n; i++) {
-                    const long qq = q + i;
+            if (lane == 0) {
+                IPos q = p;
+                for (int i = 0; i < n && q.y < Y; i++) {
                     uint32_t v;
-                    if (ptype == 2) v = px_at(qq - g.X);
-                    else if (ptype == 5) v = tl_at(qq);
-                    else v = grad_px(px_at(qq - 1), px_at(qq - g.X), tl_at(qq));
-                    store_px(frame, g, (int)(qq % g.X), (int)(qq / g.X), v);
+                    if (ptype == 2) v = load_px(frame, g, q.x, q.y - 1);
+                    else if (ptype == 5) v = tl_at(frame, g, q, padded);
+                    else {
+                        const IPos l = ipos_prev(q, X);
+                        v = grad_px(load_px(frame, g, l.x, l.y), load_px(frame, g, q.x, q.y - 1), tl_at(frame, g, q, padded));
+                    }
+                    store_px(frame, g, q.x, q.y, v);
+                    q = ipos_add(q, 1, X);
                 }
+            }
         }
         __syncwarp();
-        q += n;
-        set_cx_from(e, px_at(q - 1));
+        p = ipos_add(p, n, X);
+        const IPos l = ipos_prev(p, X);
+        set_cx_from(e, load_px(frame, g, l.x, l.y));
         PROF_ADD(c_ifill)
     }
 }
@@ -350,15 +488,15 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                          int lane) {
     const Geo& g = w.g;
     const long long thdr__ = clock64();
-    int t0 = dec_fixed(e, CX_XX);
-    const int xx1 = (dec_fixed(e, CX_XX) << 8) + t0;
-    t0 = dec_fixed(e, CX_XX);
-    int xx2 = (dec_fixed(e, CX_XX) << 8) + t0;
+    int t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
+    const int xx1 = (dec_fxc<256, CX_XX - CX_NTAB>(e) << 8) + t0;
+    t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
+    int xx2 = (dec_fxc<256, CX_XX - CX_NTAB>(e) << 8) + t0;
     if (xx2 >= g.nb) xx2 = g.nb - 1;  // corrupt input guard
     // block types of [xx1, xx2] as (type, run) pairs (screencap.cpp:1306-1313)
     for (int x = xx1; x <= xx2;) {
-        const int c = dec_fixed(e, CX_BT);
-        const int n = dec_fixed(e, CX_NTAB2);
+        const int c = dec_fxc<5, CX_BT - CX_NTAB>(e);
+        const int n = dec_fxc<256, CX_NTAB2 - CX_NTAB>(e);
         if (n <= 0) break;
         for (int i = lane; i < n && x + i < g.nb; i += 32) s_bts[x + i] = (uint8_t)c;
         x += n;
@@ -385,39 +523,49 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
         PROF_CNT(n_blocks)
         { PROF_T0
-        for (int p = lane; p < 17 * 17; p += 32) {
-            const int ty = p / 17, tx = p - ty * 17;
-            const int x = bx0 + tx - 1, y = by0 + ty - 1;
-            uint32_t v = 0;
-            if (x >= 0 && y >= 0 && x < g.X && y < g.Y) {
-                if (tx == 0 || ty == 0) v = cur_px(cc, x, y);
-                else if ((bt - 1) & 1) v = prev_px(cc, x, y);  // partial block: starts as a copy of prev
+        {   // the tile touches four blocks: resolve where each one's pixels live once, then load
+            const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
+            const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? cc.src_cur[bA] : -1);
+            const PixSrc sT = resolve_src(w, by > 0 ? cc.src_cur[bT] : -1);
+            const PixSrc sL = resolve_src(w, bx > 0 ? cc.src_cur[bL] : -1);
+            const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
+            const bool partial = (bt - 1) & 1;
+            for (int p = lane; p < 17 * 17; p += 32) {
+                const int ty = p / 17, tx = p - ty * 17;
+                const int x = bx0 + tx - 1, y = by0 + ty - 1;
+                uint32_t v = 0;
+                if (x >= 0 && y >= 0 && x < g.X && y < g.Y) {
+                    if (ty == 0) v = src_px(tx == 0 ? sA : sT, g, x, y);
+                    else if (tx == 0) v = src_px(sL, g, x, y);
+                    else if (partial) v = src_px(sP, g, x, y);  // partial block: starts as a copy of prev
+                }
+                tile[ty][tx] = v;
             }
-            tile[ty][tx] = v;
         }
         __syncwarp();
         PROF_ADD(c_tile) }
         if ((bt - 1) & 1) {
-            x1 = bx0 + dec_fixed(e, CX_SXY + 0);
-            y1 = by0 + dec_fixed(e, CX_SXY + 1);
-            x2 = bx0 + dec_fixed(e, CX_SXY + 2) + 1;
-            y2 = by0 + dec_fixed(e, CX_SXY + 3) + 1;
+            x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
+            y1 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 1>(e);
+            x2 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 2>(e) + 1;
+            y2 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 3>(e) + 1;
             if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
             if (y2 > by0 + bh) y2 = by0 + bh;
             if (x1 >= x2) x1 = x2 - 1;
             if (y1 >= y2) y1 = y2 - 1;
         }
         const int sw = x2 - x1, sh = y2 - y1;
+        const uint32_t swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;  // idx / sw == (idx * swinv) >> 16 for idx < 256
         if ((bt - 1) & 2) {  // motion vector block
             PROF_T0
             int mx = lastmx, my = lastmy;
             if (!dec_bool(e)) {
-                mx = dec_fixed(e, CX_MV + 0) - 256;
-                my = dec_fixed(e, CX_MV + 1) - 256;
+                mx = dec_fxc<512, CX_MV - CX_NTAB + 0>(e) - 256;
+                my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
             }
             lastmx = mx; lastmy = my;
             for (int p = lane; p < sw * sh; p += 32) {
-                const int xx = p % sw, yy = p / sw;
+                const int yy = (int)(((uint32_t)p * swinv) >> 16), xx = p - yy * sw;
                 int sx = x1 + xx + mx, sy = y1 + yy + my;
                 sx = min(max(sx, 0), g.X - 1); sy = min(max(sy, 0), g.Y - 1);  // corrupt input guard
                 tile[1 + y1 - by0 + yy][1 + x1 - bx0 + xx] = prev_px(cc, sx, sy);
@@ -430,26 +578,26 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             const int ox = 1 + x1 - bx0, oy = 1 + y1 - by0;
             while (pos < npx) {
                 uint32_t c = 0;
-                ptype = dec_fixed(e, CX_PTYPE + ptype);
+                ptype = dec_ptype(e, ptype);
                 if (!ptype) c = dec_rgb(e);
-                int n = dec_fixed(e, CX_NTAB + ptype);
+                int n = dec_n(e, ptype);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
                 uint32_t v = c;
                 if (ptype == 0 || ptype == 3) {  // no dependence on pixels of this run: lanes fill in parallel
                     for (int i = lane; i < n; i += 32) {
-                        const int xx = (pos + i) % sw, yy = (pos + i) / sw;
+                        const int yy = (int)(((uint32_t)(pos + i) * swinv) >> 16), xx = pos + i - yy * sw;
                         uint32_t* t = &tile[oy + yy][ox + xx];
                         if (ptype == 3) t[0] = (bt - 1) & 1 ? t[0] : prev_px(cc, x1 + xx, y1 + yy);
                         else t[0] = c;
                     }
                     __syncwarp();
-                    const int li = pos + n - 1;
-                    v = tile[oy + li / sw][ox + li % sw];
+                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                    v = tile[oy + ly][ox + li - ly * sw];
                 } else {
-                    if (lane == 0)
+                    if (lane == 0) {
+                        int yy = (int)(((uint32_t)pos * swinv) >> 16), xx = pos - yy * sw;
                         for (int i = 0; i < n; i++) {
-                            const int xx = (pos + i) % sw, yy = (pos + i) / sw;
                             uint32_t* t = &tile[oy + yy][ox + xx];
                             switch (ptype) {
                             case 1: v = t[-1]; break;
@@ -458,10 +606,15 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                             case 5: v = t[-18]; break;
                             }
                             t[0] = v;
+                            if (++xx == sw) {
+                                xx = 0;
+                                yy++;
+                            }
                         }
+                    }
                     __syncwarp();
-                    const int li = pos + n - 1;
-                    v = tile[oy + li / sw][ox + li % sw];
+                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                    v = tile[oy + ly][ox + li - ly * sw];
                 }
                 set_cx_from(e, v);
                 pos += n;
@@ -471,9 +624,13 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         __syncwarp();
         // write the whole block and hand its ownership to this frame
         { PROF_T0
-        for (int p = lane; p < bw * bh; p += 32) {
-            const int xx = p % bw, yy = p / bw;
-            store_px(frame, g, bx0 + xx, by0 + yy, tile[1 + yy][1 + xx]);
+        if (bw == 16) {
+            for (int p = lane; p < 16 * bh; p += 32) store_px(frame, g, bx0 + (p & 15), by0 + (p >> 4), tile[1 + (p >> 4)][1 + (p & 15)]);
+        } else {
+            for (int p = lane; p < bw * bh; p += 32) {
+                const int xx = p % bw, yy = p / bw;
+                store_px(frame, g, bx0 + xx, by0 + yy, tile[1 + yy][1 + xx]);
+            }
         }
         if (lane == 0) {
             if (cc.stamp[bi] != f) {
@@ -518,7 +675,6 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     e.p = nullptr;
     e.fs = fs;
     e.lane = lane;
-    e.cs = 0;
 #ifdef SCPR_PROF
     const long long tk0 = clock64();
 #endif
@@ -528,12 +684,11 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
         for (int i = lane; i < nsym; i += 32) {
             fs->cnt[off + i] = g0.cnt[i];
-            fs->freq[off + i] = g0.freq[i];
-            fs->cum[off + i] = g0.cum[i];
+            fs->fc[off + i] = ((uint32_t)g0.freq[i] << 16) | g0.cum[i];
         }
-        if (lane == t) e.cs = g0.cntsum;
     }
     __syncwarp();
+    for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(*fs, t, lane, false);
     for (int f = ch.first; f < ch.first + ch.count; f++) {
         const DecFrame df = w.frames[f];
         uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
@@ -547,12 +702,11 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
                     const int fr = PROB_SCALE / nsym, c0 = fr - (fr >> 1);
                     for (int i = lane; i < nsym; i += 32) {
                         fs->cnt[off + i] = (uint16_t)c0;
-                        fs->freq[off + i] = (uint16_t)fr;
-                        fs->cum[off + i] = (uint16_t)(fr * i);
+                        fs->fc[off + i] = ((uint32_t)fr << 16) | (uint32_t)(fr * i);
                     }
-                    if (lane == t) e.cs = c0 * nsym;
                 }
                 __syncwarp();
+                for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(*fs, t, lane, false);
             }
             for (int i = lane; i < g.nb; i += 32) {  // the whole frame is new
                 cc.src_prev[i] = cc.src_cur[i];
@@ -588,13 +742,16 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         FixedState& g0 = e.m->fx[t];
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+        uint32_t sum = 0;
         for (int i = lane; i < nsym; i += 32) {
             g0.cnt[i] = fs->cnt[off + i];
-            g0.freq[i] = fs->freq[off + i];
-            g0.cum[i] = fs->cum[off + i];
+            g0.freq[i] = (uint16_t)(fs->fc[off + i] >> 16);
+            g0.cum[i] = (uint16_t)(fs->fc[off + i] & 0xFFFFu);
+            sum += fs->cnt[off + i];
         }
-        if (lane == t) {
-            g0.cntsum = e.cs;
+        sum = __reduce_add_sync(0xFFFFFFFFu, sum);
+        if (lane == 0) {
+            g0.cntsum = (int)sum;  // cntsum is the sum of the counters at all times
             g0.nsym = nsym;
         }
     }
@@ -788,7 +945,7 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.n = n;
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
     const size_t smem = sizeof(FixedSmem) + 17 * 17 * 4 + (size_t)g.nb + 16;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(st);
     k_dec_chain<<<n_chains, 32, smem, st>>>(w);
     tm.mark("chain");

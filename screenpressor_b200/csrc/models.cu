@@ -220,27 +220,203 @@ __global__ void __launch_bounds__(32) k_replay_fixed(ReplayWork w, const uint32_
     }
 }
 
-// ---- colour contexts: one thread per (context, chain) ---------------------------------------------------
+// ---- colour contexts: one warp per (context, chain) ------------------------------------------------------
+// A context's events are replayed in order, but not one at a time:
+//  * kinds 4/5 (SmallContext, <= 16 symbols, every event changes the frequencies): up to 32 events per
+//    step.  Inside a step the frequency of symbol k seen by event t is f_k + 50 * (#earlier events of the
+//    step with symbol k), the running total is tot + 50 t, and `maxpos` only moves when some symbol
+//    overtakes it -- so lanes compute their events' intervals independently from ballots / match masks,
+//    and a step is cut at the first event that (a) meets a new symbol, (b) triggers the rescale
+//    (tot + 100 > 4096 after its update, ans_contexts.h:214) or (c) overtakes maxpos (:212-213).
+//  * kinds 6/7 (flat tables): epoch-wise like the fixed tables; kind 6 additionally tracks the number of
+//    distinct symbols met (promotion to kind 7 at the 41st, ans_contexts.h:631) with match masks.
+//  * everything else (raw kinds 0..3, new symbols, promotions) takes the one-event path on lane 0.
+__device__ __forceinline__ int shift_for(int tot) {
+    int shift = 0;
+    while (tot <= PROB_SCALE / 2) {
+        tot <<= 1;
+        shift++;
+    }
+    return shift;
+}
+
 __global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32_t* __restrict__ seg_off) {
-    const int ctx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int ctx = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int ch = blockIdx.y;
-    if (ctx >= NUM_COLOR_CX) return;
     const ChainDesc cd = w.chains[ch];
     const uint32_t* seg = seg_off + (size_t)ch * (NUM_CX + 1);
     const uint32_t m = seg[ctx + 1] - seg[ctx];
     ColorState& x = reinterpret_cast<ModelState*>(w.states + (size_t)cd.state * sizeof(ModelState))->color[ctx];
-    if (cd.renew) x.kind = 0;  // Context::renew, ans_contexts.h:1050
-    const uint32_t pos = cd.ev_off + seg[ctx];
-    for (uint32_t i = 0; i < m; i++) {
-        const uint32_t idx = w.sorted[pos + i];
-        const int c = (int)(w.events[idx] & 0xFFu);
-        uint32_t iv;
-        if (x.kind < 4) {  // no statistics yet: the byte goes out raw (screencap.h:313-315)
-            cc_update_raw(x, c, w.f0);
-            iv = make_iv(0, (uint32_t)c);
-        } else
-            iv = cc_encode_counted(x, c);
-        w.intervals[idx] = iv;
+    if (cd.renew && lane == 0) x.kind = 0;  // Context::renew, ans_contexts.h:1050
+    if (m == 0) return;
+    __syncwarp();
+    const uint32_t pos0 = cd.ev_off + seg[ctx];
+    const uint32_t lt = (1u << lane) - 1;
+    uint32_t i = 0;
+    while (i < m) {
+        const int kind = x.kind;
+        // this step's events: lane t holds event i + t
+        const bool valid = i + lane < m;
+        uint32_t idx = 0;
+        int c = -1;
+        if (valid) {
+            idx = w.sorted[pos0 + i + lane];
+            c = (int)(w.events[idx] & 0xFFu);
+        }
+        if (kind == 4 || kind == 5) {
+            const int d = x.d, maxpos = x.maxpos;
+            const int ls = lane < d ? x.ssym[lane] : -1;            // lane k: symbol k
+            const int lf = lane < d ? x.sfreq[lane] : 0;            //         and its frequency
+            int tot = x.cntsum;
+            if (kind == 4) tot = 256 - d + (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)lf);  // ans_contexts.h:303
+            // position of each event's symbol
+            int pos = -1;
+            for (int k = 0; k < d; k++)
+                if (__shfl_sync(0xFFFFFFFFu, ls, k) == c) pos = k;
+            const uint32_t bad = __ballot_sync(0xFFFFFFFFu, !valid || pos < 0);
+            int B = bad ? __ffs(bad) - 1 : 32;                                   // (a) new symbol / end of events
+            const int kR = tot + 100 > PROB_SCALE ? 0 : (PROB_SCALE - 100 - tot) / 50 + 1;
+            B = min(B, kR + 1);                                                  // (b) rescale after event kR
+            if (B > 0) {
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, pos);
+                const int cnt_same = __popc(same & lt);                          // earlier events with my symbol
+                const int fpos = __shfl_sync(0xFFFFFFFFu, lf, pos < 0 ? 0 : pos);
+                const int fmax = __shfl_sync(0xFFFFFFFFu, lf, maxpos);
+                const uint32_t maxm = __ballot_sync(0xFFFFFFFFu, pos == maxpos);
+                const int my_f = fpos + 50 * (cnt_same + 1);
+                const int max_f = fmax + 50 * __popc(maxm & (lt | (1u << lane)));
+                const uint32_t over = __ballot_sync(0xFFFFFFFFu, lane < B && pos != maxpos && my_f > max_f);
+                int newmax = maxpos;
+                if (over) {                                                      // (c) maxpos moves after that event
+                    const int tO = __ffs(over) - 1;
+                    B = min(B, tO + 1);
+                    if (tO < B) newmax = __shfl_sync(0xFFFFFFFFu, pos, tO);
+                }
+                // prefix of the frequencies, and the per-event dynamic part
+                int pf = lf;
+#pragma unroll
+                for (int dd = 1; dd < 16; dd <<= 1) {
+                    const int u = __shfl_up_sync(0xFFFFFFFFu, pf, dd);
+                    if (lane >= dd) pf += u;
+                }
+                pf -= lf;  // exclusive
+                const int base = __shfl_sync(0xFFFFFFFFu, pf, pos < 0 ? 0 : pos);
+                int less = 0;  // earlier events of the step whose symbol lies below mine
+                uint32_t inb = 0;
+                for (int k = 0; k < d; k++) {
+                    const uint32_t mk = __ballot_sync(0xFFFFFFFFu, pos == k && lane < B);
+                    if (k < pos) less += __popc(mk & lt);
+                    if (lane == k) inb = mk;
+                }
+                if (lane < B) {
+                    const int tt = tot + 50 * lane;
+                    const int shift = shift_for(tt);
+                    const int bonus = (PROB_SCALE - (tt << shift)) >> shift;
+                    const int cum = (c - pos) + base + 50 * less + (maxpos < pos ? bonus : 0);
+                    const int fr = fpos + 50 * cnt_same + (pos == maxpos ? bonus : 0);
+                    w.intervals[idx] = make_iv((uint32_t)(fr << shift) & 0xFFFFu, (uint32_t)(cum << shift) & 0xFFFFu);
+                }
+                // state after the step
+                int nf = lf + 50 * __popc(inb);
+                tot += 50 * B;
+                if (tot + 50 > PROB_SCALE) {  // rescale, ans_contexts.h:186-193
+                    nf -= nf >> 1;
+                    tot = 256 - d + (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(lane < d ? nf : 0));
+                }
+                if (lane < d) x.sfreq[lane] = (uint16_t)nf;
+                if (lane == 0) {
+                    x.maxpos = (uint8_t)newmax;
+                    if (kind == 5) x.cntsum = tot;
+                }
+                i += B;
+                __syncwarp();
+                continue;
+            }
+        } else if (kind == 7 || kind == 6) {
+            const int step = kind == 7 ? 16 : (25 << x.fshift);
+            const int cntsum = x.cntsum;
+            // events until the rescale fires: cntsum + step*k + step > 4096
+            const int K = (PROB_SCALE - step - cntsum) / step + 1;
+            int B = min(32, min((int)(m - i), K));
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, valid ? c : -1 - lane);
+            const bool leader = (grp & lt) == 0;
+            const int cntc = valid ? x.cnt[c] : 1;
+            const uint32_t newm = __ballot_sync(0xFFFFFFFFu, valid && kind == 6 && cntc == 0 && leader);
+            const int d0 = x.d;
+            // kind 6: a new symbol when 40 are already met promotes the context (not counted): cut before it
+            const uint32_t promo = __ballot_sync(0xFFFFFFFFu, (newm >> lane & 1) && d0 + __popc(newm & lt) >= 40);
+            if (promo) B = min(B, __ffs(promo) - 1);
+            if (B > 0) {
+                if (lane < B) {
+                    w.intervals[idx] = make_iv(x.freq[c], x.cum[c]);
+                    if (leader) {  // one writer per distinct symbol of the step
+                        const int k = __popc(grp & ((B >= 32 ? 0xFFFFFFFFu : (1u << B) - 1)));
+                        int nc = cntc;
+                        if (kind == 6 && nc == 0) {  // placeSymbol, ans_contexts.h:632-635
+                            const int fr = 1 << x.fshift;
+                            nc = fr - (fr >> 1);
+                        }
+                        x.cnt[c] = (uint16_t)(nc + step * k);
+                    }
+                }
+                const uint32_t inB = B >= 32 ? 0xFFFFFFFFu : (1u << B) - 1;
+                const int nd = d0 + __popc(newm & inB);
+                int ns = cntsum + step * B;
+                __syncwarp();
+                if (ns + step > PROB_SCALE) {  // rescale by the whole warp: 8 symbols per lane
+                    uint32_t cn[8], sum = 0;
+                    const int sh = kind == 6 ? (x.fshift > 0 ? x.fshift - 1 : 0) : 0;
+                    for (int j = 0; j < 8; j++) {
+                        cn[j] = x.cnt[lane * 8 + j];
+                        sum += cn[j] ? cn[j] : (1u << sh);  // kind 6: unmet symbols weigh 1 << sh (ans_contexts.h:747-750)
+                    }
+                    uint32_t inc = sum;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
+                        if (lane >= dd) inc += u;
+                    }
+                    uint32_t cf = inc - sum, tots = 0;
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t fr = cn[j] ? cn[j] : (1u << sh);
+                        x.freq[lane * 8 + j] = (uint16_t)fr;
+                        x.cum[lane * 8 + j] = (uint16_t)cf;
+                        cf += fr;
+                        const uint32_t nc = cn[j] - (cn[j] >> 1);  // stays 0 for unmet symbols
+                        x.cnt[lane * 8 + j] = (uint16_t)nc;
+                        tots += nc;
+                    }
+                    ns = (int)__reduce_add_sync(0xFFFFFFFFu, tots);
+                    if (kind == 6) {
+                        const int nfs = x.fshift > 0 ? x.fshift - 1 : 0;
+                        const int shft = nfs > 0 ? nfs - 1 : 0;
+                        ns = (ns + ((256 - nd) << shft)) & 0xFFFF;
+                        __syncwarp();
+                        if (lane == 0) x.fshift = (uint8_t)nfs;
+                    }
+                }
+                if (lane == 0) {
+                    x.cntsum = kind == 6 ? (ns & 0xFFFF) : ns;
+                    x.d = (uint16_t)nd;
+                }
+                i += B;
+                __syncwarp();
+                continue;
+            }
+        }
+        // one event on lane 0: raw kinds, new symbols, promotions
+        if (lane == 0) {
+            uint32_t iv;
+            if (x.kind < 4) {  // no statistics yet: the byte goes out raw (screencap.h:313-315)
+                cc_update_raw(x, c, w.f0);
+                iv = make_iv(0, (uint32_t)c);
+            } else
+                iv = cc_encode_counted(x, c);
+            w.intervals[idx] = iv;
+        }
+        i += 1;
+        __syncwarp();
     }
 }
 
@@ -269,7 +445,7 @@ void launch_replay(const ReplayWork& w, cudaStream_t st, uint64_t* launches) {
     if (w.tm) w.tm->mark("sort");
     k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, st>>>(w, w.seg_off);
     if (w.tm) w.tm->mark("fixed");
-    k_replay_color<<<dim3(NUM_COLOR_CX / 128, w.n_chains), 128, 0, st>>>(w, w.seg_off);
+    k_replay_color<<<dim3(NUM_COLOR_CX / 4, w.n_chains), 128, 0, st>>>(w, w.seg_off);
     *launches += 2;
 }
 

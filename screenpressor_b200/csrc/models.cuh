@@ -240,7 +240,7 @@ __device__ inline void c7_from_set(ColorState& x, int c) {  // :917-951
 }
 
 // ---- Context::update for kinds 0..3 (the byte is stored raw), ans_contexts.cpp:3-31, 52-59 --------
-__device__ inline void cc_update_raw(ColorState& x, int c, int f0) {
+static __device__ __noinline__ void cc_update_raw(ColorState& x, int c, int f0) {
     switch (x.kind) {
     case 0:
         for (int i = 0; i < 8; i++) x.seen[i] = 0;
@@ -295,7 +295,7 @@ __device__ inline void cc_update_raw(ColorState& x, int c, int f0) {
 }
 
 // ---- Context::encode for kinds >= 4, ans_contexts.cpp:34-50 -----------------------------------------
-__device__ inline uint32_t cc_encode_counted(ColorState& x, int c) {
+static __device__ __noinline__ uint32_t cc_encode_counted(ColorState& x, int c) {
     uint32_t iv = 0;
     switch (x.kind) {
     case 4: {

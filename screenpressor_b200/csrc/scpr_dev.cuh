@@ -73,7 +73,7 @@ struct Geo {
 
 // RGB triple of pixel (x, y) as 0x00RRGGBB-style u32 (memory bytes 0,1,2 in bits 0-7, 8-15, 16-23)
 __device__ __forceinline__ uint32_t load_px(const uint8_t* f, const Geo& g, int x, int y) {
-    const uint8_t* p = f + (size_t)y * g.pitch + (size_t)x * g.bpp;
+    const uint8_t* p = f + (uint32_t)(y * g.pitch + x * g.bpp);  // a frame is < 4 GB (<= 65536 blocks)
     if (g.bpp == 4) return *reinterpret_cast<const uint32_t*>(p) & 0x00FFFFFFu;
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
 }
