@@ -164,7 +164,7 @@ void scpr_destroy(scpr_codec* c) {
                    &c->ftype, &c->blocks, &c->pframes, &c->runs, &c->bts_rle, &c->ihdr, &c->desc, &c->exit_tab, &c->entry,
                    &c->starts, &c->chunk_cnt, &c->frame_ev_off, &c->events, &c->intervals, &c->sorted, &c->seg_off,
                    &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
-                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands};
+                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym};
     for (DBuf* b : all) b->release();
     delete c;
 }
@@ -307,11 +307,12 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         TRY(c->blocks.ensure((size_t)(total_blocks + 1) * sizeof(ChgBlock)));
         TRY(c->runs.ensure((size_t)(total_blocks + 1) * 256 * 2));
         TRY(c->bts_rle.ensure((size_t)n_p * 2 * g.nb * 4));
-        TRY(c->cands.ensure((size_t)n_p * 17 * 4));
+        TRY(c->cands.ensure((size_t)n_p * 66 * 4));
         CK(cudaMemcpyAsync(c->pframes.p, pframes.data(), (size_t)n_p * 4, cudaMemcpyHostToDevice, st));
         pw.blocks = (ChgBlock*)c->blocks.p; pw.pframes = (const int*)c->pframes.p; pw.runs = (uint16_t*)c->runs.p;
         pw.bts_rle = (uint32_t*)c->bts_rle.p;
-        pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * 16;
+        pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * 32;
+        pw.cands0 = (int*)c->cands.p + (size_t)n_p * 33; pw.ncands0 = (int*)c->cands.p + (size_t)n_p * 65;
         launch_p_stage_a(pw, st, &c->launches);
         tm.mark("p_stage_a");
     }
@@ -396,6 +397,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
 
     if (n_chains) {
         TRY(c->sorted.ensure((size_t)(total_ev + 1) * 4));
+        TRY(c->sorted_sym.ensure((size_t)(total_ev + 1) * 2));
         TRY(c->seg_off.ensure((size_t)n_chains * (NUM_CX + 1) * 4));
         size_t hist_entries = 0;
         for (auto& cd : chains) hist_entries += replay_hist_entries(cd.n_ev);
@@ -411,7 +413,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         rw.events = (const uint32_t*)c->events.p; rw.intervals = (uint32_t*)c->intervals.p;
         rw.chains = (const ChainDesc*)c->chains.p; rw.n_chains = n_chains; rw.h_chains = chains.data();
         rw.states = (uint8_t*)c->states.p; rw.f0 = 32;
-        rw.sorted = (uint32_t*)c->sorted.p; rw.seg_off = (uint32_t*)c->seg_off.p; rw.chunk_hist = (uint32_t*)c->chunk_hist.p;
+        rw.sorted = (uint32_t*)c->sorted.p; rw.sorted_sym = (uint16_t*)c->sorted_sym.p; rw.seg_off = (uint32_t*)c->seg_off.p; rw.chunk_hist = (uint32_t*)c->chunk_hist.p;
         rw.chunk_base = (const uint32_t*)c->chunk_base.p; rw.total_events = total_ev; rw.tm = &tm;
         launch_replay(rw, st, &c->launches);
         tm.mark("replay");
@@ -472,6 +474,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     tm.mark("assemble+d2h");
     CK(cudaStreamSynchronize(st));
     tm.report("encode_batch");
+    if (tm.on) mv_stats_report();
     for (int f = 0; f < n; f++) {
         uint8_t* o = dst + frame_out[f];
         switch (ftype[f]) {

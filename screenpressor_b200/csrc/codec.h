@@ -48,7 +48,7 @@ struct scpr_codec {
     // ---- encoder workspaces ---------------------------------------------------------------------
     scpr::DBuf frames, blkinfo, summary, chg_list, hdr, ftype, blocks, pframes, runs, bts_rle, cands;
     scpr::DBuf ihdr, desc, exit_tab, entry, starts, chunk_cnt;
-    scpr::DBuf frame_ev_off, events, intervals, sorted, seg_off, chunk_hist, chunk_base, chains, rblks, scratch, out;
+    scpr::DBuf frame_ev_off, events, intervals, sorted, sorted_sym, seg_off, chunk_hist, chunk_base, chains, rblks, scratch, out;
 
     // ---- decoder state and workspaces -----------------------------------------------------------
     bool dec_created = false;        // a codec exists (first I frame seen), screencap.cpp:1698-1702

@@ -292,12 +292,16 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         rdec_advance(e, cum, freq);
     } else if (kind >= 4) {  // SmallContext: walk the (<= 16) sorted symbols, ans_contexts.h:238-283
         const uint32_t v0 = e.x & (PROB_SCALE - 1);
-        const int d = x.d, maxpos = x.maxpos;
-        int totFr = x.cntsum;
-        if (kind == 4) {
-            totFr = 256 - d;
-            for (int i = 0; i < 4; i++) totFr += x.sfreq[i];
-        }
+        // header + symbols + frequencies: four independent 128-bit loads, then registers only
+        const uint4 hd = *reinterpret_cast<const uint4*>(&x.kind);
+        const uint4 sy4 = *reinterpret_cast<const uint4*>(x.ssym);
+        const uint4 f0 = *reinterpret_cast<const uint4*>(x.sfreq);
+        const uint4 f1 = *reinterpret_cast<const uint4*>(x.sfreq + 8);
+        const int maxpos = (hd.x >> 16) & 255, d = hd.y & 0xFFFF;
+        const uint32_t syw[4] = {sy4.x, sy4.y, sy4.z, sy4.w};
+        const uint32_t frw[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        int totFr = (int)hd.z;
+        if (kind == 4) totFr = 256 - d + (int)((f0.x & 0xFFFF) + (f0.x >> 16) + (f0.y & 0xFFFF) + (f0.y >> 16));  // :303
         int shift = 0, tot = totFr;
         while (tot <= PROB_SCALE / 2) {
             tot <<= 1;
@@ -305,22 +309,33 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         }
         const int v = (int)(v0 >> shift);
         const int bonus = (PROB_SCALE - tot) >> shift;
-        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1;
-        bool found = false;
-        c = -1;
-        for (; pos < d; pos++) {
-            const int sy = x.ssym[pos];
-            const int startFr = cumFr + sy - lastSymb;
-            if (v < startFr) break;
-            fr = (x.sfreq[pos] + (pos == maxpos ? bonus : 0)) & 0xFFFF;
-            if (startFr + fr > v) {
-                c = sy;
-                cumFr = startFr;
-                found = true;
-                break;
+        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1, fpos = 0, fmax = 0;
+        bool found = false, done = false;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int fk = (int)((frw[k >> 1] >> (16 * (k & 1))) & 0xFFFF);
+            if (k == maxpos) fmax = fk;
+            if (!done && k < d) {
+                const int sk = (int)((syw[k >> 2] >> (8 * (k & 3))) & 255);
+                const int startFr = cumFr + sk - lastSymb;
+                if (v < startFr)
+                    done = true;
+                else {
+                    const int frk = (fk + (k == maxpos ? bonus : 0)) & 0xFFFF;
+                    if (startFr + frk > v) {
+                        c = sk;
+                        cumFr = startFr;
+                        fr = frk;
+                        fpos = fk;
+                        found = true;
+                        done = true;
+                    } else {
+                        cumFr = startFr + frk;
+                        lastSymb = sk + 1;
+                        pos = k + 1;
+                    }
+                }
             }
-            cumFr = startFr + fr;
-            lastSymb = sy + 1;
         }
         if (!found) {  // a symbol not met yet: width 1
             c = lastSymb + v - cumFr;
@@ -329,10 +344,10 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         }
         if (e.lane == 0) {
             if (found && totFr + 100 <= PROB_SCALE) {  // hot path: count, no rescale (ans_contexts.h:211-214)
-                const int nf = x.sfreq[pos] + 50;
+                const int nf = fpos + 50;
                 x.sfreq[pos] = (uint16_t)nf;
                 if (kind == 5) x.cntsum = totFr + 50;
-                if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;
+                if (pos != maxpos && nf > fmax) x.maxpos = (uint8_t)pos;
             } else
                 cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
         }
@@ -595,24 +610,23 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                     const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
                     v = tile[oy + ly][ox + li - ly * sw];
                 } else {
-                    if (lane == 0) {
-                        int yy = (int)(((uint32_t)pos * swinv) >> 16), xx = pos - yy * sw;
-                        for (int i = 0; i < n; i++) {
-                            uint32_t* t = &tile[oy + yy][ox + xx];
-                            switch (ptype) {
-                            case 1: v = t[-1]; break;
-                            case 2: v = t[-17]; break;
-                            case 4: v = grad_px(t[-1], t[-17], t[-18]); break;
-                            case 5: v = t[-18]; break;
-                            }
-                            t[0] = v;
-                            if (++xx == sw) {
-                                xx = 0;
-                                yy++;
-                            }
+                    // predicted from pixels of this block: one row segment of the sub-rect per step (<= 16
+                    // pixels, sources lie in the row above or left of the segment); gradient chains serially
+                    int yy = (int)(((uint32_t)pos * swinv) >> 16), xx = pos - yy * sw;
+                    for (int rem = n; rem > 0;) {
+                        const int seg = min(rem, sw - xx);
+                        uint32_t* row = &tile[oy + yy][ox + xx];
+                        if (ptype == 4) {
+                            if (lane == 0)
+                                for (int i = 0; i < seg; i++) row[i] = grad_px(row[i - 1], row[i - 17], row[i - 18]);
+                        } else if (lane < seg) {
+                            row[lane] = ptype == 1 ? row[-1] : ptype == 2 ? row[lane - 17] : row[lane - 18];
                         }
+                        __syncwarp();
+                        rem -= seg;
+                        xx = 0;
+                        yy++;
                     }
-                    __syncwarp();
                     const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
                     v = tile[oy + ly][ox + li - ly * sw];
                 }

@@ -34,8 +34,8 @@ struct ChgBlock {
     uint8_t bt;         // final block type 1..4 (reference bts[])
     uint8_t rep;        // MV equals the previously coded MV of this frame (encodeBool(true))
     uint8_t fidx;       // index of F(bi) in the frame's candidate list, 0xFF = not listed (k_mv_cands)
-    uint16_t mmask;     // bit k: candidate k of the frame reproduces this block (k_mv_prematch)
-    uint16_t pad;
+    uint8_t pad[3];
+    uint32_t mmask;     // bit k: candidate k of the frame reproduces this block (k_mv_prematch)
     int32_t prev_nonmv; // previous pixel-coded changed block of the frame (slot index), -1 if none
     uint32_t n_runs;    // pixel runs of a pixel-coded block
     uint32_t n_ev;      // events this block contributes
@@ -75,7 +75,8 @@ struct PWork {
     PFrameHdr* hdr; ChgBlock* blocks; int total_blocks;
     const int* pframes; int n_pframes;     // batch indices of P-coded frames, ascending
     int2* mvs;                             // persistent per-block MV array (reference mvs[], never cleared)
-    int* cands; int* ncands;               // per P frame: up to 16 distinct F vectors (packed x | y<<16) and their count
+    int* cands0; int* ncands0;             // per P frame: distinct F vectors of that frame alone
+    int* cands; int* ncands;               // per P frame: up to 32 distinct F vectors (packed x | y<<16) and their count
     uint16_t* runs;                        // per changed block: 256 x (ptype<<8 | n)
     uint32_t* bts_rle;                     // per P frame: scratch for the block-type RLE, 2*nb entries
     const uint32_t* frame_ev_off;          // per batch frame: first event (batch-wide index)
@@ -84,6 +85,7 @@ struct PWork {
 };
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches);   // search, resolve, runs, counts
 void launch_p_emit(const PWork& w, cudaStream_t st, uint64_t* launches);      // events
+void mv_stats_report();
 
 // I frames: pixel classification, run segmentation, event emission
 struct IWork {
@@ -116,7 +118,7 @@ struct ReplayWork {
     uint8_t* states;                           // n_states * model_state_bytes()
     int f0;                                    // Cx6 start frequency: 32 for v4 (screencap.cpp:1614)
     // sort workspace
-    uint32_t* sorted; uint32_t* seg_off; uint32_t* chunk_hist; const uint32_t* chunk_base;
+    uint32_t* sorted; uint16_t* sorted_sym; uint32_t* seg_off; uint32_t* chunk_hist; const uint32_t* chunk_base;
     uint32_t total_events;
     struct StageTimer* tm;
 };

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) k_sort_scan_ctx(uint32_t* __restrict__ se
 // warp step are ranked with match_any, across steps with a shared-memory running count.
 __global__ void __launch_bounds__(32) k_sort_place(const uint32_t* __restrict__ events, const SortChunkDesc* __restrict__ chunks,
                                                    const uint32_t* __restrict__ hist, const uint32_t* __restrict__ seg_off,
-                                                   const ChainDesc* __restrict__ chains, uint32_t* __restrict__ sorted) {
+                                                   const ChainDesc* __restrict__ chains, uint32_t* __restrict__ sorted,
+                                                   uint16_t* __restrict__ sorted_sym) {
     extern __shared__ uint16_t s_cnt[];  // NUM_CX
     const SortChunkDesc cd = chunks[blockIdx.x];
     const int lane = threadIdx.x;
@@ -107,10 +108,12 @@ __global__ void __launch_bounds__(32) k_sort_place(const uint32_t* __restrict__ 
     const uint32_t* row = hist + cd.hist_off;
     const uint32_t* seg = seg_off + (size_t)cd.chain * (NUM_CX + 1);
     uint32_t* out = sorted + chains[cd.chain].ev_off;
+    uint16_t* out_sym = sorted_sym + chains[cd.chain].ev_off;
     for (uint32_t i0 = 0; i0 < cd.len; i0 += 32) {
         const uint32_t i = i0 + lane;
         const bool ok = i < cd.len;
-        const uint32_t ctx = ok ? events[cd.ev_begin + i] >> 16 : 0xFFFFu;
+        const uint32_t ev = ok ? events[cd.ev_begin + i] : 0xFFFF0000u;
+        const uint32_t ctx = ev >> 16;
         const uint32_t m = __match_any_sync(0xFFFFFFFFu, ctx);
         const int leader = __ffs(m) - 1;
         uint32_t base = 0;
@@ -119,7 +122,11 @@ __global__ void __launch_bounds__(32) k_sort_place(const uint32_t* __restrict__ 
             s_cnt[ctx] = (uint16_t)(base + __popc(m));
         }
         base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (ok) out[seg[ctx] + row[ctx] + base + __popc(m & ((1u << lane) - 1))] = cd.ev_begin + i;
+        if (ok) {
+            const uint32_t dst = seg[ctx] + row[ctx] + base + __popc(m & ((1u << lane) - 1));
+            out[dst] = cd.ev_begin + i;
+            out_sym[dst] = (uint16_t)ev;
+        }
         __syncwarp();
     }
 }
@@ -173,11 +180,29 @@ __global__ void __launch_bounds__(32) k_replay_fixed(ReplayWork w, const uint32_
         // events until the rescale fires: cntsum + 16k + 16 > 4096 (ans_contexts.h:1074-1075)
         const uint32_t epoch = (uint32_t)((PROB_SCALE - 16 - cntsum) / 16 + 1);
         const uint32_t L = min(m, epoch);
-        for (uint32_t i = lane; i < L; i += 32) {
-            const uint32_t idx = w.sorted[pos + i];
-            const uint32_t sym = w.events[idx] & 0xFFFFu;
-            w.intervals[idx] = make_iv(s_freq[sym], s_cum[sym]);
-            atomicAdd(&s_cnt[sym], 16u);
+        // an epoch holds at most ~130 events (cntsum >= ~2046 after a renew or rescale): issue all of the
+        // lane's loads first so their latencies overlap, then look up / count
+        uint32_t idx[5], sym[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const uint32_t i = lane + 32 * u;
+            if (i < L) {
+                idx[u] = w.sorted[pos + i];
+                sym[u] = w.sorted_sym[pos + i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const uint32_t i = lane + 32 * u;
+            if (i < L) {
+                w.intervals[idx[u]] = make_iv(s_freq[sym[u]], s_cum[sym[u]]);
+                atomicAdd(&s_cnt[sym[u]], 16u);
+            }
+        }
+        for (uint32_t i = lane + 160; i < L; i += 32) {  // not reached with the reference's constants
+            const uint32_t id = w.sorted[pos + i], sy = w.sorted_sym[pos + i];
+            w.intervals[id] = make_iv(s_freq[sy], s_cum[sy]);
+            atomicAdd(&s_cnt[sy], 16u);
         }
         __syncwarp();
         cntsum += 16 * (int)L;
@@ -262,7 +287,7 @@ __global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32
         int c = -1;
         if (valid) {
             idx = w.sorted[pos0 + i + lane];
-            c = (int)(w.events[idx] & 0xFFu);
+            c = (int)(w.sorted_sym[pos0 + i + lane] & 0xFFu);
         }
         if (kind == 4 || kind == 5) {
             const int d = x.d, maxpos = x.maxpos;
@@ -439,7 +464,7 @@ void launch_replay(const ReplayWork& w, cudaStream_t st, uint64_t* launches) {
     k_sort_scan_ctx<<<w.n_chains, 256, 0, st>>>(w.seg_off);
     *launches += 2;
     if (n_chunks) {
-        k_sort_place<<<n_chunks, 32, NUM_CX * sizeof(uint16_t), st>>>(w.events, chunks, hist, w.seg_off, w.chains, w.sorted);
+        k_sort_place<<<n_chunks, 32, NUM_CX * sizeof(uint16_t), st>>>(w.events, chunks, hist, w.seg_off, w.chains, w.sorted, w.sorted_sym);
         ++*launches;
     }
     if (w.tm) w.tm->mark("sort");

@@ -19,6 +19,8 @@ struct FixedState {  // FixedSizeRansCtx<N>, ans_contexts.h:1053-1132
 
 struct alignas(16) ColorState {
     uint16_t cnt[256], freq[256], cum[256];  // kinds 6/7 (16-byte aligned for 128-bit table scans)
+    // ---- 16-byte header, then the SmallContext arrays: the decoder fetches these 64 bytes with four
+    // 128-bit loads and walks the (<= 16) symbols in registers
     uint8_t kind;    // 0 empty, 1..3 "every symbol met once" sets, 4/5 SmallContext, 6 Cx6, 7 Cx7
     uint8_t fshift;  // kind 6
     uint8_t maxpos;  // kinds 4/5
@@ -26,10 +28,12 @@ struct alignas(16) ColorState {
     uint16_t d;      // distinct symbols met
     uint16_t pad2;
     int cntsum;      // kind 5: cached totFr; kinds 6/7: counter sum
-    uint32_t seen[8];     // kinds 1..3: bitmap of symbols met
+    uint32_t pad3;
     uint8_t ssym[16];     // kinds 4/5: sorted symbols ...
     uint16_t sfreq[16];   // ... and their frequencies
+    uint32_t seen[8];     // kinds 1..3: bitmap of symbols met
 };
+static_assert(sizeof(ColorState) == 1632, "ColorState layout");
 
 struct ModelState {
     FixedState fx[NUM_FIXED_CX];

@@ -12,6 +12,8 @@
 // changed block of every frame in parallel (k_mv_search, 32 candidates per warp step, first hit by
 // ballot), and only the two state-dependent shortcut candidates are evaluated in frame/raster order
 // (k_mv_resolve); a shortcut whose vector equals F(b) needs no compare at all.
+#include <stdio.h>
+
 #include "codec.h"
 
 namespace scpr {
@@ -175,7 +177,8 @@ __device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& w
 // appearance) -- the only values last_mv can take in this frame besides (0,0).  One warp per frame;
 // lane k keeps candidate k.  Also records each block's index into that list (fidx, 0xFF = none).
 // ------------------------------------------------------------------------------------------------
-constexpr int MAXC = 16;
+constexpr int MAXC = 32;
+__device__ unsigned long long g_mv_stats[4];  // steps, c1 direct compares, c2 direct compares, blocks
 __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
     const int lane = threadIdx.x;
     const int f = w.pframes[blockIdx.x];
@@ -208,8 +211,30 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
         }
         if (k < nchg) w.blocks[off + k].fidx = (uint8_t)myidx;
     }
-    if (lane < MAXC) w.cands[(size_t)blockIdx.x * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
-    if (lane == 0) w.ncands[blockIdx.x] = ncand;
+    w.cands0[(size_t)blockIdx.x * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
+    if (lane == 0) w.ncands0[blockIdx.x] = ncand;
+}
+
+// k_mv_cands_merge: the vector stored for the block above (candidate 2) is often a leftover of an
+// earlier frame, so each frame's list is topped up with the lists of the preceding P frames.
+__global__ void __launch_bounds__(32) k_mv_cands_merge(PWork w) {
+    const int lane = threadIdx.x;
+    const int pi = blockIdx.x;
+    int cand = w.cands0[(size_t)pi * MAXC + lane];
+    int ncand = w.ncands0[pi];
+    for (int back = 1; back <= 12 && pi - back >= 0 && ncand < MAXC; back++) {
+        const int pv = w.cands0[(size_t)(pi - back) * MAXC + lane];
+        const int pn = w.ncands0[pi - back];
+        for (int k = 0; k < pn && ncand < MAXC; k++) {
+            const int v = __shfl_sync(0xFFFFFFFFu, pv, k);
+            if (!__ballot_sync(0xFFFFFFFFu, lane < ncand && cand == v)) {
+                if (lane == ncand) cand = v;
+                ncand++;
+            }
+        }
+    }
+    w.cands[(size_t)pi * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
+    if (lane == 0) w.ncands[pi] = ncand;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,18 +265,24 @@ __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
         const int mx = (int)(int16_t)(cv & 0xFFFF), my = cv >> 16;
         if (in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane)) mask |= 1u << k;
     }
-    if (lane == 0) b.mmask = (uint16_t)mask;
+    if (lane == 0) b.mmask = mask;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_mv_resolve: the serial part of FindMV (screencap.cpp:715-735), one warp walking P frames and
 // their changed blocks in order.  Candidate 1 = last_mv, candidate 2 = persistent MV of the block
-// above; search hits (= F) update last_mv, shortcut hits do not.  With the prematch masks the walk
-// is table look-ups: blocks are taken 32 at a time (one per lane, fields exchanged by shuffles),
-// and a direct compare is only needed for a vector outside the frame's candidate list.
+// above; search hits (= F) update last_mv, shortcut hits do not.
+// A step takes up to 32 consecutive changed blocks, one per lane, and resolves them together under
+// the assumption that last_mv does not change inside the step: with the prematch masks that is a
+// table look-up per lane.  last_mv only changes at a search hit, so the step is cut right after the
+// first lane that had one; everything before it is final.  The MV-repeat flag (screencap.cpp:1202)
+// and the "previous pixel-coded block" link are prefix operations over the step (ballots).
+// A step never contains a block together with its upper neighbour (their indices differ by nbx),
+// so the upper MV can be read from mvs[] when the step is loaded.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
     const int lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1;
     const Geo& g = w.g;
     for (int pi = 0; pi < w.n_pframes; pi++) {
         const int f = w.pframes[pi];
@@ -259,16 +290,16 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
         const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
         const int nc = w.ncands[pi];
-        const int cand = lane < MAXC ? w.cands[(size_t)pi * MAXC + lane] : 0x7FFFFFFF;  // lane k: candidate k
+        const int cand = w.cands[(size_t)pi * MAXC + lane];  // lane k: candidate k
         int lv = 0, lidx = -1;   // last_mv (packed) and its index in the candidate list (-1: (0,0), -2: not listed)
         int cv = 0;              // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
         int prev_nonmv = -1;
         int k0 = 0;
         while (k0 < nchg) {
-            // one block per lane; the step ends before a block whose upper neighbour is inside the step
             const int k = k0 + lane;
             uint32_t bi = 0, info = 0;
-            int mmask = 0, fidx = 0xFF, fv = 0, uv = 0;
+            uint32_t mmask = 0;
+            int fidx = 0x100, fv = 0, uv = 0;
             if (k < nchg) {
                 const ChgBlock& b = w.blocks[off + k];
                 bi = b.bi; info = b.info; mmask = b.mmask; fidx = b.has_f ? b.fidx : 0x100;
@@ -279,67 +310,87 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
                 }
             }
             const uint32_t bi0 = __shfl_sync(0xFFFFFFFFu, bi, 0);
-            const int cnt = __popc(__ballot_sync(0xFFFFFFFFu, k < nchg && bi - bi0 < (uint32_t)g.nbx));
-            int out_v = 0, out_flags = 0, out_prev = -1;  // per-lane results, written after the step
-            for (int i = 0; i < cnt; i++) {
-                const int b_mask = __shfl_sync(0xFFFFFFFFu, mmask, i), b_fidx = __shfl_sync(0xFFFFFFFFu, fidx, i);
-                const int b_fv = __shfl_sync(0xFFFFFFFFu, fv, i), b_uv = __shfl_sync(0xFFFFFFFFu, uv, i);
-                const uint32_t b_bi = __shfl_sync(0xFFFFFFFFu, bi, i), b_info = __shfl_sync(0xFFFFFFFFu, info, i);
-                bool found = false;
-                int mv = 0;
-                // candidate 1: last_mv
-                if (lidx >= 0)
-                    found = (b_mask >> lidx) & 1;
-                else if (lidx == -2) {
-                    const SubRect r = subrect_of(b_bi, b_info, g);
+            int cnt = __popc(__ballot_sync(0xFFFFFFFFu, k < nchg && bi - bi0 < (uint32_t)g.nbx));
+            const bool in = lane < cnt;
+            // ---- candidate 1: last_mv (same for every lane of the step) ----
+            bool found = false;
+            int mv = 0;
+            if (lidx >= 0)
+                found = in && ((mmask >> lidx) & 1);
+            else if (lidx == -2) {  // last_mv is not in the candidate list: direct compares, lane by lane
+                if (lane == 0) atomicAdd(&g_mv_stats[1], (unsigned long long)cnt);
+                for (int i = 0; i < cnt; i++) {
+                    const SubRect r = subrect_of(__shfl_sync(0xFFFFFFFFu, bi, i), __shfl_sync(0xFFFFFFFFu, info, i), g);
                     const Windows win = windows_of(r, g);
                     const int mx = (int)(int16_t)(lv & 0xFFFF), my = lv >> 16;
-                    found = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                    const bool hit = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                    if (lane == i) found = hit;
                 }
-                if (found) mv = lv;
-                // candidate 2: the vector stored for the block above, if it differs from last_mv
-                if (!found && b_bi >= (uint32_t)g.nbx && b_uv != lv && b_uv != 0) {
-                    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < nc && cand == b_uv);
-                    if (hit)
-                        found = (b_mask >> (__ffs(hit) - 1)) & 1;
-                    else {
-                        const SubRect r = subrect_of(b_bi, b_info, g);
-                        const Windows win = windows_of(r, g);
-                        const int mx = (int)(int16_t)(b_uv & 0xFFFF), my = b_uv >> 16;
-                        found = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
-                    }
-                    if (found) mv = b_uv;
-                }
-                // the fixed-order search: first hit wins and becomes last_mv
-                if (!found && b_fidx != 0x100) {
+            }
+            if (found) mv = lv;
+            // ---- candidate 2: the vector stored for the block above, if it differs from last_mv ----
+            const bool try2 = in && !found && bi >= (uint32_t)g.nbx && uv != lv && uv != 0;
+            int uidx = -1;
+            for (int kc = 0; kc < nc; kc++)
+                if (__shfl_sync(0xFFFFFFFFu, cand, kc) == uv) uidx = kc;
+            bool f2 = try2 && uidx >= 0 && ((mmask >> uidx) & 1);
+            uint32_t slow = __ballot_sync(0xFFFFFFFFu, try2 && uidx < 0);
+            if (lane == 0) {
+                atomicAdd(&g_mv_stats[0], 1ull);
+                atomicAdd(&g_mv_stats[2], (unsigned long long)__popc(slow));
+            }
+            while (slow) {  // a stale vector that is not one of this frame's candidates: compare directly
+                const int i = __ffs(slow) - 1;
+                slow &= slow - 1;
+                const SubRect r = subrect_of(__shfl_sync(0xFFFFFFFFu, bi, i), __shfl_sync(0xFFFFFFFFu, info, i), g);
+                const Windows win = windows_of(r, g);
+                const int u = __shfl_sync(0xFFFFFFFFu, uv, i);
+                const int mx = (int)(int16_t)(u & 0xFFFF), my = u >> 16;
+                const bool hit = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                if (lane == i) f2 = hit;
+            }
+            if (f2) {
+                found = true;
+                mv = uv;
+            }
+            // ---- the fixed-order search: first hit wins and becomes last_mv; cut the step after it ----
+            const bool hit3 = in && !found && fidx != 0x100;
+            const uint32_t h3 = __ballot_sync(0xFFFFFFFFu, hit3);
+            if (h3) {
+                const int tH = __ffs(h3) - 1;
+                cnt = tH + 1;
+                if (lane == tH) {
                     found = true;
-                    mv = b_fv;
-                    lv = b_fv;
-                    lidx = b_fidx == 0xFF ? -2 : b_fidx;
+                    mv = fv;
                 }
-                int flags = (b_info & BI_PARTIAL) ? 2 : 1;
-                if (found) {
-                    flags += 2;
-                    const bool rep = b_bi > 0 && mv == cv;  // screencap.cpp:1202
-                    if (rep) flags |= 0x100; else cv = mv;
-                    if (lane == 0) w.mvs[b_bi] = make_int2((int)(int16_t)(mv & 0xFFFF), mv >> 16);
-                }
-                if (lane == i) {
-                    out_v = mv;
-                    out_flags = flags;
-                    out_prev = found ? -1 : prev_nonmv;
-                }
-                if (!found) prev_nonmv = k0 + i;
+                lv = __shfl_sync(0xFFFFFFFFu, fv, tH);
+                const int fi = __shfl_sync(0xFFFFFFFFu, fidx, tH);
+                lidx = fi == 0xFF ? -2 : fi;
             }
-            if (lane < cnt) {
+            const bool inn = lane < cnt;
+            // ---- repeat flag and links: prefix operations over the lanes of the step ----
+            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, inn && found);
+            const uint32_t before = fm & lt;
+            const int pf_lane = before ? 31 - __clz(before) : 0;
+            const int pmv = __shfl_sync(0xFFFFFFFFu, mv, pf_lane);
+            const int prev_coded = before ? pmv : cv;  // a repeated MV leaves lastmx/lastmy unchanged = same value
+            const bool rep = found && bi > 0 && mv == prev_coded;
+            const uint32_t nm = __ballot_sync(0xFFFFFFFFu, inn && !found);
+            const uint32_t nbefore = nm & lt;
+            const int my_prev_nonmv = nbefore ? k0 + 31 - __clz(nbefore) : prev_nonmv;
+            if (inn) {
                 ChgBlock& b = w.blocks[off + k];
-                b.bt = (uint8_t)(out_flags & 0xFF);
-                b.rep = (uint8_t)(out_flags >> 8);
-                b.mx = (int16_t)(out_v & 0xFFFF);
-                b.my = (int16_t)(out_v >> 16);
-                b.prev_nonmv = out_prev;
+                b.bt = (uint8_t)(((info & BI_PARTIAL) ? 2 : 1) + (found ? 2 : 0));
+                b.rep = rep;
+                b.mx = (int16_t)(mv & 0xFFFF);
+                b.my = (int16_t)(mv >> 16);
+                b.prev_nonmv = found ? -1 : my_prev_nonmv;
+                if (found) w.mvs[bi] = make_int2((int)(int16_t)(mv & 0xFFFF), mv >> 16);
             }
+            if (fm) cv = __shfl_sync(0xFFFFFFFFu, mv, 31 - __clz(fm));
+            if (nm) prev_nonmv = k0 + 31 - __clz(nm);
             __syncwarp();
+            if (lane == 0) atomicAdd(&g_mv_stats[3], (unsigned long long)cnt);
             k0 += cnt;
         }
         __threadfence();  // mvs[] of this frame visible before the next frame reads it
@@ -620,11 +671,20 @@ __global__ void __launch_bounds__(128) k_p_emit(PWork w) {
     }
 }
 
+void mv_stats_report() {
+    unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    cudaMemcpyFromSymbol(h, g_mv_stats, sizeof(h));
+    cudaMemcpyToSymbol(g_mv_stats, z, sizeof(z));
+    fprintf(stderr, "[scpr timing] mv_resolve: %llu blocks in %llu steps, direct compares: last_mv %llu, upper %llu\n", h[3], h[0], h[1], h[2]);
+}
+
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
     if (w.total_blocks > 0) {
         k_mv_search<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
         if (w.tm) w.tm->mark("mv_search");
         k_mv_cands<<<w.n_pframes, 32, 0, st>>>(w);
+        k_mv_cands_merge<<<w.n_pframes, 32, 0, st>>>(w);
+        ++*launches;
         k_mv_prematch<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
         *launches += 2;
         if (w.tm) w.tm->mark("mv_prematch");

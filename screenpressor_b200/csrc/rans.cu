@@ -19,8 +19,12 @@ constexpr int RTILE = 1024;
 
 __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__ intervals, RansBlk* __restrict__ blks,
                                                     uint8_t* __restrict__ scratch) {
-    __shared__ uint32_t s_iv[RTILE];
-    __shared__ uint32_t s_rcp[RTILE];
+    // per interval, everything the serial lane needs that does not depend on the state:
+    //   s_a = reciprocal m;  s_b = x_max = freq << 19 (0 marks a raw byte);
+    //   s_c = (4096 - freq) << 18 | shift << 13 | bias, bias = start (+ 4095 for freq 1, see below)
+    __shared__ uint32_t s_a[RTILE];
+    __shared__ uint32_t s_b[RTILE];
+    __shared__ uint32_t s_c[RTILE];
     __shared__ uint8_t s_out[2 * RTILE + 8];
     const int lane = threadIdx.x;
     RansBlk& blk = blks[blockIdx.x];
@@ -33,41 +37,52 @@ __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__
         const int lo = max(0, hi - RTILE), cnt = hi - lo;
         for (int i = lane; i < cnt; i += 32) {
             const uint32_t v = iv[lo + i];
-            const uint32_t f = v & 0xFFFFu;
-            uint32_t m = 0;
+            const uint32_t f = v & 0xFFFFu, start = v >> 16;
+            uint32_t m, sh = 0, bias = start;
             if (f >= 2) {
                 const int s = 32 - __clz(f - 1);  // ceil(log2 f)
                 m = (uint32_t)((((unsigned long long)1 << (31 + s)) + f - 1) / f);
+                sh = (uint32_t)(s - 1);
+            } else {
+                // freq 1: x / 1 == x.  mulhi(x, 2^32-1) == x - 1, compensated in the bias:
+                // x + (start + 4095) + (x - 1) * 4095 == 4096 x + start
+                m = 0xFFFFFFFFu;
+                bias = start + 4095u;
             }
-            s_iv[i] = v;
-            s_rcp[i] = m;
+            s_a[i] = m;
+            s_b[i] = f << 19;
+            s_c[i] = f ? (((1u << PROB_BITS) - f) << 18) | (sh << 13) | bias : start;
         }
         __syncwarp();
         int nout = 0;
         if (lane == 0) {
-            uint8_t* p = s_out + sizeof(s_out);
+            int pi = (int)sizeof(s_out);  // write index into s_out, moves down
+            uint32_t a = s_a[cnt - 1], b = s_b[cnt - 1], c = s_c[cnt - 1];
             for (int i = cnt - 1; i >= 0; i--) {
-                const uint32_t v = s_iv[i];
-                const uint32_t freq = v & 0xFFFFu, start = v >> 16;
-                if (freq) {  // RansEncPut (rans_byte.h:76-84) with RansEncRenorm (:59-71)
-                    const uint32_t x_max = ((RANS_L >> PROB_BITS) << 8) * freq;
-                    while (x >= x_max) {
-                        *--p = (uint8_t)(x & 0xFF);
+                // the next interval's operands are fetched before this state update (they do not depend on x)
+                const int in = i > 0 ? i - 1 : 0;
+                const uint32_t an = s_a[in], bn = s_b[in], cn = s_c[in];
+                if (b) {  // RansEncPut (rans_byte.h:76-84) with RansEncRenorm (:59-71)
+                    while (x >= b) {
+                        s_out[--pi] = (uint8_t)x;
                         x >>= 8;
                     }
-                    const uint32_t q = freq >= 2 ? __umulhi(x, s_rcp[i]) >> (31 - __clz(freq - 1)) : x;  // x / freq
-                    x = x + start + q * ((1u << PROB_BITS) - freq);  // (q << 12) + (x - q*freq) + start
+                    const uint32_t q = __umulhi(x, a) >> ((c >> 13) & 31);  // x / freq
+                    x = x + (c & 0x1FFFu) + q * (c >> 18);                  // (q << 12) + (x - q*freq) + start
                 } else
-                    *--p = (uint8_t)start;  // raw byte, ransmt.h:127-128
+                    s_out[--pi] = (uint8_t)c;  // raw byte, ransmt.h:127-128
+                a = an;
+                b = bn;
+                c = cn;
             }
             if (lo == 0) {  // RansEncFlush, rans_byte.h:87-100
-                p -= 4;
-                p[0] = (uint8_t)x;
-                p[1] = (uint8_t)(x >> 8);
-                p[2] = (uint8_t)(x >> 16);
-                p[3] = (uint8_t)(x >> 24);
+                pi -= 4;
+                s_out[pi] = (uint8_t)x;
+                s_out[pi + 1] = (uint8_t)(x >> 8);
+                s_out[pi + 2] = (uint8_t)(x >> 16);
+                s_out[pi + 3] = (uint8_t)(x >> 24);
             }
-            nout = (int)(s_out + sizeof(s_out) - p);
+            nout = (int)sizeof(s_out) - pi;
         }
         nout = __shfl_sync(0xFFFFFFFFu, nout, 0);
         __syncwarp();

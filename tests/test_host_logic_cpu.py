@@ -1,0 +1,102 @@
+"""CPU: host-side logic that does not need a GPU -- the clip generator, the keyframe policy, the
+CPU arm of bench.py, and the N > 1 sharding / timing reduction under a 2-rank gloo group."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_keyframe_policy_matches_vfw_default():
+    from screenpressor_b200 import synth
+
+    # forced_kf = npframes + 1 >= interval (screenpressor.cpp:402-406): interval 500 -> I at 0 and 500
+    k = synth.keyframe_flags(600, 500)
+    assert list(np.nonzero(k)[0]) == [0, 500]
+    assert list(np.nonzero(synth.keyframe_flags(10, 1))[0]) == list(range(10))
+    assert list(np.nonzero(synth.keyframe_flags(10, 4))[0]) == [0, 4, 8]
+
+
+def test_synthetic_clips_are_deterministic_and_well_formed():
+    from screenpressor_b200 import synth
+
+    for name, cfg in synth.CONFIGS.items():
+        a = synth.make_clip(cfg, 3)
+        b = synth.make_clip(cfg, 3)
+        assert np.array_equal(a, b), name
+        if cfg.bpp == 32:
+            assert a.shape == (3, cfg.height, cfg.width, 4) and (a[..., 3] == 255).all()
+        else:
+            stride = (cfg.width * 3 + 3) & ~3
+            assert a.shape == (3, cfg.height, stride)
+        assert not np.array_equal(a[0], a[1]) or cfg.kind == "multimon"
+
+
+def test_cfg5_contains_duplicate_frames_and_cfg2_scrolls():
+    from screenpressor_b200 import synth
+
+    c5 = synth.make_clip(synth.CONFIGS["cfg5_5120x1440"], 40)
+    dups = sum(np.array_equal(c5[i], c5[i - 1]) for i in range(1, 40))
+    assert dups >= 1
+    c2 = synth.make_clip(synth.CONFIGS["cfg2_1080p_rgb32"], 32)
+    changed = [(c2[i] != c2[i - 1]).any(axis=2).sum() for i in (29, 30)]
+    assert changed[1] > 2 * changed[0]  # frame 30 scrolls the main text pane (on top of the window drag)
+
+
+def test_bench_reference_arm_prints_contract_line(oracle_built):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-frames", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    assert line["metric"] == "1080p_rgb32_encode_decode_frames_per_s"
+
+
+def _rank_main(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, clip, keys = bench.make_workload(rank, 2)
+    # each rank owns its own clip (weak scaling, no data-path collective); timing = max over ranks
+    t = torch.tensor([10.0 + rank])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    q.put((rank, cfg.seed, int(clip[1].astype(np.uint64).sum() % 1000003), float(t.item()), int(keys.sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_max_reduction_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, seed0, sum0, t0, k0), (r1, seed1, sum1, t1, k1) = res
+    assert seed0 != seed1 and sum0 != sum1          # different clips per rank
+    assert t0 == t1 == 11.0                         # MAX over ranks
+    assert k0 == k1 == 1
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                         text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
