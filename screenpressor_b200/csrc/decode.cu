@@ -309,33 +309,27 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         }
         const int v = (int)(v0 >> shift);
         const int bonus = (PROB_SCALE - tot) >> shift;
-        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1, fpos = 0, fmax = 0;
-        bool found = false, done = false;
+        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1, fpos = 0;
+        bool found = false;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
+            if (k >= d) break;  // uniform: leaves the unrolled chain as soon as the symbol is placed
             const int fk = (int)((frw[k >> 1] >> (16 * (k & 1))) & 0xFFFF);
-            if (k == maxpos) fmax = fk;
-            if (!done && k < d) {
-                const int sk = (int)((syw[k >> 2] >> (8 * (k & 3))) & 255);
-                const int startFr = cumFr + sk - lastSymb;
-                if (v < startFr)
-                    done = true;
-                else {
-                    const int frk = (fk + (k == maxpos ? bonus : 0)) & 0xFFFF;
-                    if (startFr + frk > v) {
-                        c = sk;
-                        cumFr = startFr;
-                        fr = frk;
-                        fpos = fk;
-                        found = true;
-                        done = true;
-                    } else {
-                        cumFr = startFr + frk;
-                        lastSymb = sk + 1;
-                        pos = k + 1;
-                    }
-                }
+            const int sk = (int)((syw[k >> 2] >> (8 * (k & 3))) & 255);
+            const int startFr = cumFr + sk - lastSymb;
+            if (v < startFr) break;
+            const int frk = (fk + (k == maxpos ? bonus : 0)) & 0xFFFF;
+            if (startFr + frk > v) {
+                c = sk;
+                cumFr = startFr;
+                fr = frk;
+                fpos = fk;
+                found = true;
+                break;
             }
+            cumFr = startFr + frk;
+            lastSymb = sk + 1;
+            pos = k + 1;
         }
         if (!found) {  // a symbol not met yet: width 1
             c = lastSymb + v - cumFr;
@@ -347,7 +341,7 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
                 const int nf = fpos + 50;
                 x.sfreq[pos] = (uint16_t)nf;
                 if (kind == 5) x.cntsum = totFr + 50;
-                if (pos != maxpos && nf > fmax) x.maxpos = (uint8_t)pos;
+                if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;
             } else
                 cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
         }
@@ -535,8 +529,72 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         const int bx0 = bx * 16, by0 = by * 16;
         const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
         int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
-        // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
         PROF_CNT(n_blocks)
+        if ((bt - 1) & 2) {
+            // ---- motion-vector block: a pure gather from the previous frame, written straight to the
+            // frame (no tile, no neighbours): sub-rect from prev at (x+mx, y+my), the rest of a partial
+            // block from prev at the same place (screencap.cpp:1333-1368)
+            PROF_T0
+            if ((bt - 1) & 1) {
+                x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
+                y1 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 1>(e);
+                x2 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 2>(e) + 1;
+                y2 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 3>(e) + 1;
+                if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
+                if (y2 > by0 + bh) y2 = by0 + bh;
+                if (x1 >= x2) x1 = x2 - 1;
+                if (y1 >= y2) y1 = y2 - 1;
+            }
+            int mx = lastmx, my = lastmy;
+            if (!dec_bool(e)) {
+                mx = dec_fxc<512, CX_MV - CX_NTAB + 0>(e) - 256;
+                my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
+            }
+            lastmx = mx; lastmy = my;
+            const int gx = min(max(x1 + mx, 0), g.X - 1), gy = min(max(y1 + my, 0), g.Y - 1);  // corrupt input guard
+            const int cbx = gx >> 4, cby = gy >> 4;
+            PixSrc sq[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // the source rectangle spans at most 2 x 2 blocks of the previous frame
+                const int qx = min(cbx + (q & 1), g.nbx - 1), qy = min(cby + (q >> 1), g.nby - 1);
+                const int b = qy * g.nbx + qx;
+                sq[q] = resolve_src(w, cc.stamp[b] == f ? cc.src_prev[b] : cc.src_cur[b]);
+            }
+            const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
+            uint32_t px[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // all loads first (a source block may be this very block)
+                const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
+                const int x = bx0 + xx, y = by0 + yy;
+                px[u] = 0;
+                if (xx < bw && yy < bh) {
+                    if (x >= x1 && x < x2 && y >= y1 && y < y2) {
+                        const int sx = min(max(x + mx, 0), g.X - 1), sy = min(max(y + my, 0), g.Y - 1);
+                        const int q = ((sx >> 4) > cbx ? 1 : 0) + ((sy >> 4) > cby ? 2 : 0);
+                        px[u] = src_px(q == 0 ? sq[0] : q == 1 ? sq[1] : q == 2 ? sq[2] : sq[3], g, sx, sy);
+                    } else
+                        px[u] = src_px(sP, g, x, y);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
+                if (xx < bw && yy < bh) store_px(frame, g, bx0 + xx, by0 + yy, px[u]);
+            }
+            if (lane == 0) {
+                if (cc.stamp[bi] != f) {
+                    cc.src_prev[bi] = cc.src_cur[bi];
+                    cc.stamp[bi] = f;
+                }
+                cc.src_cur[bi] = f;
+                upd[bi] = 1;
+            }
+            __syncwarp();
+            PROF_ADD(c_mv)
+            continue;
+        }
+        // ---- pixel-coded block, decoded in a shared-memory tile ----
+        // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
         { PROF_T0
         {   // the tile touches four blocks: resolve where each one's pixels live once, then load
             const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
@@ -545,16 +603,22 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             const PixSrc sL = resolve_src(w, bx > 0 ? cc.src_cur[bL] : -1);
             const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
             const bool partial = (bt - 1) & 1;
-            for (int p = lane; p < 17 * 17; p += 32) {
-                const int ty = p / 17, tx = p - ty * 17;
-                const int x = bx0 + tx - 1, y = by0 + ty - 1;
-                uint32_t v = 0;
-                if (x >= 0 && y >= 0 && x < g.X && y < g.Y) {
-                    if (ty == 0) v = src_px(tx == 0 ? sA : sT, g, x, y);
-                    else if (tx == 0) v = src_px(sL, g, x, y);
-                    else if (partial) v = src_px(sP, g, x, y);  // partial block: starts as a copy of prev
+            if (partial) {  // block starts as a copy of the previous frame's block
+                for (int p = lane; p < 17 * 17; p += 32) {
+                    const int ty = p / 17, tx = p - ty * 17;
+                    const int x = bx0 + tx - 1, y = by0 + ty - 1;
+                    uint32_t v = 0;
+                    if (x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : tx == 0 ? sL : sP, g, x, y);
+                    tile[ty][tx] = v;
                 }
-                tile[ty][tx] = v;
+            } else {  // every pixel of the block is coded: only the 33 neighbours are needed
+                for (int p = lane; p < 33; p += 32) {
+                    const int ty = p < 17 ? 0 : p - 16, tx = p < 17 ? p : 0;
+                    const int x = bx0 + tx - 1, y = by0 + ty - 1;
+                    uint32_t v = 0;
+                    if (x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : sL, g, x, y);
+                    tile[ty][tx] = v;
+                }
             }
         }
         __syncwarp();
@@ -571,22 +635,7 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         }
         const int sw = x2 - x1, sh = y2 - y1;
         const uint32_t swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;  // idx / sw == (idx * swinv) >> 16 for idx < 256
-        if ((bt - 1) & 2) {  // motion vector block
-            PROF_T0
-            int mx = lastmx, my = lastmy;
-            if (!dec_bool(e)) {
-                mx = dec_fxc<512, CX_MV - CX_NTAB + 0>(e) - 256;
-                my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
-            }
-            lastmx = mx; lastmy = my;
-            for (int p = lane; p < sw * sh; p += 32) {
-                const int yy = (int)(((uint32_t)p * swinv) >> 16), xx = p - yy * sw;
-                int sx = x1 + xx + mx, sy = y1 + yy + my;
-                sx = min(max(sx, 0), g.X - 1); sy = min(max(sy, 0), g.Y - 1);  // corrupt input guard
-                tile[1 + y1 - by0 + yy][1 + x1 - bx0 + xx] = prev_px(cc, sx, sy);
-            }
-            PROF_ADD(c_mv)
-        } else {  // pixel runs over the sub-rect in its own raster order
+        {  // pixel runs over the sub-rect in its own raster order
             PROF_T0
             int pos = 0, ptype = 0;
             const int npx = sw * sh;
