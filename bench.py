@@ -172,17 +172,28 @@ def run_cuda(args):
     d_out = torch.empty(frames * fb, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
     enc, dec = ScreenCodec(local), ScreenCodec(local)
+    for c in (enc, dec):
+        c.Init(CodecParameters(W, H, 32))
+        c.set_stream(stream.cuda_stream)
+    enc.reserve_clip_output(64 << 20)
+    stage = {"enc_ms": 0.0, "dec_ms": 0.0}
 
     def fresh():
-        for c in (enc, dec):
-            c.Init(CodecParameters(W, H, 32))
-            c.set_stream(stream.cuda_stream)
-        enc.reserve_clip_output(64 << 20)
+        # a new clip: Deinit + Init semantics (prev, models, frame counters), device workspaces are kept
+        enc.Reset()
+        dec.Reset()
 
     def step_device():
         fresh()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
         s, sizes, fts = enc.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=frames)
+        e1.record(stream)
         dec.DecompressClip(s, sizes, fts, device_ptr=d_out.data_ptr())
+        e2.record(stream)
+        e2.synchronize()
+        stage["enc_ms"] += e0.elapsed_time(e1)
+        stage["dec_ms"] += e1.elapsed_time(e2)
         return s, sizes
 
     def step_host():
@@ -222,18 +233,13 @@ def run_cuda(args):
     if rank == 0:
         sampler.start()
     l0 = enc.kernel_launches() + dec.kernel_launches()
-    # launches are counted per codec object and fresh() re-creates them: accumulate manually
-    launches = 0
-
-    def counted_device():
-        nonlocal launches
-        r = step_device()
-        launches += enc.kernel_launches() + dec.kernel_launches()
-        return r
-
-    ms, (s, sizes) = timed(counted_device, args.steps)
+    stage["enc_ms"] = stage["dec_ms"] = 0.0
+    ms, (s, sizes) = timed(step_device, args.steps)
+    launches = enc.kernel_launches() + dec.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * frames * args.steps / (ms / 1e3)
+    enc_fps = frames * args.steps / (stage["enc_ms"] / 1e3)
+    dec_fps = frames * args.steps / (stage["dec_ms"] / 1e3)
 
     # end-to-end leg
     step_host()
@@ -242,6 +248,43 @@ def run_cuda(args):
     ms_e2e, (s2, sizes2) = timed(step_host, args.steps)
     e2e = world * frames * args.steps / (ms_e2e / 1e3)
     stream_bytes = int(sizes.sum())
+
+    # several independent clips in flight on one GPU (decode parallelism is per GOP chain):
+    # `multi` codec pairs, one CUDA stream + host thread each, same clip
+    multi = None
+    if args.multi > 1 and world == 1:
+        import threading as th
+
+        pairs = []
+        for k in range(args.multi):
+            st_k = torch.cuda.Stream()
+            e_k, d_k = ScreenCodec(local), ScreenCodec(local)
+            for c in (e_k, d_k):
+                c.Init(CodecParameters(W, H, 32))
+                c.set_stream(st_k.cuda_stream)
+            e_k.reserve_clip_output(64 << 20)
+            pairs.append((e_k, d_k, torch.empty(frames * fb, dtype=torch.uint8, device="cuda")))
+
+        def work(e_k, d_k, out_k):
+            e_k.Reset(); d_k.Reset()
+            s_k, sz_k, ft_k = e_k.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=frames)
+            d_k.DecompressClip(s_k, sz_k, ft_k, device_ptr=out_k.data_ptr())
+
+        def run_all():
+            ts = [th.Thread(target=work, args=p) for p in pairs]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+
+        run_all()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_all()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert all(torch.equal(p[2], d_in) for p in pairs)
+        multi = {"clips_in_flight": args.multi, "value": args.multi * frames / dt, "unit": "frames/s",
+                 "note": "same metric with several independent 600-frame clips decoded/encoded concurrently on one GPU (wall clock)"}
+        del pairs
 
     # roofline leg: the frame-scan kernel (stage A pass 1), timed alone with CUDA events on its stream
     fresh()
@@ -279,10 +322,19 @@ def run_cuda(args):
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
                 "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "encode_fps": enc_fps, "decode_fps": dec_fps,
+        "multi_clip": multi,
         "clocks": clocks,
         "roofline": {"kernel": "k_frame_scan32", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms},
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms,
+                     "share_of_step": scan_ms / (ms / args.steps),
+                     "note": "the HBM-bound stage (delta / changed-block detection); the step itself is dominated by the "
+                             "decoder's serial GOP chain, see dominant_kernel"},
+        "dominant_kernel": {"kernel": "k_dec_chain", "share_of_step": (stage["dec_ms"] / args.steps) / (ms / args.steps),
+                            "bound": "serial dependency chain of one GOP (one warp, ~6 cycles per issued instruction, profiles/)",
+                            "algorithmic_decode_bytes_per_step": frames * W * H * 8,
+                            "achieved_GBps": frames * W * H * 8 / (stage["dec_ms"] / args.steps / 1e3) / 1e9},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -299,6 +351,7 @@ def main():
     ap.add_argument("--frames", type=int, default=synth.CONFIGS[WORKLOAD].frames)
     ap.add_argument("--ref-frames", type=int, default=200, help="bounded sample for the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", type=int, default=0, help="also measure N independent clips in flight on one GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,7 +26,7 @@ typedef struct scpr_params {
     uint16_t redmask, greenmask, bluemask;   /* 16 bpp only */
     uint32_t high_range_x, high_range_y;     /* motion search ranges; v4 clamps these to 256 (screencap.cpp:79) */
     uint32_t low_range_x, low_range_y;       /* 8, 8 (screenpressor.cpp:377-378) */
-    uint32_t loss;                           /* bits of loss, 0..4; only 0 is built yet */
+    uint32_t loss;                           /* bits of loss, 0..4 (quality -> loss, screenpressor.cpp:418-422) */
 } scpr_params;
 
 typedef struct scpr_codec scpr_codec;
@@ -35,7 +35,7 @@ enum {
     SCPR_OK = 0,
     SCPR_E_CUDA = -1000,        /* a CUDA call failed; scpr_last_error() has the text */
     SCPR_E_PARAM = -1001,       /* bad argument */
-    SCPR_E_UNSUPPORTED = -1002, /* feature outside the built hot path (16 bpp, loss > 0, v2 streams) */
+    SCPR_E_UNSUPPORTED = -1002, /* feature outside the built hot path (16 bpp, v2 streams) */
     SCPR_E_DSTSIZE = -1003,     /* destination buffer too small */
     SCPR_E_NODEVICE = -1004     /* no CUDA device: this library never computes on the CPU */
 };
@@ -45,10 +45,16 @@ int scpr_create(const scpr_params* p, int device, scpr_codec** out);
 /* replaces ScreenCodec::Deinit / ~ScreenCodec (screencap.cpp:1619-1629) */
 void scpr_destroy(scpr_codec* c);
 
+/* Deinit() followed by Init() with the same parameters (what CodecInst does between clips,
+ * screenpressor.cpp:441-447, 343-384), keeping the device workspaces: the next frame starts a new clip. */
+int scpr_reset(scpr_codec* c);
+
 /* replaces ScreenCodec::CompressFrame (screencap.cpp:1632-1692).
  * src: host frame, rows top to bottom, pitch width*4 (32 bpp) or (width*3+3)&~3 (24 bpp).
  * *ftype in: 0 = I requested, 1 = P requested; out: type actually coded (first and flat frames
- * are always I, screencap.cpp:1488-1511).  Returns the byte count written to dst, or < 0. */
+ * are always I, screencap.cpp:1488-1511).  loss = bits of loss for this frame (the clip entry points use
+ * the value given at creation); in lossy mode the `_dev` clip variant masks the caller's frames in place,
+ * as the reference mutates its source buffer.  Returns the byte count written to dst, or < 0. */
 int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss);
 
 /* replaces ScreenCodec::DecompressFrame (screencap.cpp:1695-1743).

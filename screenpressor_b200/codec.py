@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = i32
         fn.argtypes = [vp, vp, vp, vp, i32, vp, i32]
+    lib.scpr_reset.restype = i32
+    lib.scpr_reset.argtypes = [vp]
     lib.scpr_set_stream.restype = i32
     lib.scpr_set_stream.argtypes = [vp, vp]
     lib.scpr_last_error.restype = C.c_char_p
@@ -137,6 +139,10 @@ class ScreenCodec:
         self.frame_bytes = self.pitch * params.height
         self.max_size = params.width * params.height * 6  # CompressGetSize, screenpressor.cpp:386-388
         self._dst = np.empty(self.max_size + 64, dtype=np.uint8)
+
+    def Reset(self) -> None:
+        """Deinit() + Init() with the same parameters, keeping device workspaces (start of a new clip)."""
+        self._check(self._lib.scpr_reset(self._h))
 
     def Deinit(self) -> None:
         if self._h:

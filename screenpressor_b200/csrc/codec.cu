@@ -115,9 +115,9 @@ int scpr_create(const scpr_params* p, int device, scpr_codec** out) {
         set_error("bits_per_pixel %d: only 24 and 32 are built", (int)p->bits_per_pixel);
         return SCPR_E_UNSUPPORTED;
     }
-    if (p->loss != 0) {
-        set_error("lossy modes are not built yet (loss must be 0)");
-        return SCPR_E_UNSUPPORTED;
+    if (p->loss > 5) {
+        set_error("loss must be 0..5 bits");
+        return SCPR_E_PARAM;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -129,6 +129,7 @@ int scpr_create(const scpr_params* p, int device, scpr_codec** out) {
     scpr_codec* c = new scpr_codec();
     c->p = *p;
     c->device = device;
+    c->loss = (int)p->loss;
     Geo& g = c->g;
     g.X = (int)p->width;
     g.Y = (int)p->height;
@@ -164,9 +165,24 @@ void scpr_destroy(scpr_codec* c) {
                    &c->ftype, &c->blocks, &c->pframes, &c->runs, &c->bts_rle, &c->ihdr, &c->desc, &c->exit_tab, &c->entry,
                    &c->starts, &c->chunk_cnt, &c->frame_ev_off, &c->events, &c->intervals, &c->sorted, &c->seg_off,
                    &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
-                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym};
+                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym, &c->summary2};
     for (DBuf* b : all) b->release();
     delete c;
+}
+
+int scpr_reset(scpr_codec* c) {
+    if (!c) return SCPR_E_PARAM;
+    CK(cudaSetDevice(c->device));
+    c->fn = 0;
+    c->last_was_flat = false;
+    c->have_models = false;
+    c->loss = (int)c->p.loss;
+    c->dec_created = false;
+    c->dec_last_was_flat = false;
+    CK(cudaMemsetAsync(c->prev.p, 0, c->g.frame_bytes, c->st));
+    CK(cudaMemsetAsync(c->mvs.p, 0, (size_t)c->g.nb * sizeof(int2), c->st));
+    if (c->dec_prev.p) CK(cudaMemsetAsync(c->dec_prev.p, 0, (size_t)c->dec_prev_pitch * c->g.Y, c->st));
+    return SCPR_OK;
 }
 
 int scpr_set_stream(scpr_codec* c, void* cuda_stream) {
@@ -200,6 +216,15 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     CK(cudaMemsetAsync(c->ftype.p, FT_P, (size_t)n, st));
     launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, st,
                       &c->launches);
+    if (c->loss) {
+        // lossy mode: the flat test above ran on the raw frames (IsFlat precedes DoLoss); now mask the
+        // non-flat frames in place and redo the differencing on the masked pixels
+        launch_apply_loss(const_cast<uint8_t*>(d_frames), n, g, (const FrameSummary*)c->summary.p, c->loss, st, &c->launches);
+        TRY(c->summary2.ensure((size_t)n * sizeof(FrameSummary)));
+        CK(cudaMemsetAsync(c->summary2.p, 0, (size_t)n * sizeof(FrameSummary), st));
+        launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary2.p, st,
+                          &c->launches);
+    }
     tm.mark("scan");
     launch_compact_changed((const uint32_t*)c->blkinfo.p, (const uint8_t*)c->ftype.p, n, g, (uint32_t*)c->chg_list.p,
                            (PFrameHdr*)c->hdr.p, st, &c->launches);
@@ -208,6 +233,12 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     std::vector<PFrameHdr> hdr(n);
     CK(cudaMemcpyAsync(summary.data(), c->summary.p, (size_t)n * sizeof(FrameSummary), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hdr.data(), c->hdr.p, (size_t)n * sizeof(PFrameHdr), cudaMemcpyDeviceToHost, st));
+    if (c->loss) {  // "changed" comes from the masked pass, flatness and the flat colour from the raw one
+        std::vector<FrameSummary> s2(n);
+        CK(cudaMemcpyAsync(s2.data(), c->summary2.p, (size_t)n * sizeof(FrameSummary), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int f = 0; f < n; f++) summary[f].changed = s2[f].changed;
+    }
     CK(cudaStreamSynchronize(st));
 
     // ---- host plan: frame types and chains (CScreenCapt::CompressFrame, screencap.cpp:1456-1518) --
@@ -518,10 +549,8 @@ int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const ui
 
 int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss) {
     if (!c || !src || !dst || !ftype || dst_cap <= 0) return SCPR_E_PARAM;
-    if (loss != 0) {
-        set_error("lossy modes are not built yet (loss must be 0)");
-        return SCPR_E_UNSUPPORTED;
-    }
+    if (loss < 0 || loss > 5) return SCPR_E_PARAM;
+    c->loss = loss;  // SetupLossMask on change, screencap.cpp:1635-1638
     const uint8_t key = *ftype ? 0 : 1;
     uint32_t size = 0;
     uint8_t ft = 0;

@@ -36,6 +36,7 @@ struct scpr_codec {
     uint64_t launches = 0;
 
     // ---- encoder state carried between calls (CScreenCapt members, screencap.h:445-463) ----------
+    int loss = 0;                    // bits of loss applied to non-flat frames (SetupLossMask, screencap.cpp:127-139)
     unsigned fn = 0;                 // coded (non-flat) frames so far
     bool last_was_flat = false;
     uint8_t last_flat_clr[3] = {0, 0, 0};
@@ -46,6 +47,7 @@ struct scpr_codec {
     int n_states = 0, cur_state = 0;
 
     // ---- encoder workspaces ---------------------------------------------------------------------
+    scpr::DBuf summary2;
     scpr::DBuf frames, blkinfo, summary, chg_list, hdr, ftype, blocks, pframes, runs, bts_rle, cands;
     scpr::DBuf ihdr, desc, exit_tab, entry, starts, chunk_cnt;
     scpr::DBuf frame_ev_off, events, intervals, sorted, sorted_sym, seg_off, chunk_hist, chunk_base, chains, rblks, scratch, out;

@@ -258,14 +258,16 @@ __device__ __forceinline__ int dec_fx(Ent& e, int t, int off, int row) {
     }
     const uint32_t fc = fs.fc[off + j];
     const int left = fs.left[t] - 1;
-    if (e.lane == 0) {
-        fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
-        fs.left[t] = left;
-    }
+    // every lane of the (converged) warp performs the same read-modify-write with the same values:
+    // no lane predicate, no divergence, no barrier on the per-symbol path
+    fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
+    fs.left[t] = left;
     rdec_advance(e, fc & 0xFFFFu, fc >> 16);
     rdec_count(e);
-    __syncwarp();
-    if (left == 0) fixed_rebuild(fs, t, e.lane, true);
+    if (left == 0) {
+        __syncwarp();
+        fixed_rebuild(fs, t, e.lane, true);
+    }
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return j;
 }
@@ -281,14 +283,22 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
     ColorState& x = e.m->color[id];
     const int kind = x.kind;
     int c;
-    if (kind >= 6) {  // flat table: two ballot levels over cum[256], then lane 0 updates
+    if (kind >= 6) {  // flat table: two ballot levels over cum[256]
         const uint32_t v = e.x & (PROB_SCALE - 1);
         const bool le = x.cum[e.lane * 8] <= v;
         const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
         const bool le2 = e.lane < 8 && x.cum[L * 8 + (e.lane & 7)] <= v;
         c = L * 8 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
         const uint32_t freq = x.freq[c], cum = x.cum[c];
-        if (e.lane == 0) cc_encode_counted(x, c);
+        const int cn = x.cnt[c], cs = x.cntsum;
+        const int step = kind == 7 ? 16 : (25 << x.fshift);
+        if (cn != 0 && cs + 2 * step <= PROB_SCALE) {  // symbol already met, no rescale: count it (all lanes, same values)
+            x.cnt[c] = (uint16_t)(cn + step);
+            x.cntsum = cs + step;
+        } else {
+            if (e.lane == 0) cc_encode_counted(x, c);  // new symbol, promotion or rescale
+            __syncwarp();
+        }
         rdec_advance(e, cum, freq);
     } else if (kind >= 4) {  // SmallContext: walk the (<= 16) sorted symbols, ans_contexts.h:238-283
         const uint32_t v0 = e.x & (PROB_SCALE - 1);
@@ -336,21 +346,21 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
             cumFr = v;
             fr = 1;
         }
-        if (e.lane == 0) {
-            if (found && totFr + 100 <= PROB_SCALE) {  // hot path: count, no rescale (ans_contexts.h:211-214)
-                const int nf = fpos + 50;
-                x.sfreq[pos] = (uint16_t)nf;
-                if (kind == 5) x.cntsum = totFr + 50;
-                if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;
-            } else
-                cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
+        if (found && totFr + 100 <= PROB_SCALE) {  // hot path: count, no rescale (ans_contexts.h:211-214); all lanes, same values
+            const int nf = fpos + 50;
+            x.sfreq[pos] = (uint16_t)nf;
+            if (kind == 5) x.cntsum = totFr + 50;
+            if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;  // sfreq[maxpos] is not the entry just written
+        } else {
+            if (e.lane == 0) cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
+            __syncwarp();
         }
         rdec_advance(e, (uint32_t)(cumFr << shift) & 0xFFFFu, (uint32_t)(fr << shift) & 0xFFFFu);
     } else {
         c = *e.p++;
         if (e.lane == 0) cc_update_raw(x, c, e.f0);
+        __syncwarp();  // lane 0's model stores are visible to the whole warp before the next symbol
     }
-    __syncwarp();  // lane 0's model stores are visible to the whole warp before the next symbol
     rdec_count(e);
     PROF_ADD(c_color) PROF_CNT(n_color)
     return c;

@@ -202,6 +202,38 @@ __global__ void __launch_bounds__(256) k_compact_changed(const uint32_t* __restr
     }
 }
 
+// Lossy modes (SetupLossMask / CMD_DOLOSS, screencap.cpp:127-139, 852-861): every colour byte of a
+// non-flat frame becomes (b & ~(2^loss - 1)) | (2^loss >> 1), in place, before differencing; the masked
+// frame is what the next frame is compared against.  Flat frames are left untouched (the reference
+// stores them in prev before DoLoss runs, screencap.cpp:1488-1499).
+__global__ void __launch_bounds__(256) k_apply_loss(uint8_t* __restrict__ frames, int n, Geo g, const FrameSummary* __restrict__ summary,
+                                                    uint32_t keep, uint32_t corr) {
+    const size_t words_per_frame = g.frame_bytes / 4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * words_per_frame) return;
+    const int f = (int)(i / words_per_frame);
+    if (!summary[f].notflat) return;
+    uint32_t* p = reinterpret_cast<uint32_t*>(frames) + i;
+    *p = (*p & keep) | corr;
+}
+
+void launch_apply_loss(uint8_t* frames, int n, const Geo& g, const FrameSummary* summary, int loss, cudaStream_t st, uint64_t* launches) {
+    uint32_t m = (1u << loss) - 1;
+    m |= m << 8;
+    m |= m << 16;
+    uint32_t cm = (1u << loss) >> 1;
+    cm |= cm << 8;
+    cm |= cm << 16;
+    const size_t words = (size_t)n * (g.frame_bytes / 4);
+    uint32_t keep = ~m;
+    if (g.bpp == 4) {  // the alpha byte is not part of the picture: leave it alone
+        keep |= 0xFF000000u;
+        cm &= 0x00FFFFFFu;
+    }
+    k_apply_loss<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(frames, n, g, summary, keep, cm);
+    ++*launches;
+}
+
 void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
                        FrameSummary* summary, cudaStream_t st, uint64_t* launches) {
     if (g.bpp == 4 && (g.X & 3) == 0) {

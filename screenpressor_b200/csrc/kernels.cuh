@@ -65,6 +65,7 @@ struct RansBlk {
 // ---- stage A --------------------------------------------------------------------------------
 void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
                        FrameSummary* summary, cudaStream_t st, uint64_t* launches);
+void launch_apply_loss(uint8_t* frames, int n, const Geo& g, const FrameSummary* summary, int loss, cudaStream_t st, uint64_t* launches);
 void launch_compact_changed(const uint32_t* blkinfo, const uint8_t* ftype, int n, const Geo& g, uint32_t* chg_list,
                             PFrameHdr* hdr, cudaStream_t st, uint64_t* launches);
 

@@ -189,6 +189,27 @@ def test_flat_and_duplicate_frames(scpr, oracle_built):
         assert np.array_equal(dec.DecompressFrame(got[i][0], None, got[i][1]), frames[i].reshape(-1)), i
 
 
+@pytest.mark.parametrize("loss", [1, 2, 3, 4])
+def test_lossy_modes_match_oracle(scpr, oracle_built, loss):
+    """quality -> loss bits (screenpressor.cpp:418-422): masked pixels, masked frame becomes `prev`"""
+    for (w, h, bpp, seed) in [(200, 100, 32, 77), (201, 100, 24, 78), (320, 200, 32, 79)]:
+        clip, keys = fuzz_clip(w, h, 20, seed + loss, bpp, 16)
+        orc = oracle_built.OracleCodec(w, h, bpp, loss)
+        want = [orc.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), not keys[i]) for i in range(len(clip))]
+        enc = scpr.ScreenCodec(0)
+        enc.Init(scpr.CodecParameters(w, h, bpp, loss=loss))
+        got = _split(*enc.CompressClip(clip, keys))
+        assert got == want, (w, h, bpp, loss, [i for i in range(len(got)) if got[i] != want[i]][:5])
+        enc2 = scpr.ScreenCodec(0)
+        enc2.Init(scpr.CodecParameters(w, h, bpp))
+        got2 = [enc2.CompressFrame(clip[i], 0 if keys[i] else 1, loss) for i in range(len(clip))]
+        assert got2 == want
+        dec = _new(scpr, w, h, bpp)
+        dorc = oracle_built.OracleCodec(w, h, bpp, loss)
+        for i, (data, ft) in enumerate(want):
+            assert np.array_equal(dec.DecompressFrame(data, None, ft), dorc.decompress(data, ft)), (loss, i)
+
+
 def test_error_behaviour(scpr):
     dec = _new(scpr, 64, 48, 32)
     with pytest.raises(scpr.ScprError):          # P before any I: the reference returns 0 (screencap.cpp:1699)
