@@ -15,6 +15,7 @@
 // the chain only writes the blocks a frame changes (decoded in a shared-memory tile), tracks for
 // every block which frame holds its current pixels, and k_dec_fill afterwards gathers every
 // untouched block of every frame from that source in one HBM-bound pass.
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -103,33 +104,64 @@ __device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, in
     }
 }
 
-// ---- entropy state ------------------------------------------------------------------------------------
-// The rANS state, the byte cursor and the colour-context registers are held identically by all 32
-// lanes (every lane executes the same arithmetic on the same values), so no broadcast is needed
-// between symbols; only model *stores* are done by one lane.
-//
-// With one resident warp per chain the decoder is bound by the latency of its dependent
-// instruction chain, so the per-symbol path is kept to two shared-memory loads:
-//   * the 21 fixed tables live in shared memory for the whole chain: fc[] = freq<<16|cum per symbol,
-//     cnt[] the adaptive counters, and -- because a table's intervals are frozen between rescales
-//     (ans_contexts.h:1070-1091) -- a direct slot -> symbol map lut[4096] per table that is rebuilt
-//     together with the table (every ~128 symbols of that table, by the whole warp).  A symbol is
-//     then  v = x & 4095;  sym = lut[v];  fc = fc[sym];  x = freq*(x>>12) + v - cum.
-//   * "events until the next rescale" is a countdown per table (the rescale instant depends only on
-//     the number of events, each adds 16 to cntsum).
+// ---- shared memory, addressed explicitly -------------------------------------------------------------
+// One resident warp per chain is bound by the latency of its dependent instruction chain, so the
+// per-symbol path must be short: all table state lives in shared memory and is reached with 32-bit
+// shared addresses (ld.shared / st.shared, never generic loads).
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w));
+}
+
+// Fixed tables t = 0..20 (context id CX_NTAB + t): 0-5 ntab[ptype], 6 ntab2, 7 xx, 8 bt, 9-12 sxy, 13-14 mv,
+// 15-20 ptype[last].  Because a table's intervals are frozen between rescales (ans_contexts.h:1070-1091),
+// derived look-up structures are rebuilt together with the table (every ~128 symbols of that table, by
+// the whole warp):
+//   * ntab[0..5] (one symbol per pixel run, the hottest tables): lut32[4096] = sym<<24 | freq<<12 | cum,
+//     so a run length costs ONE shared load on the rANS dependency chain;
+//   * ptype[0..5] (6 symbols): the cumulative frequencies as 8 halfwords, fetched with one 128-bit load
+//     whose address does not depend on the rANS state; the symbol comes from five compares;
+//   * the other <= 256-symbol tables: slot -> symbol bytes lut8[4096], then fc[sym];
+//   * the two 512-symbol MV tables: two ballot levels over fc[].
+// "Events until the next rescale" is a countdown per table (the rescale instant depends only on the
+// number of events, each adds 16 to cntsum).
 constexpr int FX_TOTAL = 3192;
-constexpr int LUT_ROW = 32 * 132;  // 128 slots per lane + 4 bytes padding: conflict-free fills
-constexpr int N_LUT = 19;          // every table except the two 512-symbol MV tables
+constexpr int LUT8_ROW = 32 * 132;  // 128 slots per lane + 4 bytes padding: conflict-free fills
+constexpr uint32_t S_FC = 0;                             // u32[FX_TOTAL]: freq << 16 | cum
+constexpr uint32_t S_CNT = S_FC + FX_TOTAL * 4;          // u16[FX_TOTAL]: adaptive counters
+constexpr uint32_t S_LEFT = S_CNT + FX_TOTAL * 2;        // i32[24]
+constexpr uint32_t S_PCUM = S_LEFT + 24 * 4;             // 6 x u16[8]
+constexpr uint32_t S_LUT8 = S_PCUM + 6 * 16;             // 7 x LUT8_ROW (tables 6..12)
+constexpr uint32_t S_LUT32 = S_LUT8 + 7 * LUT8_ROW;      // 6 x u32[4096] (tables 0..5), XOR-swizzled
+constexpr uint32_t S_KMAP = S_LUT32 + 6 * 16384;         // u8[12288]: kind of every colour context
+constexpr uint32_t S_TILE = S_KMAP + NUM_COLOR_CX;       // u32[17][17]
+constexpr uint32_t S_BTS = S_TILE + 1168;                // u8[nb]
+static_assert(S_PCUM % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0, "shared layout alignment");
 __host__ __device__ constexpr int fx_off(int t) {
     return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
 }
-__host__ __device__ constexpr int fx_lut(int t) { return t < 13 ? t : t - 2; }
-struct FixedSmem {
-    uint32_t fc[FX_TOTAL];
-    uint16_t cnt[FX_TOTAL];
-    int left[24];
-    uint8_t lut[N_LUT][LUT_ROW];
-};
 
 #ifdef SCPR_PROF
 #define PROF_T0 const long long t0__ = clock64();
@@ -141,49 +173,78 @@ struct FixedSmem {
 #define PROF_CNT(field)
 #endif
 
+// The rANS state, the byte window and the colour-context registers are held identically by all 32
+// lanes (every lane executes the same arithmetic on the same values), so no broadcast is needed
+// between symbols.  The stream is read through a three-word window (aligned 32-bit loads issued two
+// words ahead), so no load sits on the renormalisation path.
 struct Ent {
 #ifdef SCPR_PROF
     long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
-              c_hdr = 0, c_total = 0;
+              c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0, c_raw = 0, n_raw = 0;
 #endif
-    const uint8_t* p;
     uint32_t x;
-    int ndec;
+    uint32_t w0, w1, w2, k8;  // window: stream bytes from bit k8 of w0 on
+    const uint32_t* wp;       // address of w0
+    int nleft;                // symbols until the next RansDecInit
     uint32_t cx, cx1;
+    uint32_t sb;              // shared-memory base address
     ModelState* m;
-    FixedSmem* fs;
     int f0;
     int lane;
 };
-__device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
-    e.x = (uint32_t)e.p[0] | ((uint32_t)e.p[1] << 8) | ((uint32_t)e.p[2] << 16) | ((uint32_t)e.p[3] << 24);
-    e.p += 4;
+__device__ __forceinline__ void rd_seek(Ent& e, const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    e.wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    e.k8 = (uint32_t)(a & 3) * 8;
+    e.w0 = e.wp[0];
+    e.w1 = e.wp[1];
+    e.w2 = e.wp[2];
 }
-__device__ __forceinline__ void rdec_count(Ent& e) {  // re-init every 131072 symbols (screencap.h:327-331)
-    if (++e.ndec == RANS_BLOCK) {
-        rdec_init(e);
-        e.ndec = 0;
+__device__ __forceinline__ uint32_t rd_peek(const Ent& e) { return __funnelshift_r(e.w0, e.w1, e.k8); }
+__device__ __forceinline__ void rd_skip(Ent& e, uint32_t bits) {  // bits = 8 * bytes, <= 32
+    e.k8 += bits;
+    if (e.k8 >= 32) {
+        e.k8 -= 32;
+        e.w0 = e.w1;
+        e.w1 = e.w2;
+        e.w2 = e.wp[3];
+        e.wp++;
     }
 }
-__device__ __forceinline__ void rdec_advance(Ent& e, uint32_t start, uint32_t freq) {  // RansDecAdvance
-    uint32_t x = e.x;
-    x = freq * (x >> PROB_BITS) + (x & (PROB_SCALE - 1)) - start;
-    while (x < RANS_L) x = (x << 8) | *e.p++;
-    e.x = x;
+__device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
+    e.x = rd_peek(e);
+    rd_skip(e, 32);
+}
+__device__ __forceinline__ void rdec_count(Ent& e) {  // re-init every 131072 symbols (screencap.h:327-331)
+    if (--e.nleft == 0) {
+        rdec_init(e);
+        e.nleft = RANS_BLOCK;
+    }
+}
+// RansDecAdvance with the symbol's slot offset d = (x & 4095) - start already formed; a valid stream needs at
+// most two renormalisation bytes (x >= 2^11 after the update), taken branch-free from the window
+__device__ __forceinline__ void rdec_advance(Ent& e, uint32_t d, uint32_t freq) {
+    const uint32_t x = freq * (e.x >> PROB_BITS) + d;
+    const uint32_t t = rd_peek(e);
+    const bool p1 = x < RANS_L, p2 = x < (1u << 15);
+    const uint32_t x1 = (x << 8) | (t & 0xFFu), x2 = (x << 16) | __byte_perm(t, 0, 0x4401);
+    e.x = p2 ? x2 : (p1 ? x1 : x);
+    rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
 }
 
 // (Re)build the derived data of fixed table t from its counters: `rescale` applies the
 // FixedSizeRansCtx rescale (freq := cnt, cum := prefix, cnt -= freq>>1, ans_contexts.h:1075-1090);
 // without it the intervals in fc[] are kept (table just loaded).  Then the countdown and the
-// slot -> symbol map.  Whole warp.
-__device__ __noinline__ void fixed_rebuild(FixedSmem& fs, int t, int lane, bool rescale) {
+// look-up structure of the table's class.  Whole warp.
+__device__ __noinline__ void fixed_rebuild(uint32_t sb, int t, int lane, bool rescale) {
     const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
+    const uint32_t fcb = sb + S_FC + off * 4, cnb = sb + S_CNT + off * 2;
     const int per = (nsym + 31) >> 5, b = lane * per;
     uint32_t ns = 0;
     if (rescale) {
         uint32_t sum = 0;
         for (int j = 0; j < per; j++)
-            if (b + j < nsym) sum += fs.cnt[off + b + j];
+            if (b + j < nsym) sum += lds16(cnb + (b + j) * 2);
         uint32_t inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -193,189 +254,399 @@ __device__ __noinline__ void fixed_rebuild(FixedSmem& fs, int t, int lane, bool 
         uint32_t cf = inc - sum;
         for (int j = 0; j < per; j++)
             if (b + j < nsym) {
-                const uint32_t fr = fs.cnt[off + b + j];
-                fs.fc[off + b + j] = (fr << 16) | cf;
+                const uint32_t fr = lds16(cnb + (b + j) * 2);
+                sts32(fcb + (b + j) * 4, (fr << 16) | cf);
                 cf += fr;
                 const uint32_t nc = fr - (fr >> 1);
-                fs.cnt[off + b + j] = (uint16_t)nc;
+                sts16(cnb + (b + j) * 2, nc);
                 ns += nc;
             }
     } else {
         for (int j = 0; j < per; j++)
-            if (b + j < nsym) ns += fs.cnt[off + b + j];
+            if (b + j < nsym) ns += lds16(cnb + (b + j) * 2);
     }
     const int cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
-    if (lane == 0) fs.left[t] = (PROB_SCALE - 16 - cntsum) / 16 + 1;  // events until cntsum + 16 > 4096
+    if (lane == 0) sts32(sb + S_LEFT + t * 4, (uint32_t)((PROB_SCALE - 16 - cntsum) / 16 + 1));  // events until cntsum + 16 > 4096
     __syncwarp();
-    if (nsym > 256) return;
-    // slot -> symbol map: lane owns slots [128*lane, 128*lane + 128)
-    uint8_t* row = fs.lut[fx_lut(t)] + lane * 132;
+    if (t >= 15) {  // ptype: c0..c5, c6 = total
+        if (lane < 8) {
+            uint32_t c = 0xFFFFu;
+            if (lane < 6) c = lds32(fcb + lane * 4) & 0xFFFFu;
+            else if (lane == 6) {
+                const uint32_t fc = lds32(fcb + 5 * 4);
+                c = (fc & 0xFFFFu) + (fc >> 16);
+            }
+            sts16(sb + S_PCUM + (t - 15) * 16 + lane * 2, c);
+        }
+        __syncwarp();
+        return;
+    }
+    if (t >= 13) return;
+    // slot -> symbol: lane owns slots [128*lane, 128*lane + 128)
     const int s0 = lane * 128;
     int lo = 0, hi = nsym - 1;  // last symbol whose cum <= s0
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if ((int)(fs.fc[off + mid] & 0xFFFFu) <= s0) lo = mid; else hi = mid - 1;
+        if ((int)(lds32(fcb + mid * 4) & 0xFFFFu) <= s0) lo = mid; else hi = mid - 1;
     }
     int j = lo;
-    uint32_t fcj = fs.fc[off + j];
+    uint32_t fcj = lds32(fcb + j * 4);
     int endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
-    for (int wd = 0; wd < 32; wd++) {
-        const int s = s0 + 4 * wd;
-        uint32_t word;
-        if (s + 4 <= endj || j == nsym - 1)
-            word = (uint32_t)j * 0x01010101u;
-        else {
-            word = 0;
+    if (t < 6) {
+        // entry = sym<<24 | freq<<12 | cum (freq, cum < 4096 for a table of >= 2 symbols).  Slot s is stored at
+        // word s ^ ((s >> 5) & 0x1C): for this lane's 128 slots that is an XOR of the 16-byte group index with
+        // lane & 7, which spreads the 8 lanes of a quarter warp over all banks (conflict-free 128-bit stores).
+        const uint32_t row = sb + S_LUT32 + (uint32_t)t * 16384u + (uint32_t)s0 * 4u;
+        const uint32_t swz = (uint32_t)(lane & 7) << 4;
+        for (int g = 0; g < 32; g++) {
+            const int s = s0 + 4 * g;
+            uint32_t w[4];
+            if (s + 4 <= endj || j == nsym - 1) {
+                w[0] = w[1] = w[2] = w[3] = ((uint32_t)j << 24) | ((fcj >> 16) << 12) | (fcj & 0xFFFu);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                while (s + k >= endj && j < nsym - 1) {
-                    j++;
-                    fcj = fs.fc[off + j];
-                    endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
+                for (int k = 0; k < 4; k++) {
+                    while (s + k >= endj && j < nsym - 1) {
+                        j++;
+                        fcj = lds32(fcb + j * 4);
+                        endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
+                    }
+                    w[k] = ((uint32_t)j << 24) | ((fcj >> 16) << 12) | (fcj & 0xFFFu);
                 }
-                word |= (uint32_t)j << (8 * k);
             }
+            sts128(row + (((uint32_t)g << 4) ^ swz), w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint32_t*>(row + 4 * wd) = word;
+    } else {
+        const uint32_t row = sb + S_LUT8 + (uint32_t)(t - 6) * LUT8_ROW + (uint32_t)lane * 132u;
+        for (int g = 0; g < 32; g++) {
+            const int s = s0 + 4 * g;
+            uint32_t word;
+            if (s + 4 <= endj || j == nsym - 1)
+                word = (uint32_t)j * 0x01010101u;
+            else {
+                word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    while (s + k >= endj && j < nsym - 1) {
+                        j++;
+                        fcj = lds32(fcb + j * 4);
+                        endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
+                    }
+                    word |= (uint32_t)j << (8 * k);
+                }
+            }
+            sts32(row + 4 * g, word);
+        }
     }
     __syncwarp();
 }
 
-// decodeF (screencap.h:346-359) for table t (0..20) with NSYM symbols; off = fx_off(t), row = fx_lut(t)
-template <int NSYM>
-__device__ __forceinline__ int dec_fx(Ent& e, int t, int off, int row) {
-    PROF_T0
-    FixedSmem& fs = *e.fs;
-    const uint32_t v = e.x & (PROB_SCALE - 1);
-    int j;
-    if (NSYM <= 256) {
-        j = fs.lut[row][v + ((v >> 7) << 2)];
-    } else {  // 512 symbols: two ballot levels over the cumulative frequencies
-        const bool le = (fs.fc[off + e.lane * 16] & 0xFFFFu) <= v;
-        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
-        const bool le2 = e.lane < 16 && (fs.fc[off + L * 16 + (e.lane & 15)] & 0xFFFFu) <= v;
-        j = L * 16 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
-    }
-    const uint32_t fc = fs.fc[off + j];
-    const int left = fs.left[t] - 1;
-    // every lane of the (converged) warp performs the same read-modify-write with the same values:
-    // no lane predicate, no divergence, no barrier on the per-symbol path
-    fs.cnt[off + j] = (uint16_t)(fs.cnt[off + j] + 16);
-    fs.left[t] = left;
-    rdec_advance(e, fc & 0xFFFFu, fc >> 16);
+// common tail of a fixed-table symbol: count it (every lane of the converged warp performs the same
+// read-modify-write with the same values: no lane predicate, no divergence, no barrier on the per-symbol
+// path), run the countdown, rebuild the table when it expires
+__device__ __forceinline__ void fx_update(Ent& e, int t, int off, int sym) {
+    const uint32_t ca = e.sb + S_CNT + (uint32_t)(off + sym) * 2u, la = e.sb + S_LEFT + (uint32_t)t * 4u;
+    sts16(ca, lds16(ca) + 16);
+    const uint32_t left = lds32(la) - 1;
+    sts32(la, left);
     rdec_count(e);
     if (left == 0) {
         __syncwarp();
-        fixed_rebuild(fs, t, e.lane, true);
+#ifdef SCPR_PROF
+        const long long tr__ = clock64();
+#endif
+        fixed_rebuild(e.sb, t, e.lane, true);
+#ifdef SCPR_PROF
+        e.c_rebuild += clock64() - tr__;
+        e.n_rebuild++;
+#endif
     }
+}
+
+// run length through ntab[ptype] (decodeN, screencap.h:346-359, 361)
+__device__ __forceinline__ int dec_n(Ent& e, int ptype) {
+    PROF_T0
+    const uint32_t v = e.x & (PROB_SCALE - 1);
+    const uint32_t en = lds32(e.sb + S_LUT32 + ((uint32_t)ptype << 14) + ((v ^ ((v >> 5) & 0x1Cu)) << 2));
+    const int sym = (int)(en >> 24);
+    rdec_advance(e, v - (en & 0xFFFu), (en >> 12) & 0xFFFu);
+    fx_update(e, ptype, ptype << 8, sym);
+    PROF_ADD(c_fixed) PROF_CNT(n_fixed)
+    return sym;
+}
+// pixel type through ptypetab[last] (decodeP)
+__device__ __forceinline__ int dec_ptype(Ent& e, int last) {
+    PROF_T0
+    const uint4 q = lds128(e.sb + S_PCUM + (uint32_t)last * 16u);
+    const uint32_t v = e.x & (PROB_SCALE - 1);
+    const uint32_t c1 = q.x >> 16, c2 = q.y & 0xFFFFu, c3 = q.y >> 16, c4 = q.z & 0xFFFFu, c5 = q.z >> 16, c6 = q.w & 0xFFFFu;
+    const bool g1 = v >= c1, g2 = v >= c2, g3 = v >= c3, g4 = v >= c4, g5 = v >= c5;
+    const int sym = (int)g1 + (int)g2 + (int)g3 + (int)g4 + (int)g5;
+    // the cumulative frequencies are strictly increasing: cum = the largest one <= v, next = the smallest one > v
+    const uint32_t cum = max(max(g1 ? c1 : 0u, g2 ? c2 : 0u), max(g3 ? c3 : 0u, max(g4 ? c4 : 0u, g5 ? c5 : 0u)));
+    const uint32_t nxt = min(min(min(g1 ? c6 : c1, g2 ? c6 : c2), min(g3 ? c6 : c3, g4 ? c6 : c4)), g5 ? c6 : c5);
+    rdec_advance(e, v - cum, nxt - cum);
+    fx_update(e, 15 + last, 3144 + 8 * last, sym);
+    PROF_ADD(c_fixed) PROF_CNT(n_fixed)
+    return sym;
+}
+// decodeF for the remaining tables (compile-time table T with NSYM symbols)
+template <int NSYM, int T>
+__device__ __forceinline__ int dec_fxc(Ent& e) {
+    PROF_T0
+    constexpr int off = fx_off(T);
+    const uint32_t fcb = e.sb + S_FC + off * 4;
+    const uint32_t v = e.x & (PROB_SCALE - 1);
+    int j;
+    if (NSYM <= 256) {
+        j = (int)lds8(e.sb + S_LUT8 + (uint32_t)(T - 6) * LUT8_ROW + v + ((v >> 7) << 2));
+    } else {  // 512 symbols: two ballot levels over the cumulative frequencies
+        const bool le = (lds32(fcb + e.lane * 64) & 0xFFFFu) <= v;
+        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
+        const bool le2 = e.lane < 16 && (lds32(fcb + (L * 16 + (e.lane & 15)) * 4) & 0xFFFFu) <= v;
+        j = L * 16 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
+    }
+    const uint32_t fc = lds32(fcb + j * 4);
+    rdec_advance(e, v - (fc & 0xFFFFu), fc >> 16);
+    fx_update(e, T, off, j);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return j;
 }
-template <int NSYM, int T>
-__device__ __forceinline__ int dec_fxc(Ent& e) { return dec_fx<NSYM>(e, T, fx_off(T), fx_lut(T)); }
-__device__ __forceinline__ int dec_n(Ent& e, int ptype) { return dec_fx<256>(e, ptype, ptype << 8, ptype); }
-__device__ __forceinline__ int dec_ptype(Ent& e, int last) { return dec_fx<6>(e, 15 + last, 3144 + 8 * last, 13 + last); }
+__device__ __forceinline__ int dec_bool(Ent& e) {  // decodeBool
+    const uint32_t v = e.x & (PROB_SCALE - 1);
+    const int flag = v >= PROB_SCALE / 2;
+    rdec_advance(e, v & (PROB_SCALE / 2 - 1), PROB_SCALE / 2);
+    rdec_count(e);
+    return flag;
+}
 
-// ---- colour contexts (global memory, L1 resident working set) --------------------------------------------
-// find: uniform (all lanes); update: lane 0.
+// ---- colour contexts (global memory; the 128-byte head of a context is one L1 line) ---------------------
+// The search is spread over the lanes: every lane tests its own entries against the slot and forms its own
+// candidate successor state, a ballot names the winner, one shuffle delivers it.  Counting, rescaling and
+// the SmallContext prefix sums are done by the lanes in parallel as well; only first occurrences of a
+// symbol and promotions between kinds go through the serial state machine of models.cuh on lane 0.
+constexpr int CS_SENT = 64, CS_CNT = 128, CS_FREQ = 640, CS_CUM = 1152;
+static_assert(offsetof(ColorState, sent) == CS_SENT && offsetof(ColorState, cnt) == CS_CNT && offsetof(ColorState, freq) == CS_FREQ &&
+                  offsetof(ColorState, cum) == CS_CUM && offsetof(ColorState, ssym) == 16 && offsetof(ColorState, sfreq) == 32,
+              "ColorState layout");
+
+// after the serial state machine touched a context: publish its kind, and for a SmallContext rebuild the
+// packed entries (and the cached totFr of kind 4, which the reference recomputes on every call, :303)
+__device__ __noinline__ void color_refresh(ModelState* m, uint32_t sb, int lane, int id) {
+    ColorState& x = m->color[id];
+    __syncwarp();
+    const int kind = x.kind;
+    if (lane == 0) sts8(sb + S_KMAP + id, kind);
+    if (kind == 4 || kind == 5) {
+        const int k = lane & 15, d = x.d;
+        const uint32_t s = x.ssym[k], f = k < d ? x.sfreq[k] : 0u;
+        uint32_t inc = f;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o, 16);
+            if (k >= o) inc += u;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 15, 16);
+        if (lane < d) x.sent[k] = s | (f << 8) | ((inc - f + s - k) << 20);
+        if (lane == 0 && kind == 4) x.cntsum = (int)(256 - d + total);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int dec_color_small(Ent& e, uint8_t* xs, int id) {  // SmallContext decode, ans_contexts.h:238-283
+    const uint4 hd = *reinterpret_cast<const uint4*>(xs);
+    const int k = e.lane & 15;
+    const uint32_t ent = *reinterpret_cast<const uint32_t*>(xs + CS_SENT + 4 * k);
+    const uint32_t v0 = e.x & (PROB_SCALE - 1);
+    const int maxpos = (hd.x >> 16) & 255, d = hd.y & 0xFFFF, totFr = (int)hd.z;
+    const int shift = max(0, __clz(totFr - 1) - 20);  // smallest shift with totFr << shift > 2048
+    const int bonus = (PROB_SCALE - (totFr << shift)) >> shift;
+    const int v = (int)(v0 >> shift);
+    const int sk = ent & 255, fk = (ent >> 8) & 0xFFF, bk = ent >> 20;
+    const int st = bk + (k > maxpos ? bonus : 0);
+    const int fr = fk + (k == maxpos ? bonus : 0);
+    const bool ge = e.lane < d && v >= st;
+    const bool hit = ge && v < st + fr;
+    const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit);
+    int c;
+    if (bh) {
+        const int pos = __ffs(bh) - 1;
+        // every lane advanced its own candidate; take the winner's
+        const uint32_t xk = (uint32_t)(fr << shift) * (e.x >> PROB_BITS) + (v0 - (uint32_t)(st << shift));
+        const uint32_t xn = __shfl_sync(0xFFFFFFFFu, xk, pos);
+        c = __shfl_sync(0xFFFFFFFFu, sk, pos);
+        const int fmax = __shfl_sync(0xFFFFFFFFu, fk, maxpos);
+        const int nf = __shfl_sync(0xFFFFFFFFu, fk, pos) + 50;
+        // renormalise (as rdec_advance)
+        const uint32_t t = rd_peek(e);
+        const bool p1 = xn < RANS_L, p2 = xn < (1u << 15);
+        e.x = p2 ? ((xn << 16) | __byte_perm(t, 0, 0x4401)) : (p1 ? ((xn << 8) | (t & 0xFFu)) : xn);
+        rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
+        // count the symbol (ans_contexts.h:205-214): freq += 50, totFr += 50, maxpos moves on strict >
+        const int ntot = totFr + 50;
+        uint32_t ne = ent + (k == pos ? (50u << 8) : 0u) + (k > pos ? (50u << 20) : 0u);
+        if (ntot + 50 > PROB_SCALE) {  // rescale: f -= f >> 1 (:186-193); the prefix sums follow
+            const uint32_t f2 = e.lane < d ? ((ne >> 8) & 0xFFFu) : 0u;
+            const uint32_t h = f2 - (f2 >> 1);
+            uint32_t inc = h;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o, 16);
+                if (k >= o) inc += u;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 15, 16);
+            ne = (uint32_t)sk | (h << 8) | ((inc - h + sk - k) << 20);
+            if (e.lane < d) {
+                *reinterpret_cast<uint32_t*>(xs + CS_SENT + 4 * k) = ne;
+                *reinterpret_cast<uint16_t*>(xs + 32 + 2 * k) = (uint16_t)h;
+            }
+            if (e.lane == 0) *reinterpret_cast<int*>(xs + 8) = (int)(256 - d + total);
+            PROF_CNT(n_resc)
+        } else {
+            if (e.lane < d && k >= pos) *reinterpret_cast<uint32_t*>(xs + CS_SENT + 4 * k) = ne;
+            if (e.lane == pos) *reinterpret_cast<uint16_t*>(xs + 32 + 2 * k) = (uint16_t)nf;
+            if (e.lane == 0) *reinterpret_cast<int*>(xs + 8) = ntot;
+        }
+        if (e.lane == 0 && pos != maxpos && nf > fmax) xs[2] = (uint8_t)pos;
+    } else {  // a symbol not met yet: width 1 in the gap after the last entry below it
+        const uint32_t bg = __ballot_sync(0xFFFFFFFFu, ge);
+        int lastSymb = 0, cumFr = 0;
+        if (bg) {
+            const int K = 31 - __clz(bg);
+            lastSymb = __shfl_sync(0xFFFFFFFFu, sk, K) + 1;
+            cumFr = __shfl_sync(0xFFFFFFFFu, st + fr, K);
+        }
+        c = lastSymb + v - cumFr;
+        rdec_advance(e, v0 - (uint32_t)(v << shift), (uint32_t)(1 << shift));
+        if (e.lane == 0) cc_encode_counted(e.m->color[id], c & 255);  // insert / promote: the general path
+        color_refresh(e.m, e.sb, e.lane, id);
+        PROF_CNT(n_gen)
+    }
+    return c;
+}
+
+// kinds 6/7: flat tables cnt/freq/cum[256]; lane owns symbols [8*lane, 8*lane + 8)
+__device__ __forceinline__ uint32_t half_at(const uint4& r, int idx) {  // halfword idx (0..7) of a 128-bit row
+    const int w = idx >> 1;
+    const uint32_t word = w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+    return (idx & 1) ? (word >> 16) : (word & 0xFFFFu);
+}
+__device__ __noinline__ void flat_rescale(uint8_t* xs, int kind, int lane) {  // c6 rescale (:742-796) / Cx7 rescale (:959-981)
+    __syncwarp();
+    const uint4 cn = *reinterpret_cast<const uint4*>(xs + CS_CNT + lane * 16);
+    const int fshift = xs[1], d = *reinterpret_cast<const uint16_t*>(xs + 4);
+    const uint32_t c0 = kind == 6 ? (1u << (fshift > 0 ? fshift - 1 : 0)) : 0u;
+    uint32_t fr[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t w = j < 2 ? cn.x : j < 4 ? cn.y : j < 6 ? cn.z : cn.w;
+        const uint32_t c = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        fr[j] = (kind == 6 && c == 0) ? c0 : c;
+        sum += fr[j];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    uint32_t cf = inc - sum, ns = 0;
+    uint32_t cu[8], nc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cu[j] = cf & 0xFFFFu;
+        cf += fr[j];
+        const uint32_t w = j < 2 ? cn.x : j < 4 ? cn.y : j < 6 ? cn.z : cn.w;
+        const uint32_t c = (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+        nc[j] = c - (c >> 1);  // kind 6: symbols not met keep 0
+        ns += nc[j];
+    }
+    *reinterpret_cast<uint4*>(xs + CS_FREQ + lane * 16) =
+        make_uint4(fr[0] | (fr[1] << 16), fr[2] | (fr[3] << 16), fr[4] | (fr[5] << 16), fr[6] | (fr[7] << 16));
+    *reinterpret_cast<uint4*>(xs + CS_CUM + lane * 16) =
+        make_uint4(cu[0] | (cu[1] << 16), cu[2] | (cu[3] << 16), cu[4] | (cu[5] << 16), cu[6] | (cu[7] << 16));
+    *reinterpret_cast<uint4*>(xs + CS_CNT + lane * 16) =
+        make_uint4(nc[0] | (nc[1] << 16), nc[2] | (nc[3] << 16), nc[4] | (nc[5] << 16), nc[6] | (nc[7] << 16));
+    ns = __reduce_add_sync(0xFFFFFFFFu, ns);
+    if (lane == 0) {
+        if (kind == 6) {
+            const int nfs = fshift > 0 ? fshift - 1 : 0;
+            const int shft = nfs > 0 ? nfs - 1 : 0;
+            xs[1] = (uint8_t)nfs;
+            *reinterpret_cast<int*>(xs + 8) = (int)((((256 - d) << shft) + ns) & 0xFFFFu);
+        } else {
+            *reinterpret_cast<int*>(xs + 8) = (int)ns;
+        }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int kind) {
+    const uint4 hd = *reinterpret_cast<const uint4*>(xs);
+    const uint4 cr = *reinterpret_cast<const uint4*>(xs + CS_CUM + e.lane * 16);
+    const uint4 fq = *reinterpret_cast<const uint4*>(xs + CS_FREQ + e.lane * 16);
+    const uint32_t v = e.x & (PROB_SCALE - 1);
+    // number of this lane's cumulative frequencies <= v, two halfwords at a time (values < 2^15: no borrow between halves)
+    const uint32_t vv = (v * 0x10001u) | 0x80008000u;
+    const uint32_t m = (((vv - cr.x) & 0x80008000u) >> 15) | (((vv - cr.y) & 0x80008000u) >> 14) | (((vv - cr.z) & 0x80008000u) >> 13) |
+                       (((vv - cr.w) & 0x80008000u) >> 12);
+    const int idx = __popc(m) - 1;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m & 1u);
+    const int L = 31 - __clz(bal | 1u);
+    const uint32_t cum = half_at(cr, idx & 7), freq = half_at(fq, idx & 7);
+    const uint32_t xk = freq * (e.x >> PROB_BITS) + (v - cum);
+    const uint32_t xn = __shfl_sync(0xFFFFFFFFu, xk, L);
+    const int c = L * 8 + __shfl_sync(0xFFFFFFFFu, idx, L);
+    const uint32_t t = rd_peek(e);
+    const bool p1 = xn < RANS_L, p2 = xn < (1u << 15);
+    e.x = p2 ? ((xn << 16) | __byte_perm(t, 0, 0x4401)) : (p1 ? ((xn << 8) | (t & 0xFFu)) : xn);
+    rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
+    // count the symbol
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(xs + CS_CNT);
+    const int cn = cnt[c], cs = (int)hd.z;
+    const int step = kind == 7 ? 16 : (25 << ((hd.x >> 8) & 255));
+    if (cn != 0 || kind == 7) {  // met before: count (+ rescale), ans_contexts.h:686-691, 959-981
+        if (e.lane == 0) {
+            cnt[c] = (uint16_t)(cn + step);
+            *reinterpret_cast<int*>(xs + 8) = (cs + step) & 0xFFFF;
+        }
+        if (cs + 2 * step > PROB_SCALE) {
+            flat_rescale(xs, kind, e.lane);
+            PROF_CNT(n_resc)
+        }
+    } else {  // first occurrence in a Cx6: placeSymbol or the promotion to Cx7
+        if (e.lane == 0) cc_encode_counted(e.m->color[id], c);
+        color_refresh(e.m, e.sb, e.lane, id);
+        PROF_CNT(n_gen)
+    }
+    return c;
+}
 __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
     PROF_T0
-    ColorState& x = e.m->color[id];
-    const int kind = x.kind;
+    uint8_t* xs = reinterpret_cast<uint8_t*>(&e.m->color[id]);
+    const int kind = (int)lds8(e.sb + S_KMAP + id);
     int c;
-    if (kind >= 6) {  // flat table: two ballot levels over cum[256]
-        const uint32_t v = e.x & (PROB_SCALE - 1);
-        const bool le = x.cum[e.lane * 8] <= v;
-        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
-        const bool le2 = e.lane < 8 && x.cum[L * 8 + (e.lane & 7)] <= v;
-        c = L * 8 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
-        const uint32_t freq = x.freq[c], cum = x.cum[c];
-        const int cn = x.cnt[c], cs = x.cntsum;
-        const int step = kind == 7 ? 16 : (25 << x.fshift);
-        if (cn != 0 && cs + 2 * step <= PROB_SCALE) {  // symbol already met, no rescale: count it (all lanes, same values)
-            x.cnt[c] = (uint16_t)(cn + step);
-            x.cntsum = cs + step;
-        } else {
-            if (e.lane == 0) cc_encode_counted(x, c);  // new symbol, promotion or rescale
-            __syncwarp();
-        }
-        rdec_advance(e, cum, freq);
-    } else if (kind >= 4) {  // SmallContext: walk the (<= 16) sorted symbols, ans_contexts.h:238-283
-        const uint32_t v0 = e.x & (PROB_SCALE - 1);
-        // header + symbols + frequencies: four independent 128-bit loads, then registers only
-        const uint4 hd = *reinterpret_cast<const uint4*>(&x.kind);
-        const uint4 sy4 = *reinterpret_cast<const uint4*>(x.ssym);
-        const uint4 f0 = *reinterpret_cast<const uint4*>(x.sfreq);
-        const uint4 f1 = *reinterpret_cast<const uint4*>(x.sfreq + 8);
-        const int maxpos = (hd.x >> 16) & 255, d = hd.y & 0xFFFF;
-        const uint32_t syw[4] = {sy4.x, sy4.y, sy4.z, sy4.w};
-        const uint32_t frw[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-        int totFr = (int)hd.z;
-        if (kind == 4) totFr = 256 - d + (int)((f0.x & 0xFFFF) + (f0.x >> 16) + (f0.y & 0xFFFF) + (f0.y >> 16));  // :303
-        int shift = 0, tot = totFr;
-        while (tot <= PROB_SCALE / 2) {
-            tot <<= 1;
-            shift++;
-        }
-        const int v = (int)(v0 >> shift);
-        const int bonus = (PROB_SCALE - tot) >> shift;
-        int cumFr = 0, lastSymb = 0, pos = 0, fr = 1, fpos = 0;
-        bool found = false;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k >= d) break;  // uniform: leaves the unrolled chain as soon as the symbol is placed
-            const int fk = (int)((frw[k >> 1] >> (16 * (k & 1))) & 0xFFFF);
-            const int sk = (int)((syw[k >> 2] >> (8 * (k & 3))) & 255);
-            const int startFr = cumFr + sk - lastSymb;
-            if (v < startFr) break;
-            const int frk = (fk + (k == maxpos ? bonus : 0)) & 0xFFFF;
-            if (startFr + frk > v) {
-                c = sk;
-                cumFr = startFr;
-                fr = frk;
-                fpos = fk;
-                found = true;
-                break;
-            }
-            cumFr = startFr + frk;
-            lastSymb = sk + 1;
-            pos = k + 1;
-        }
-        if (!found) {  // a symbol not met yet: width 1
-            c = lastSymb + v - cumFr;
-            cumFr = v;
-            fr = 1;
-        }
-        if (found && totFr + 100 <= PROB_SCALE) {  // hot path: count, no rescale (ans_contexts.h:211-214); all lanes, same values
-            const int nf = fpos + 50;
-            x.sfreq[pos] = (uint16_t)nf;
-            if (kind == 5) x.cntsum = totFr + 50;
-            if (pos != maxpos && nf > x.sfreq[maxpos]) x.maxpos = (uint8_t)pos;  // sfreq[maxpos] is not the entry just written
-        } else {
-            if (e.lane == 0) cc_encode_counted(x, c);  // new symbol, promotion or rescale: the general path
-            __syncwarp();
-        }
-        rdec_advance(e, (uint32_t)(cumFr << shift) & 0xFFFFu, (uint32_t)(fr << shift) & 0xFFFFu);
-    } else {
-        c = *e.p++;
-        if (e.lane == 0) cc_update_raw(x, c, e.f0);
-        __syncwarp();  // lane 0's model stores are visible to the whole warp before the next symbol
+    if (kind >= 6) {
+        c = dec_color_flat(e, xs, id, kind);
+        PROF_ADD(c_flat) PROF_CNT(n_flat)
+    } else if (kind >= 4) {
+        c = dec_color_small(e, xs, id);
+        PROF_ADD(c_small) PROF_CNT(n_small)
+    } else {  // no statistics yet: the byte is stored raw (screencap.h:324-325)
+        c = (int)(rd_peek(e) & 0xFFu);
+        rd_skip(e, 8);
+        if (e.lane == 0) cc_update_raw(e.m->color[id], c, e.f0);
+        color_refresh(e.m, e.sb, e.lane, id);
+        PROF_ADD(c_raw) PROF_CNT(n_raw)
     }
     rdec_count(e);
     PROF_ADD(c_color) PROF_CNT(n_color)
     return c;
 }
-__device__ inline int dec_bool(Ent& e) {  // decodeBool
-    const int flag = (e.x & (PROB_SCALE - 1)) >= PROB_SCALE / 2;
-    rdec_advance(e, flag ? PROB_SCALE / 2 : 0, PROB_SCALE / 2);
-    rdec_count(e);
-    return flag;
-}
 __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
     uint32_t px = 0;
 #pragma unroll 1
     for (int ch = 0; ch < 3; ch++) {  // one copy of the colour decoder in the instruction stream
-        const uint32_t v = (uint32_t)dec_color(e, ch * 4096 + (int)(e.cx + e.cx1));
+        const uint32_t v = (uint32_t)dec_color(e, ch * 4096 + (int)(e.cx + e.cx1)) & 255u;
         e.cx1 = (e.cx << 6) & 0xFC0;
         e.cx = v >> 2;
         px |= v << (8 * ch);
@@ -444,6 +715,7 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     IPos p{0, 0};
     int ptype = 0;
     int hdr = X + 1;
+    uint32_t lastv = 0;  // the pixel before p in raster order
     // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
     while (hdr > 0) {
         const uint32_t c = dec_rgb(e);
@@ -455,58 +727,64 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
         }
         p = ipos_add(p, n, X);
         hdr -= n;
-        __syncwarp();
+        lastv = c;
     }
+    __syncwarp();
     while (p.y < Y) {
-        uint32_t c = 0;
+        uint32_t c = lastv;  // type 1: the previous pixel in raster order, whatever the row
         ptype = dec_ptype(e, ptype);
         if (!ptype) c = dec_rgb(e);
         const int n = dec_n(e, ptype);
         if (n <= 0) return;
         PROF_T0
         if (ptype == 0 || ptype == 1) {
-            if (ptype == 1) {
-                const IPos l = ipos_prev(p, X);
-                c = load_px(frame, g, l.x, l.y);
-            }
             for (int i = lane; i < n; i += 32) {
                 const IPos q = ipos_add(p, i, X);
                 if (q.y < Y) store_px(frame, g, q.x, q.y, c);
             }
-        } else if (n < X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
-            for (int i = lane; i < n; i += 32) {
-                const IPos q = ipos_add(p, i, X);
-                if (q.y < Y) store_px(frame, g, q.x, q.y, ptype == 2 ? load_px(frame, g, q.x, q.y - 1) : tl_at(frame, g, q, padded));
-            }
-        } else {  // gradient chains through the left pixel; tiny frames may read their own run
-            if (lane == 0) {
-                IPos q = p;
-                for (int i = 0; i < n && q.y < Y; i++) {
-                    uint32_t v;
-                    if (ptype == 2) v = load_px(frame, g, q.x, q.y - 1);
-                    else if (ptype == 5) v = tl_at(frame, g, q, padded);
-                    else {
-                        const IPos l = ipos_prev(q, X);
-                        v = grad_px(load_px(frame, g, l.x, l.y), load_px(frame, g, q.x, q.y - 1), tl_at(frame, g, q, padded));
+            p = ipos_add(p, n, X);
+            lastv = c;
+        } else {
+            if (n < X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
+                for (int i = lane; i < n; i += 32) {
+                    const IPos q = ipos_add(p, i, X);
+                    if (q.y < Y) store_px(frame, g, q.x, q.y, ptype == 2 ? load_px(frame, g, q.x, q.y - 1) : tl_at(frame, g, q, padded));
+                }
+            } else {  // gradient chains through the left pixel; tiny frames may read their own run
+                if (lane == 0) {
+                    IPos q = p;
+                    for (int i = 0; i < n && q.y < Y; i++) {
+                        uint32_t v;
+                        if (ptype == 2) v = load_px(frame, g, q.x, q.y - 1);
+                        else if (ptype == 5) v = tl_at(frame, g, q, padded);
+                        else {
+                            const IPos l = ipos_prev(q, X);
+                            v = grad_px(load_px(frame, g, l.x, l.y), load_px(frame, g, q.x, q.y - 1), tl_at(frame, g, q, padded));
+                        }
+                        store_px(frame, g, q.x, q.y, v);
+                        q = ipos_add(q, 1, X);
                     }
-                    store_px(frame, g, q.x, q.y, v);
-                    q = ipos_add(q, 1, X);
                 }
             }
+            __syncwarp();
+            p = ipos_add(p, n, X);
+            const IPos l = ipos_prev(p, X);
+            lastv = l.y < Y ? load_px(frame, g, l.x, l.y) : 0u;
         }
-        __syncwarp();
-        p = ipos_add(p, n, X);
-        const IPos l = ipos_prev(p, X);
-        set_cx_from(e, load_px(frame, g, l.x, l.y));
+        set_cx_from(e, lastv);
         PROF_ADD(c_ifill)
     }
 }
 
 // ---- P frame (DecompressP, screencap.cpp:1275-1432) ------------------------------------------------
-__device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame, int f, uint8_t* s_bts, uint32_t (*tile)[17],
-                         int lane) {
+__device__ __forceinline__ uint32_t tile_at(uint32_t tb, int ty, int tx) { return lds32(tb + (uint32_t)(ty * 17 + tx) * 4u); }
+
+__device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame, int f, int lane) {
     const Geo& g = w.g;
+    const uint32_t tb = e.sb + S_TILE, btsb = e.sb + S_BTS;
+#ifdef SCPR_PROF
     const long long thdr__ = clock64();
+#endif
     int t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
     const int xx1 = (dec_fxc<256, CX_XX - CX_NTAB>(e) << 8) + t0;
     t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
@@ -517,7 +795,7 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         const int c = dec_fxc<5, CX_BT - CX_NTAB>(e);
         const int n = dec_fxc<256, CX_NTAB2 - CX_NTAB>(e);
         if (n <= 0) break;
-        for (int i = lane; i < n && x + i < g.nb; i += 32) s_bts[x + i] = (uint8_t)c;
+        for (int i = lane; i < n && x + i < g.nb; i += 32) sts8(btsb + x + i, c);
         x += n;
     }
     __syncwarp();
@@ -530,11 +808,11 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
     // visit changed blocks only: 32 block types per step, ballot, iterate the set bits
     for (int b0 = xx1 & ~31; b0 <= xx2; b0 += 32) {
       const int myb = b0 + lane;
-      uint32_t chm = __ballot_sync(0xFFFFFFFFu, myb >= xx1 && myb <= xx2 && s_bts[myb] != 0);
+      uint32_t chm = __ballot_sync(0xFFFFFFFFu, myb >= xx1 && myb <= xx2 && lds8(btsb + myb) != 0);
       while (chm) {
         const int bi = b0 + __ffs(chm) - 1;
         chm &= chm - 1;
-        const int bt = s_bts[bi];
+        const int bt = (int)lds8(btsb + bi);
         const int by = bi / g.nbx, bx = bi - by * g.nbx;
         const int bx0 = bx * 16, by0 = by * 16;
         const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
@@ -604,35 +882,27 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             continue;
         }
         // ---- pixel-coded block, decoded in a shared-memory tile ----
-        // tile[1+yy][1+xx] = block pixel; row 0 / column 0 = the neighbours above / left (current frame)
+        // tile[1+yy][1+xx] = block pixel, initially the previous frame's block (so pixels of type 3, and the part
+        // of a partial block outside the sub-rect, are already in place); row 0 / column 0 = the neighbours
+        // above / left in the current frame.  The loads are issued first, the sub-rect symbols are decoded while
+        // they are in flight.
+        uint32_t tv[10];
         { PROF_T0
-        {   // the tile touches four blocks: resolve where each one's pixels live once, then load
             const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
             const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? cc.src_cur[bA] : -1);
             const PixSrc sT = resolve_src(w, by > 0 ? cc.src_cur[bT] : -1);
             const PixSrc sL = resolve_src(w, bx > 0 ? cc.src_cur[bL] : -1);
             const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
-            const bool partial = (bt - 1) & 1;
-            if (partial) {  // block starts as a copy of the previous frame's block
-                for (int p = lane; p < 17 * 17; p += 32) {
-                    const int ty = p / 17, tx = p - ty * 17;
-                    const int x = bx0 + tx - 1, y = by0 + ty - 1;
-                    uint32_t v = 0;
-                    if (x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : tx == 0 ? sL : sP, g, x, y);
-                    tile[ty][tx] = v;
-                }
-            } else {  // every pixel of the block is coded: only the 33 neighbours are needed
-                for (int p = lane; p < 33; p += 32) {
-                    const int ty = p < 17 ? 0 : p - 16, tx = p < 17 ? p : 0;
-                    const int x = bx0 + tx - 1, y = by0 + ty - 1;
-                    uint32_t v = 0;
-                    if (x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : sL, g, x, y);
-                    tile[ty][tx] = v;
-                }
+#pragma unroll
+            for (int u = 0; u < 10; u++) {
+                const int p = lane + 32 * u;
+                const int ty = p / 17, tx = p - ty * 17;
+                const int x = bx0 + tx - 1, y = by0 + ty - 1;
+                uint32_t v = 0;
+                if (p < 17 * 17 && x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : tx == 0 ? sL : sP, g, x, y);
+                tv[u] = v;
             }
-        }
-        __syncwarp();
-        PROF_ADD(c_tile) }
+          PROF_ADD(c_tile) }
         if ((bt - 1) & 1) {
             x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
             y1 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 1>(e);
@@ -643,9 +913,19 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             if (x1 >= x2) x1 = x2 - 1;
             if (y1 >= y2) y1 = y2 - 1;
         }
+        { PROF_T0
+#pragma unroll
+            for (int u = 0; u < 10; u++) {
+                const int p = lane + 32 * u;
+                if (p < 17 * 17) sts32(tb + (uint32_t)p * 4u, tv[u]);
+            }
+            __syncwarp();
+          PROF_ADD(c_tile) }
         const int sw = x2 - x1, sh = y2 - y1;
-        const uint32_t swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;  // idx / sw == (idx * swinv) >> 16 for idx < 256
-        {  // pixel runs over the sub-rect in its own raster order
+        const uint32_t swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;   // idx / sw == (idx * swinv) >> 16 for idx < 256
+        const uint32_t sw1inv = (65536u + (uint32_t)sw) / (uint32_t)(sw + 1);  // same for sw + 1
+        {  // pixel runs over the sub-rect in its own raster order.  The sources of every predicted pixel lie
+           // outside the run (closed forms below), so the lanes fill a run independently of each other.
             PROF_T0
             int pos = 0, ptype = 0;
             const int npx = sw * sh;
@@ -657,40 +937,39 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                 int n = dec_n(e, ptype);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
-                uint32_t v = c;
-                if (ptype == 0 || ptype == 3) {  // no dependence on pixels of this run: lanes fill in parallel
-                    for (int i = lane; i < n; i += 32) {
-                        const int yy = (int)(((uint32_t)(pos + i) * swinv) >> 16), xx = pos + i - yy * sw;
-                        uint32_t* t = &tile[oy + yy][ox + xx];
-                        if (ptype == 3) t[0] = (bt - 1) & 1 ? t[0] : prev_px(cc, x1 + xx, y1 + yy);
-                        else t[0] = c;
-                    }
-                    __syncwarp();
-                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
-                    v = tile[oy + ly][ox + li - ly * sw];
-                } else {
-                    // predicted from pixels of this block: one row segment of the sub-rect per step (<= 16
-                    // pixels, sources lie in the row above or left of the segment); gradient chains serially
-                    int yy = (int)(((uint32_t)pos * swinv) >> 16), xx = pos - yy * sw;
-                    for (int rem = n; rem > 0;) {
-                        const int seg = min(rem, sw - xx);
-                        uint32_t* row = &tile[oy + yy][ox + xx];
-                        if (ptype == 4) {
-                            if (lane == 0)
-                                for (int i = 0; i < seg; i++) row[i] = grad_px(row[i - 1], row[i - 17], row[i - 18]);
-                        } else if (lane < seg) {
-                            row[lane] = ptype == 1 ? row[-1] : ptype == 2 ? row[lane - 17] : row[lane - 18];
+                const int yy0 = (int)(((uint32_t)pos * swinv) >> 16), xx0 = pos - yy0 * sw;
+                if (ptype == 4) {  // gradient chains through the left pixel: serial
+                    if (lane == 0) {
+                        int xx = xx0, yy = yy0;
+                        for (int i = 0; i < n; i++) {
+                            const uint32_t a = tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u;
+                            sts32(a, grad_px(lds32(a - 4), lds32(a - 68), lds32(a - 72)));
+                            if (++xx == sw) {
+                                xx = 0;
+                                yy++;
+                            }
                         }
-                        __syncwarp();
-                        rem -= seg;
-                        xx = 0;
-                        yy++;
                     }
-                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
-                    v = tile[oy + ly][ox + li - ly * sw];
+                } else if (ptype != 3) {
+                    for (int i = lane; i < n; i += 32) {
+                        const int idx = pos + i;
+                        const int yy = (int)(((uint32_t)idx * swinv) >> 16), xx = idx - yy * sw;
+                        uint32_t v = c;
+                        if (ptype == 1) {  // left: the pixel before the row segment the pixel lies in
+                            v = yy == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + yy, ox - 1);
+                        } else if (ptype == 2) {  // top: the pixel above the run's first row in this column
+                            v = tile_at(tb, oy + (xx >= xx0 ? yy0 : yy0 + 1) - 1, ox + xx);
+                        } else if (ptype == 5) {  // top-left: walk the diagonal until it leaves the run or the sub-rect
+                            const int k = min((int)(((uint32_t)i * sw1inv) >> 16) + 1, xx + 1);
+                            v = tile_at(tb, oy + yy - k, ox + xx - k);
+                        }
+                        sts32(tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u, v);
+                    }
                 }
-                set_cx_from(e, v);
+                __syncwarp();
                 pos += n;
+                const int li = pos - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                set_cx_from(e, tile_at(tb, oy + ly, ox + li - ly * sw));
             }
             PROF_ADD(c_runs)
         }
@@ -698,11 +977,11 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         // write the whole block and hand its ownership to this frame
         { PROF_T0
         if (bw == 16) {
-            for (int p = lane; p < 16 * bh; p += 32) store_px(frame, g, bx0 + (p & 15), by0 + (p >> 4), tile[1 + (p >> 4)][1 + (p & 15)]);
+            for (int p = lane; p < 16 * bh; p += 32) store_px(frame, g, bx0 + (p & 15), by0 + (p >> 4), tile_at(tb, 1 + (p >> 4), 1 + (p & 15)));
         } else {
             for (int p = lane; p < bw * bh; p += 32) {
                 const int xx = p % bw, yy = p / bw;
-                store_px(frame, g, bx0 + xx, by0 + yy, tile[1 + yy][1 + xx]);
+                store_px(frame, g, bx0 + xx, by0 + yy, tile_at(tb, 1 + yy, 1 + xx));
             }
         }
         if (lane == 0) {
@@ -722,9 +1001,8 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
 // one warp per chain
 __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     extern __shared__ __align__(16) uint8_t s_mem[];
-    FixedSmem* fs = reinterpret_cast<FixedSmem*>(s_mem);
-    uint32_t(*tile)[17] = reinterpret_cast<uint32_t(*)[17]>(s_mem + sizeof(FixedSmem));
-    uint8_t* s_bts = s_mem + sizeof(FixedSmem) + 17 * 17 * 4;
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_mem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb));  // keep the base in a register: otherwise it is rematerialised (S2R) at every use
     const int lane = threadIdx.x;
     const DecChain ch = w.chains[blockIdx.x];
     const Geo& g = w.g;
@@ -743,25 +1021,27 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     e.m = reinterpret_cast<ModelState*>(w.states + (size_t)ch.state * sizeof(ModelState));
     e.f0 = w.f0;
     e.cx = e.cx1 = 0;
-    e.ndec = 0;
+    e.nleft = RANS_BLOCK;
     e.x = 0;
-    e.p = nullptr;
-    e.fs = fs;
+    e.w0 = e.w1 = e.w2 = e.k8 = 0;
+    e.wp = nullptr;
+    e.sb = sb;
     e.lane = lane;
 #ifdef SCPR_PROF
     const long long tk0 = clock64();
 #endif
-    // fixed tables of the chain's model state -> shared memory (a renewing first frame overwrites them)
+    // fixed tables and context kinds of the chain's model state -> shared memory (a renewing first frame overwrites them)
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         const FixedState& g0 = e.m->fx[t];
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
         for (int i = lane; i < nsym; i += 32) {
-            fs->cnt[off + i] = g0.cnt[i];
-            fs->fc[off + i] = ((uint32_t)g0.freq[i] << 16) | g0.cum[i];
+            sts16(sb + S_CNT + (off + i) * 2, g0.cnt[i]);
+            sts32(sb + S_FC + (off + i) * 4, ((uint32_t)g0.freq[i] << 16) | g0.cum[i]);
         }
     }
+    for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, reinterpret_cast<const uint32_t*>(e.m->kmap)[i]);
     __syncwarp();
-    for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(*fs, t, lane, false);
+    for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
     for (int f = ch.first; f < ch.first + ch.count; f++) {
         const DecFrame df = w.frames[f];
         uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
@@ -770,16 +1050,17 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
         if (df.kind == DK_FLAT || df.kind == DK_I) {
             if (df.kind == DK_I || df.renew) {  // RenewI
                 for (int i = lane; i < NUM_COLOR_CX; i += 32) e.m->color[i].kind = 0;
+                for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, 0);
                 for (int t = 0; t < NUM_FIXED_CX; t++) {  // FixedSizeRansCtx::renew, ans_contexts.h:1114-1131
                     const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
                     const int fr = PROB_SCALE / nsym, c0 = fr - (fr >> 1);
                     for (int i = lane; i < nsym; i += 32) {
-                        fs->cnt[off + i] = (uint16_t)c0;
-                        fs->fc[off + i] = ((uint32_t)fr << 16) | (uint32_t)(fr * i);
+                        sts16(sb + S_CNT + (off + i) * 2, c0);
+                        sts32(sb + S_FC + (off + i) * 4, ((uint32_t)fr << 16) | (uint32_t)(fr * i));
                     }
                 }
                 __syncwarp();
-                for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(*fs, t, lane, false);
+                for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
             }
             for (int i = lane; i < g.nb; i += 32) {  // the whole frame is new
                 cc.src_prev[i] = cc.src_cur[i];
@@ -788,39 +1069,40 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
             }
             __syncwarp();
             if (df.kind == DK_I) {
-                e.p = w.stream + df.src_off + 1;
-                e.ndec = 0;
+                rd_seek(e, w.stream + df.src_off + 1);
+                e.nleft = RANS_BLOCK;
                 e.cx = e.cx1 = 0;
                 rdec_init(e);
                 decode_i(w, e, frame, lane);
             }
             continue;
         }
-        e.p = w.stream + df.src_off + 1;
-        e.ndec = 0;
+        rd_seek(e, w.stream + df.src_off + 1);
+        e.nleft = RANS_BLOCK;
         rdec_init(e);
-        decode_p(w, cc, e, frame, f, s_bts, tile, lane);
+        decode_p(w, cc, e, frame, f, lane);
         __threadfence_block();
     }
 #ifdef SCPR_PROF
     if (lane == 0)
-        printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc) | "
-               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f\n",
+        printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc; %lld serial, %lld rescales) | "
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld\n",
                (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
-               e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.c_hdr * 1e-6, e.c_tile * 1e-6, e.n_blocks,
-               e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6);
+               e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
+               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw);
 #endif
-    // leave the fixed tables behind for the next call
+    // leave the fixed tables and the kinds behind for the next call
     __syncwarp();
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         FixedState& g0 = e.m->fx[t];
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
         uint32_t sum = 0;
         for (int i = lane; i < nsym; i += 32) {
-            g0.cnt[i] = fs->cnt[off + i];
-            g0.freq[i] = (uint16_t)(fs->fc[off + i] >> 16);
-            g0.cum[i] = (uint16_t)(fs->fc[off + i] & 0xFFFFu);
-            sum += fs->cnt[off + i];
+            const uint32_t cn = lds16(sb + S_CNT + (off + i) * 2), fc = lds32(sb + S_FC + (off + i) * 4);
+            g0.cnt[i] = (uint16_t)cn;
+            g0.freq[i] = (uint16_t)(fc >> 16);
+            g0.cum[i] = (uint16_t)(fc & 0xFFFFu);
+            sum += cn;
         }
         sum = __reduce_add_sync(0xFFFFFFFFu, sum);
         if (lane == 0) {
@@ -828,6 +1110,7 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
             g0.nsym = nsym;
         }
     }
+    for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) reinterpret_cast<uint32_t*>(e.m->kmap)[i] = lds32(sb + S_KMAP + 4 * i);
 }
 
 // source frame of every block of every frame: thread per block, frames in order
@@ -1017,7 +1300,11 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.fill_src = (int16_t*)(ws + 3 * map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
     w.n = n;
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
-    const size_t smem = sizeof(FixedSmem) + 17 * 17 * 4 + (size_t)g.nb + 16;
+    const size_t smem = (size_t)S_BTS + (size_t)g.nb + 16;
+    if (smem > 227 * 1024) {
+        set_error("frame has too many blocks for the decoder's shared-memory block map");
+        return SCPR_E_PARAM;
+    }
     CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(st);
     k_dec_chain<<<n_chains, 32, smem, st>>>(w);

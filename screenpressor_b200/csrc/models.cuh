@@ -17,27 +17,31 @@ struct FixedState {  // FixedSizeRansCtx<N>, ans_contexts.h:1053-1132
     uint16_t cnt[512], freq[512], cum[512];
 };
 
-struct alignas(16) ColorState {
-    uint16_t cnt[256], freq[256], cum[256];  // kinds 6/7 (16-byte aligned for 128-bit table scans)
-    // ---- 16-byte header, then the SmallContext arrays: the decoder fetches these 64 bytes with four
-    // 128-bit loads and walks the (<= 16) symbols in registers
+// 128-byte head = everything kinds 0..5 touch (one cache line), then the flat tables of kinds 6/7.
+struct alignas(128) ColorState {
     uint8_t kind;    // 0 empty, 1..3 "every symbol met once" sets, 4/5 SmallContext, 6 Cx6, 7 Cx7
     uint8_t fshift;  // kind 6
     uint8_t maxpos;  // kinds 4/5
     uint8_t pad;
     uint16_t d;      // distinct symbols met
     uint16_t pad2;
-    int cntsum;      // kind 5: cached totFr; kinds 6/7: counter sum
+    int cntsum;      // kind 5: cached totFr (the decoder also caches it for kind 4); kinds 6/7: counter sum
     uint32_t pad3;
     uint8_t ssym[16];     // kinds 4/5: sorted symbols ...
     uint16_t sfreq[16];   // ... and their frequencies
-    uint32_t seen[8];     // kinds 1..3: bitmap of symbols met
+    union {
+        uint32_t seen[8];   // kinds 1..3: bitmap of symbols met
+        uint32_t sent[16];  // kinds 4/5, decoder only: entry k packed as sym | freq << 8 | start << 20 with
+                            // start = sum of the frequencies before k + (ssym[k] - k), see decode.cu
+    };
+    uint16_t cnt[256], freq[256], cum[256];  // kinds 6/7 (16-byte aligned rows for 128-bit table scans)
 };
-static_assert(sizeof(ColorState) == 1632, "ColorState layout");
+static_assert(sizeof(ColorState) == 1664, "ColorState layout");
 
 struct ModelState {
-    FixedState fx[NUM_FIXED_CX];
     ColorState color[NUM_COLOR_CX];
+    FixedState fx[NUM_FIXED_CX];
+    uint8_t kmap[NUM_COLOR_CX];  // decoder: kind of every colour context (kept in shared memory while a chain runs)
 };
 
 // ---- kinds 1..3 ------------------------------------------------------------------------------
