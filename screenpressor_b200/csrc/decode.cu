@@ -136,29 +136,32 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 }
 
 // Fixed tables t = 0..20 (context id CX_NTAB + t): 0-5 ntab[ptype], 6 ntab2, 7 xx, 8 bt, 9-12 sxy, 13-14 mv,
-// 15-20 ptype[last].  Because a table's intervals are frozen between rescales (ans_contexts.h:1070-1091),
-// derived look-up structures are rebuilt together with the table (every ~128 symbols of that table, by
-// the whole warp):
-//   * ntab[0..5] (one symbol per pixel run, the hottest tables): lut32[4096] = sym<<24 | freq<<12 | cum,
-//     so a run length costs ONE shared load on the rANS dependency chain;
-//   * ptype[0..5] (6 symbols): the cumulative frequencies as 8 halfwords, fetched with one 128-bit load
-//     whose address does not depend on the rANS state; the symbol comes from five compares;
-//   * the other <= 256-symbol tables: slot -> symbol bytes lut8[4096], then fc[sym];
-//   * the two 512-symbol MV tables: two ballot levels over fc[].
-// "Events until the next rescale" is a countdown per table (the rescale instant depends only on the
-// number of events, each adds 16 to cntsum).
+// 15-20 ptype[last].  A single warp issues roughly one instruction every 4-6 cycles on this serial code, so
+// the per-symbol path is kept to a few dozen instructions and everything rare sits behind a uniform branch:
+//   * ntab[0..5] (one symbol per pixel run, the hottest tables): because a table's intervals are frozen
+//     between rescales (ans_contexts.h:1070-1091), a slot -> (sym<<24 | freq<<12 | cum) map lut32[4096] is
+//     rebuilt together with the table (every ~128 symbols of that table, by the whole warp), so a run length
+//     costs ONE shared load on the rANS dependency chain;
+//   * every other table is searched by the lanes: lane j holds interval j (freq<<16 | cum), tests the slot
+//     against it and forms its own candidate successor state; a ballot names the winner and one shuffle
+//     delivers its state (tables of 256 / 512 symbols take a first ballot over every 8th / 16th cum).
+// "Events until the next rescale" is a countdown per table (the rescale instant depends only on the number
+// of events, each adds 16 to cntsum).
 constexpr int FX_TOTAL = 3192;
-constexpr int LUT8_ROW = 32 * 132;  // 128 slots per lane + 4 bytes padding: conflict-free fills
+constexpr int NCACHE = 256;                              // SmallContext cache entries
 constexpr uint32_t S_FC = 0;                             // u32[FX_TOTAL]: freq << 16 | cum
 constexpr uint32_t S_CNT = S_FC + FX_TOTAL * 4;          // u16[FX_TOTAL]: adaptive counters
 constexpr uint32_t S_LEFT = S_CNT + FX_TOTAL * 2;        // i32[24]
-constexpr uint32_t S_PCUM = S_LEFT + 24 * 4;             // 6 x u16[8]
-constexpr uint32_t S_LUT8 = S_PCUM + 6 * 16;             // 7 x LUT8_ROW (tables 6..12)
-constexpr uint32_t S_LUT32 = S_LUT8 + 7 * LUT8_ROW;      // 6 x u32[4096] (tables 0..5), XOR-swizzled
+constexpr uint32_t S_HEADS = S_LEFT + 24 * 4;            // u32[128]: bit s = an interval starts at slot s (lut32 rebuild)
+constexpr uint32_t S_LASTH = S_HEADS + 128 * 4;          // u32[128]: last interval start before each 32-slot word
+constexpr uint32_t S_LUT32 = S_LASTH + 128 * 4;          // 6 x u32[4096] (tables 0..5)
 constexpr uint32_t S_KMAP = S_LUT32 + 6 * 16384;         // u8[12288]: kind of every colour context
 constexpr uint32_t S_TILE = S_KMAP + NUM_COLOR_CX;       // u32[17][17]
-constexpr uint32_t S_BTS = S_TILE + 1168;                // u8[nb]
-static_assert(S_PCUM % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0, "shared layout alignment");
+constexpr uint32_t S_CTAG = S_TILE + 1168;               // u32[NCACHE]: context id held by a cache entry (~0 = none)
+constexpr uint32_t S_CHDR = S_CTAG + NCACHE * 4;         // uint2[NCACHE]: totFr | maxpos<<16 | d<<20 | shift<<28, bonus | sfreq[maxpos]<<16
+constexpr uint32_t S_CENT = S_CHDR + NCACHE * 8;         // u32[NCACHE][16]: entry k = ssym | sfreq << 8 | start << 20
+constexpr uint32_t S_BTS = S_CENT + NCACHE * 64;         // u8[nb]
+static_assert(S_HEADS % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0 && S_CTAG % 16 == 0, "shared layout alignment");
 __host__ __device__ constexpr int fx_off(int t) {
     return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
 }
@@ -175,16 +178,17 @@ __host__ __device__ constexpr int fx_off(int t) {
 
 // The rANS state, the byte window and the colour-context registers are held identically by all 32
 // lanes (every lane executes the same arithmetic on the same values), so no broadcast is needed
-// between symbols.  The stream is read through a three-word window (aligned 32-bit loads issued two
-// words ahead), so no load sits on the renormalisation path.
+// between symbols.  The stream is read through a two-word window (aligned 32-bit loads, one word
+// ahead), so no load sits on the renormalisation path.
 struct Ent {
 #ifdef SCPR_PROF
     long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
-              c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0, c_raw = 0, n_raw = 0;
+              c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0,
+              c_raw = 0, n_raw = 0, n_miss = 0;
 #endif
     uint32_t x;
-    uint32_t w0, w1, w2, k8;  // window: stream bytes from bit k8 of w0 on
-    const uint32_t* wp;       // address of w0
+    uint32_t w0, w1, k8;      // window: stream bytes from bit k8 of w0 on
+    const uint32_t* wp;       // address of w1
     int nleft;                // symbols until the next RansDecInit
     uint32_t cx, cx1;
     uint32_t sb;              // shared-memory base address
@@ -194,11 +198,10 @@ struct Ent {
 };
 __device__ __forceinline__ void rd_seek(Ent& e, const uint8_t* p) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    e.wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    e.wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3) + 1;
     e.k8 = (uint32_t)(a & 3) * 8;
-    e.w0 = e.wp[0];
-    e.w1 = e.wp[1];
-    e.w2 = e.wp[2];
+    e.w0 = __ldg(e.wp - 1);
+    e.w1 = __ldg(e.wp);
 }
 __device__ __forceinline__ uint32_t rd_peek(const Ent& e) { return __funnelshift_r(e.w0, e.w1, e.k8); }
 __device__ __forceinline__ void rd_skip(Ent& e, uint32_t bits) {  // bits = 8 * bytes, <= 32
@@ -206,9 +209,7 @@ __device__ __forceinline__ void rd_skip(Ent& e, uint32_t bits) {  // bits = 8 * 
     if (e.k8 >= 32) {
         e.k8 -= 32;
         e.w0 = e.w1;
-        e.w1 = e.w2;
-        e.w2 = e.wp[3];
-        e.wp++;
+        e.w1 = __ldg(++e.wp);
     }
 }
 __device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
@@ -221,21 +222,25 @@ __device__ __forceinline__ void rdec_count(Ent& e) {  // re-init every 131072 sy
         e.nleft = RANS_BLOCK;
     }
 }
-// RansDecAdvance with the symbol's slot offset d = (x & 4095) - start already formed; a valid stream needs at
-// most two renormalisation bytes (x >= 2^11 after the update), taken branch-free from the window
-__device__ __forceinline__ void rdec_advance(Ent& e, uint32_t d, uint32_t freq) {
-    const uint32_t x = freq * (e.x >> PROB_BITS) + d;
-    const uint32_t t = rd_peek(e);
-    const bool p1 = x < RANS_L, p2 = x < (1u << 15);
-    const uint32_t x1 = (x << 8) | (t & 0xFFu), x2 = (x << 16) | __byte_perm(t, 0, 0x4401);
-    e.x = p2 ? x2 : (p1 ? x1 : x);
-    rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
+// renormalisation of RansDecAdvance: a valid stream needs at most two bytes (x >= 2^11 after the update)
+__device__ __forceinline__ void rdec_renorm(Ent& e, uint32_t x) {
+    if (x < RANS_L) {
+        const uint32_t t = rd_peek(e);
+        const bool p2 = x < (1u << 15);
+        x = p2 ? ((x << 16) | __byte_perm(t, 0, 0x4401)) : ((x << 8) | (t & 0xFFu));
+        rd_skip(e, p2 ? 16u : 8u);
+    }
+    e.x = x;
 }
+// RansDecAdvance with the symbol's slot offset d = (x & 4095) - start already formed
+__device__ __forceinline__ void rdec_advance(Ent& e, uint32_t d, uint32_t freq) { rdec_renorm(e, freq * (e.x >> PROB_BITS) + d); }
+
+__device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v)); }
 
 // (Re)build the derived data of fixed table t from its counters: `rescale` applies the
 // FixedSizeRansCtx rescale (freq := cnt, cum := prefix, cnt -= freq>>1, ans_contexts.h:1075-1090);
-// without it the intervals in fc[] are kept (table just loaded).  Then the countdown and the
-// look-up structure of the table's class.  Whole warp.
+// without it the intervals in fc[] are kept (table just loaded).  Then the countdown and, for the run
+// length tables, the slot map.  Whole warp.
 __device__ __noinline__ void fixed_rebuild(uint32_t sb, int t, int lane, bool rescale) {
     const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
     const uint32_t fcb = sb + S_FC + off * 4, cnb = sb + S_CNT + off * 2;
@@ -268,89 +273,71 @@ __device__ __noinline__ void fixed_rebuild(uint32_t sb, int t, int lane, bool re
     const int cntsum = (int)__reduce_add_sync(0xFFFFFFFFu, ns);
     if (lane == 0) sts32(sb + S_LEFT + t * 4, (uint32_t)((PROB_SCALE - 16 - cntsum) / 16 + 1));  // events until cntsum + 16 > 4096
     __syncwarp();
-    if (t >= 15) {  // ptype: c0..c5, c6 = total
-        if (lane < 8) {
-            uint32_t c = 0xFFFFu;
-            if (lane < 6) c = lds32(fcb + lane * 4) & 0xFFFFu;
-            else if (lane == 6) {
-                const uint32_t fc = lds32(fcb + 5 * 4);
-                c = (fc & 0xFFFFu) + (fc >> 16);
-            }
-            sts16(sb + S_PCUM + (t - 15) * 16 + lane * 2, c);
-        }
-        __syncwarp();
-        return;
-    }
-    if (t >= 13) return;
-    // slot -> symbol: lane owns slots [128*lane, 128*lane + 128)
-    const int s0 = lane * 128;
-    int lo = 0, hi = nsym - 1;  // last symbol whose cum <= s0
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)(lds32(fcb + mid * 4) & 0xFFFFu) <= s0) lo = mid; else hi = mid - 1;
-    }
-    int j = lo;
-    uint32_t fcj = lds32(fcb + j * 4);
-    int endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
-    if (t < 6) {
-        // entry = sym<<24 | freq<<12 | cum (freq, cum < 4096 for a table of >= 2 symbols).  Slot s is stored at
-        // word s ^ ((s >> 5) & 0x1C): for this lane's 128 slots that is an XOR of the 16-byte group index with
-        // lane & 7, which spreads the 8 lanes of a quarter warp over all banks (conflict-free 128-bit stores).
-        const uint32_t row = sb + S_LUT32 + (uint32_t)t * 16384u + (uint32_t)s0 * 4u;
-        const uint32_t swz = (uint32_t)(lane & 7) << 4;
-        for (int g = 0; g < 32; g++) {
-            const int s = s0 + 4 * g;
-            uint32_t w[4];
-            if (s + 4 <= endj || j == nsym - 1) {
-                w[0] = w[1] = w[2] = w[3] = ((uint32_t)j << 24) | ((fcj >> 16) << 12) | (fcj & 0xFFFu);
-            } else {
+    if (t >= 6) return;
+    // ---- slot map of a 256-symbol table.  (1) every symbol drops its entry at its first slot and marks that
+    // slot in a 4096-bit mask; (2) per 32-slot word, the last marked slot before it (prefix maximum); (3) each
+    // lane fills groups of 4 slots, consecutive lanes consecutive groups (conflict-free 128-bit accesses): the
+    // entry in force at the group's first slot comes from the mask, the other three follow the group's own marks.
+    const uint32_t lut = sb + S_LUT32 + (uint32_t)t * 16384u, heads = sb + S_HEADS, lasth = sb + S_LASTH;
+    sts128(heads + 16 * lane, 0, 0, 0, 0);
+    __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    while (s + k >= endj && j < nsym - 1) {
-                        j++;
-                        fcj = lds32(fcb + j * 4);
-                        endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
-                    }
-                    w[k] = ((uint32_t)j << 24) | ((fcj >> 16) << 12) | (fcj & 0xFFFu);
-                }
-            }
-            sts128(row + (((uint32_t)g << 4) ^ swz), w[0], w[1], w[2], w[3]);
-        }
-    } else {
-        const uint32_t row = sb + S_LUT8 + (uint32_t)(t - 6) * LUT8_ROW + (uint32_t)lane * 132u;
-        for (int g = 0; g < 32; g++) {
-            const int s = s0 + 4 * g;
-            uint32_t word;
-            if (s + 4 <= endj || j == nsym - 1)
-                word = (uint32_t)j * 0x01010101u;
-            else {
-                word = 0;
+    for (int i = 0; i < 8; i++) {
+        const int j = lane + 32 * i;
+        const uint32_t fc = lds32(fcb + j * 4);
+        const uint32_t c = fc & 0xFFFu;
+        sts32(lut + c * 4, ((uint32_t)j << 24) | ((fc >> 16) << 12) | c);
+        red_or_shared(heads + ((c >> 5) << 2), 1u << (c & 31));
+    }
+    __syncwarp();
+    {
+        const uint4 m = lds128(heads + 16 * lane);
+        const int w0 = 4 * lane;
+        // last mark inside each of my four words (-1: none), then the running maximum before each word
+        const int h0 = m.x ? 32 * w0 + 31 - __clz(m.x) : -1;
+        const int h1 = m.y ? 32 * (w0 + 1) + 31 - __clz(m.y) : -1;
+        const int h2 = m.z ? 32 * (w0 + 2) + 31 - __clz(m.z) : -1;
+        const int h3 = m.w ? 32 * (w0 + 3) + 31 - __clz(m.w) : -1;
+        const int mine = max(max(h0, h1), max(h2, h3));
+        int inc = mine;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    while (s + k >= endj && j < nsym - 1) {
-                        j++;
-                        fcj = lds32(fcb + j * 4);
-                        endj = (int)(fcj & 0xFFFFu) + (int)(fcj >> 16);
-                    }
-                    word |= (uint32_t)j << (8 * k);
-                }
-            }
-            sts32(row + 4 * g, word);
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc = max(inc, u);
         }
+        int before = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+        if (lane == 0) before = 0;
+        const int b1 = max(before, h0), b2 = max(b1, h1), b3 = max(b2, h2);
+        sts128(lasth + 16 * lane, (uint32_t)before, (uint32_t)b1, (uint32_t)b2, (uint32_t)b3);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        const int g = 32 * i + lane;
+        const int w = g >> 3, pos = (g & 7) * 4;
+        const uint32_t m = lds32(heads + 4 * w);
+        const uint32_t lb = lds32(lasth + 4 * w);
+        const uint4 q = lds128(lut + 16 * g);
+        const uint32_t below = m & ((2u << pos) - 1u);
+        const uint32_t head = below ? (uint32_t)(32 * w + 31 - __clz(below)) : lb;
+        const uint32_t cur = lds32(lut + 4 * head);
+        const uint32_t e1 = (m >> (pos + 1)) & 1u ? q.y : cur;
+        const uint32_t e2 = (m >> (pos + 2)) & 1u ? q.z : e1;
+        const uint32_t e3 = (m >> (pos + 3)) & 1u ? q.w : e2;
+        sts128(lut + 16 * g, cur, e1, e2, e3);
     }
     __syncwarp();
 }
 
 // common tail of a fixed-table symbol: count it (every lane of the converged warp performs the same
 // read-modify-write with the same values: no lane predicate, no divergence, no barrier on the per-symbol
-// path), run the countdown, rebuild the table when it expires
-__device__ __forceinline__ void fx_update(Ent& e, int t, int off, int sym) {
-    const uint32_t ca = e.sb + S_CNT + (uint32_t)(off + sym) * 2u, la = e.sb + S_LEFT + (uint32_t)t * 4u;
+// path), run the countdown (`left` was loaded from `la` before the search), rebuild the table when it expires
+__device__ __forceinline__ void fx_update(Ent& e, int t, uint32_t la, uint32_t left, int idx) {
+    const uint32_t ca = e.sb + S_CNT + (uint32_t)idx * 2u;
     sts16(ca, lds16(ca) + 16);
-    const uint32_t left = lds32(la) - 1;
-    sts32(la, left);
+    sts32(la, left - 1);
     rdec_count(e);
-    if (left == 0) {
+    if (left == 1) {
         __syncwarp();
 #ifdef SCPR_PROF
         const long long tr__ = clock64();
@@ -366,52 +353,45 @@ __device__ __forceinline__ void fx_update(Ent& e, int t, int off, int sym) {
 // run length through ntab[ptype] (decodeN, screencap.h:346-359, 361)
 __device__ __forceinline__ int dec_n(Ent& e, int ptype) {
     PROF_T0
+    const uint32_t la = e.sb + S_LEFT + (uint32_t)ptype * 4u;
+    const uint32_t left = lds32(la);
     const uint32_t v = e.x & (PROB_SCALE - 1);
-    const uint32_t en = lds32(e.sb + S_LUT32 + ((uint32_t)ptype << 14) + ((v ^ ((v >> 5) & 0x1Cu)) << 2));
+    const uint32_t en = lds32(e.sb + S_LUT32 + ((uint32_t)ptype << 14) + (v << 2));
     const int sym = (int)(en >> 24);
     rdec_advance(e, v - (en & 0xFFFu), (en >> 12) & 0xFFFu);
-    fx_update(e, ptype, ptype << 8, sym);
+    fx_update(e, ptype, la, left, (ptype << 8) + sym);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return sym;
 }
-// pixel type through ptypetab[last] (decodeP)
-__device__ __forceinline__ int dec_ptype(Ent& e, int last) {
+// decodeF for every other table: NSYM symbols, table t at fc[off]
+template <int NSYM>
+__device__ __forceinline__ int dec_tab(Ent& e, int t, int off) {
     PROF_T0
-    const uint4 q = lds128(e.sb + S_PCUM + (uint32_t)last * 16u);
+    const uint32_t la = e.sb + S_LEFT + (uint32_t)t * 4u;
+    const uint32_t left = lds32(la);
+    const uint32_t fcb = e.sb + S_FC + (uint32_t)off * 4u;
     const uint32_t v = e.x & (PROB_SCALE - 1);
-    const uint32_t c1 = q.x >> 16, c2 = q.y & 0xFFFFu, c3 = q.y >> 16, c4 = q.z & 0xFFFFu, c5 = q.z >> 16, c6 = q.w & 0xFFFFu;
-    const bool g1 = v >= c1, g2 = v >= c2, g3 = v >= c3, g4 = v >= c4, g5 = v >= c5;
-    const int sym = (int)g1 + (int)g2 + (int)g3 + (int)g4 + (int)g5;
-    // the cumulative frequencies are strictly increasing: cum = the largest one <= v, next = the smallest one > v
-    const uint32_t cum = max(max(g1 ? c1 : 0u, g2 ? c2 : 0u), max(g3 ? c3 : 0u, max(g4 ? c4 : 0u, g5 ? c5 : 0u)));
-    const uint32_t nxt = min(min(min(g1 ? c6 : c1, g2 ? c6 : c2), min(g3 ? c6 : c3, g4 ? c6 : c4)), g5 ? c6 : c5);
-    rdec_advance(e, v - cum, nxt - cum);
-    fx_update(e, 15 + last, 3144 + 8 * last, sym);
-    PROF_ADD(c_fixed) PROF_CNT(n_fixed)
-    return sym;
-}
-// decodeF for the remaining tables (compile-time table T with NSYM symbols)
-template <int NSYM, int T>
-__device__ __forceinline__ int dec_fxc(Ent& e) {
-    PROF_T0
-    constexpr int off = fx_off(T);
-    const uint32_t fcb = e.sb + S_FC + off * 4;
-    const uint32_t v = e.x & (PROB_SCALE - 1);
-    int j;
-    if (NSYM <= 256) {
-        j = (int)lds8(e.sb + S_LUT8 + (uint32_t)(T - 6) * LUT8_ROW + v + ((v >> 7) << 2));
-    } else {  // 512 symbols: two ballot levels over the cumulative frequencies
-        const bool le = (lds32(fcb + e.lane * 64) & 0xFFFFu) <= v;
-        const int L = 31 - __clz(__ballot_sync(0xFFFFFFFFu, le));
-        const bool le2 = e.lane < 16 && (lds32(fcb + (L * 16 + (e.lane & 15)) * 4) & 0xFFFFu) <= v;
-        j = L * 16 + __popc(__ballot_sync(0xFFFFFFFFu, le2)) - 1;
+    constexpr int W = NSYM > 32 ? NSYM / 32 : NSYM;      // intervals searched by the final ballot
+    constexpr int WP = W <= 8 ? 8 : 16;                  // lanes that hold one (power of two >= W)
+    uint32_t base = 0;
+    if (NSYM > 32) {
+        const uint32_t c0 = lds32(fcb + (uint32_t)e.lane * (W * 4)) & 0xFFFFu;
+        base = (uint32_t)(31 - __clz(__ballot_sync(0xFFFFFFFFu, c0 <= v) | 1u)) * W;
     }
-    const uint32_t fc = lds32(fcb + j * 4);
-    rdec_advance(e, v - (fc & 0xFFFFu), fc >> 16);
-    fx_update(e, T, off, j);
+    const uint32_t fc = lds32(fcb + (base + (uint32_t)(e.lane & (WP - 1))) * 4u);
+    const uint32_t d = v - (fc & 0xFFFFu), f = fc >> 16;
+    const uint32_t bh = __ballot_sync(0xFFFFFFFFu, e.lane < W && d < f);
+    const int j = 31 - __clz(bh | 1u);
+    const uint32_t xk = f * (e.x >> PROB_BITS) + d;
+    rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, j));
+    const int sym = (int)base + j;
+    fx_update(e, t, la, left, off + sym);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
-    return j;
+    return sym;
 }
+template <int NSYM, int T>
+__device__ __forceinline__ int dec_fxc(Ent& e) { return dec_tab<NSYM>(e, T, fx_off(T)); }
+__device__ __forceinline__ int dec_ptype(Ent& e, int last) { return dec_tab<6>(e, 15 + last, 3144 + 8 * last); }  // decodeP
 __device__ __forceinline__ int dec_bool(Ent& e) {  // decodeBool
     const uint32_t v = e.x & (PROB_SCALE - 1);
     const int flag = v >= PROB_SCALE / 2;
@@ -420,105 +400,142 @@ __device__ __forceinline__ int dec_bool(Ent& e) {  // decodeBool
     return flag;
 }
 
-// ---- colour contexts (global memory; the 128-byte head of a context is one L1 line) ---------------------
-// The search is spread over the lanes: every lane tests its own entries against the slot and forms its own
-// candidate successor state, a ballot names the winner, one shuffle delivers it.  Counting, rescaling and
-// the SmallContext prefix sums are done by the lanes in parallel as well; only first occurrences of a
-// symbol and promotions between kinds go through the serial state machine of models.cuh on lane 0.
-constexpr int CS_SENT = 64, CS_CNT = 128, CS_FREQ = 640, CS_CUM = 1152;
-static_assert(offsetof(ColorState, sent) == CS_SENT && offsetof(ColorState, cnt) == CS_CNT && offsetof(ColorState, freq) == CS_FREQ &&
-                  offsetof(ColorState, cum) == CS_CUM && offsetof(ColorState, ssym) == 16 && offsetof(ColorState, sfreq) == 32,
+// ---- colour contexts -----------------------------------------------------------------------------------
+// Screen content keeps a small working set of SmallContexts (kinds 4/5: <= 16 sorted symbols) busy.  They are
+// held in a direct-mapped shared-memory cache, one entry per lane: entry k = ssym | sfreq << 8 | start << 20
+// with start = the frequencies before k + the symbols not met below ssym[k], plus a two-word header with
+// totFr, maxpos, d and -- recomputed when the context is updated, i.e. off the rANS dependency chain -- the
+// normalising shift and the bonus (the code space left over by rounding, lent to the most probable symbol for
+// one look-up, ans_contexts.h:195-236).  The search is then: every lane forms its interval, tests the slot
+// and advances its own candidate state; a ballot names the winner, one shuffle delivers its state and one its
+// entry.  The canonical ColorState in global memory is only read when a context enters the cache and written
+// when it leaves (eviction, a symbol not met before, end of the launch).
+// Kinds 6/7 (flat 256-symbol tables) stay in global memory, searched and rescaled by all 32 lanes; first
+// occurrences of a symbol and promotions between kinds go through the serial state machine of models.cuh.
+constexpr int CS_CNT = 128, CS_FREQ = 640, CS_CUM = 1152;
+static_assert(offsetof(ColorState, cnt) == CS_CNT && offsetof(ColorState, freq) == CS_FREQ && offsetof(ColorState, cum) == CS_CUM &&
+                  offsetof(ColorState, ssym) == 16 && offsetof(ColorState, sfreq) == 32,
               "ColorState layout");
+__device__ __forceinline__ uint32_t cache_slot(int id) { return (uint32_t)(id ^ (id >> 7)) & (NCACHE - 1); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y)); }
 
-// after the serial state machine touched a context: publish its kind, and for a SmallContext rebuild the
-// packed entries (and the cached totFr of kind 4, which the reference recomputes on every call, :303)
-__device__ __noinline__ void color_refresh(ModelState* m, uint32_t sb, int lane, int id) {
-    ColorState& x = m->color[id];
-    __syncwarp();
-    const int kind = x.kind;
-    if (lane == 0) sts8(sb + S_KMAP + id, kind);
-    if (kind == 4 || kind == 5) {
-        const int k = lane & 15, d = x.d;
-        const uint32_t s = x.ssym[k], f = k < d ? x.sfreq[k] : 0u;
-        uint32_t inc = f;
+// inclusive prefix sum over 16 lanes
+__device__ __forceinline__ uint32_t scan16(uint32_t v, int k) {
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o, 16);
-            if (k >= o) inc += u;
+    for (int o = 1; o < 16; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o, 16);
+        if (k >= o) v += u;
+    }
+    return v;
+}
+// header of a cached SmallContext: totFr is normalised by `shift` to (2048, 4096]; what is left of 4096 is the bonus
+__device__ __forceinline__ void small_header(uint32_t a, int totFr, int maxpos, int d, uint32_t fmax) {
+    const int shift = max(0, __clz(totFr - 1) - 20);  // smallest shift with totFr << shift > 2048
+    const uint32_t bonus = (uint32_t)(PROB_SCALE - (totFr << shift)) >> shift;
+    sts64(a, (uint32_t)totFr | ((uint32_t)maxpos << 16) | ((uint32_t)d << 20) | ((uint32_t)shift << 28), bonus | (fmax << 16));
+}
+// cache entry h -> its ColorState (kinds 4/5 keep kind and d; the hot path changes sfreq, maxpos, totFr only)
+__device__ __noinline__ void cache_writeback(ModelState* m, uint32_t sb, int lane, uint32_t h) {
+    const uint32_t tag = lds32(sb + S_CTAG + 4 * h);
+    if (tag != 0xFFFFFFFFu) {
+        ColorState& x = m->color[tag];
+        if (lane < 16) {
+            const uint32_t ent = lds32(sb + S_CENT + 64 * h + 4 * lane);
+            x.ssym[lane] = (uint8_t)ent;
+            x.sfreq[lane] = (uint16_t)((ent >> 8) & 0xFFFu);
         }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 15, 16);
-        if (lane < d) x.sent[k] = s | (f << 8) | ((inc - f + s - k) << 20);
-        if (lane == 0 && kind == 4) x.cntsum = (int)(256 - d + total);
+        if (lane == 0) {
+            const uint32_t h0 = lds32(sb + S_CHDR + 8 * h);
+            x.cntsum = (int)(h0 & 0xFFFFu);
+            x.maxpos = (uint8_t)((h0 >> 16) & 15u);
+            sts32(sb + S_CTAG + 4 * h, 0xFFFFFFFFu);
+        }
     }
     __syncwarp();
 }
+// bring SmallContext `id` into entry h (evicting its occupant)
+__device__ __noinline__ void cache_load(ModelState* m, uint32_t sb, int lane, uint32_t h, int id) {
+    cache_writeback(m, sb, lane, h);
+    const ColorState& x = m->color[id];
+    const int k = lane & 15, d = x.d, maxpos = x.maxpos, kind = x.kind;
+    const uint32_t s = x.ssym[k], f = k < d ? x.sfreq[k] : 0u;
+    const uint32_t inc = scan16(f, k);
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 15, 16);
+    const uint32_t fmax = __shfl_sync(0xFFFFFFFFu, f, maxpos & 15);
+    // the reference recomputes totFr of a Cx4 on every call (:303) and caches it for a Cx5
+    const int totFr = kind == 4 ? (int)(256 - d + total) : x.cntsum;
+    if (lane < 16) sts32(sb + S_CENT + 64 * h + 4 * k, k < d ? (s | (f << 8) | ((inc - f + s - k) << 20)) : 0u);
+    if (lane == 0) {
+        small_header(sb + S_CHDR + 8 * h, totFr, maxpos, d, fmax);
+        sts32(sb + S_CTAG + 4 * h, (uint32_t)id);
+    }
+    __syncwarp();
+}
+// after the serial state machine touched a context: publish its kind
+__device__ __forceinline__ void color_refresh(ModelState* m, uint32_t sb, int lane, int id) {
+    __syncwarp();
+    if (lane == 0) sts8(sb + S_KMAP + id, m->color[id].kind);
+    __syncwarp();
+}
 
-__device__ __forceinline__ int dec_color_small(Ent& e, uint8_t* xs, int id) {  // SmallContext decode, ans_contexts.h:238-283
-    const uint4 hd = *reinterpret_cast<const uint4*>(xs);
+// SmallContext decode (ans_contexts.h:238-283) from cache entry h; `ent` = this lane's entry, `hd` = the header
+__device__ __forceinline__ int dec_color_small(Ent& e, int id, uint32_t h, uint32_t ent, uint2 hd) {
     const int k = e.lane & 15;
-    const uint32_t ent = *reinterpret_cast<const uint32_t*>(xs + CS_SENT + 4 * k);
+    const int maxpos = (hd.x >> 16) & 15u, shift = hd.x >> 28;
+    const uint32_t bonus = hd.y & 0xFFFFu;
     const uint32_t v0 = e.x & (PROB_SCALE - 1);
-    const int maxpos = (hd.x >> 16) & 255, d = hd.y & 0xFFFF, totFr = (int)hd.z;
-    const int shift = max(0, __clz(totFr - 1) - 20);  // smallest shift with totFr << shift > 2048
-    const int bonus = (PROB_SCALE - (totFr << shift)) >> shift;
-    const int v = (int)(v0 >> shift);
-    const int sk = ent & 255, fk = (ent >> 8) & 0xFFF, bk = ent >> 20;
-    const int st = bk + (k > maxpos ? bonus : 0);
-    const int fr = fk + (k == maxpos ? bonus : 0);
-    const bool ge = e.lane < d && v >= st;
-    const bool hit = ge && v < st + fr;
-    const uint32_t bh = __ballot_sync(0xFFFFFFFFu, hit);
+    const uint32_t fr = (((ent >> 8) & 0xFFFu) + (k == maxpos ? bonus : 0u)) << shift;
+    const uint32_t st = ((ent >> 20) + (k > maxpos ? bonus : 0u)) << shift;
+    const uint32_t dd = v0 - st;
+    const uint32_t bh = __ballot_sync(0xFFFFFFFFu, e.lane < 16 && dd < fr);
     int c;
     if (bh) {
-        const int pos = __ffs(bh) - 1;
+        const int pos = 31 - __clz(bh);
         // every lane advanced its own candidate; take the winner's
-        const uint32_t xk = (uint32_t)(fr << shift) * (e.x >> PROB_BITS) + (v0 - (uint32_t)(st << shift));
-        const uint32_t xn = __shfl_sync(0xFFFFFFFFu, xk, pos);
-        c = __shfl_sync(0xFFFFFFFFu, sk, pos);
-        const int fmax = __shfl_sync(0xFFFFFFFFu, fk, maxpos);
-        const int nf = __shfl_sync(0xFFFFFFFFu, fk, pos) + 50;
-        // renormalise (as rdec_advance)
-        const uint32_t t = rd_peek(e);
-        const bool p1 = xn < RANS_L, p2 = xn < (1u << 15);
-        e.x = p2 ? ((xn << 16) | __byte_perm(t, 0, 0x4401)) : (p1 ? ((xn << 8) | (t & 0xFFu)) : xn);
-        rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
-        // count the symbol (ans_contexts.h:205-214): freq += 50, totFr += 50, maxpos moves on strict >
-        const int ntot = totFr + 50;
+        const uint32_t xk = fr * (e.x >> PROB_BITS) + dd;
+        rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, pos));
+        const uint32_t we = __shfl_sync(0xFFFFFFFFu, ent, pos);
+        c = (int)(we & 255u);
+        // count the symbol (ans_contexts.h:205-214): freq += 50, totFr += 50, maxpos moves on strict >, rescale
+        const int d = (hd.x >> 20) & 31u;
+        int ntot = (int)(hd.x & 0xFFFFu) + 50;
+        const uint32_t nf = ((we >> 8) & 0xFFFu) + 50u;
+        uint32_t fmax = hd.y >> 16;
+        const bool moved = pos != maxpos && nf > fmax;
+        const int nmax = moved ? pos : maxpos;
+        fmax = (moved || pos == maxpos) ? nf : fmax;
         uint32_t ne = ent + (k == pos ? (50u << 8) : 0u) + (k > pos ? (50u << 20) : 0u);
         if (ntot + 50 > PROB_SCALE) {  // rescale: f -= f >> 1 (:186-193); the prefix sums follow
-            const uint32_t f2 = e.lane < d ? ((ne >> 8) & 0xFFFu) : 0u;
-            const uint32_t h = f2 - (f2 >> 1);
-            uint32_t inc = h;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o, 16);
-                if (k >= o) inc += u;
-            }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 15, 16);
-            ne = (uint32_t)sk | (h << 8) | ((inc - h + sk - k) << 20);
-            if (e.lane < d) {
-                *reinterpret_cast<uint32_t*>(xs + CS_SENT + 4 * k) = ne;
-                *reinterpret_cast<uint16_t*>(xs + 32 + 2 * k) = (uint16_t)h;
-            }
-            if (e.lane == 0) *reinterpret_cast<int*>(xs + 8) = (int)(256 - d + total);
+            const uint32_t sym = ent & 255u, f2 = k < d ? ((ne >> 8) & 0xFFFu) : 0u;
+            const uint32_t hf = f2 - (f2 >> 1);
+            const uint32_t inc = scan16(hf, k);
+            ntot = (int)(256 - d + __shfl_sync(0xFFFFFFFFu, inc, 15, 16));
+            ne = sym | (hf << 8) | ((inc - hf + sym - k) << 20);
+            fmax -= fmax >> 1;
             PROF_CNT(n_resc)
-        } else {
-            if (e.lane < d && k >= pos) *reinterpret_cast<uint32_t*>(xs + CS_SENT + 4 * k) = ne;
-            if (e.lane == pos) *reinterpret_cast<uint16_t*>(xs + 32 + 2 * k) = (uint16_t)nf;
-            if (e.lane == 0) *reinterpret_cast<int*>(xs + 8) = ntot;
         }
-        if (e.lane == 0 && pos != maxpos && nf > fmax) xs[2] = (uint8_t)pos;
+        if (e.lane < d) sts32(e.sb + S_CENT + 64 * h + 4 * k, ne);
+        small_header(e.sb + S_CHDR + 8 * h, ntot, nmax, d, fmax);
     } else {  // a symbol not met yet: width 1 in the gap after the last entry below it
-        const uint32_t bg = __ballot_sync(0xFFFFFFFFu, ge);
+        const int d = (hd.x >> 20) & 31u;
+        const int v = (int)(v0 >> shift);
+        const int su = (int)(st >> shift), fu = (int)(fr >> shift);
+        const uint32_t bg = __ballot_sync(0xFFFFFFFFu, e.lane < d && v >= su);
         int lastSymb = 0, cumFr = 0;
         if (bg) {
             const int K = 31 - __clz(bg);
-            lastSymb = __shfl_sync(0xFFFFFFFFu, sk, K) + 1;
-            cumFr = __shfl_sync(0xFFFFFFFFu, st + fr, K);
+            lastSymb = (int)(__shfl_sync(0xFFFFFFFFu, ent, K) & 255u) + 1;
+            cumFr = __shfl_sync(0xFFFFFFFFu, su + fu, K);
         }
-        c = lastSymb + v - cumFr;
+        c = (lastSymb + v - cumFr) & 255;
         rdec_advance(e, v0 - (uint32_t)(v << shift), (uint32_t)(1 << shift));
-        if (e.lane == 0) cc_encode_counted(e.m->color[id], c & 255);  // insert / promote: the general path
+        cache_writeback(e.m, e.sb, e.lane, h);  // insert / promote on the canonical state: the general path
+        if (e.lane == 0) cc_encode_counted(e.m->color[id], c);
         color_refresh(e.m, e.sb, e.lane, id);
         PROF_CNT(n_gen)
     }
@@ -594,12 +611,8 @@ __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int k
     const int L = 31 - __clz(bal | 1u);
     const uint32_t cum = half_at(cr, idx & 7), freq = half_at(fq, idx & 7);
     const uint32_t xk = freq * (e.x >> PROB_BITS) + (v - cum);
-    const uint32_t xn = __shfl_sync(0xFFFFFFFFu, xk, L);
+    rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, L));
     const int c = L * 8 + __shfl_sync(0xFFFFFFFFu, idx, L);
-    const uint32_t t = rd_peek(e);
-    const bool p1 = xn < RANS_L, p2 = xn < (1u << 15);
-    e.x = p2 ? ((xn << 16) | __byte_perm(t, 0, 0x4401)) : (p1 ? ((xn << 8) | (t & 0xFFu)) : xn);
-    rd_skip(e, p2 ? 16u : (p1 ? 8u : 0u));
     // count the symbol
     uint16_t* cnt = reinterpret_cast<uint16_t*>(xs + CS_CNT);
     const int cn = cnt[c], cs = (int)hd.z;
@@ -622,24 +635,36 @@ __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int k
 }
 __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
     PROF_T0
-    uint8_t* xs = reinterpret_cast<uint8_t*>(&e.m->color[id]);
-    const int kind = (int)lds8(e.sb + S_KMAP + id);
+    const uint32_t h = cache_slot(id);
+    const uint32_t tag = lds32(e.sb + S_CTAG + 4 * h);
+    uint32_t ent = lds32(e.sb + S_CENT + 64 * h + 4 * (e.lane & 15));
+    uint2 hd = lds64(e.sb + S_CHDR + 8 * h);
     int c;
-    if (kind >= 6) {
-        c = dec_color_flat(e, xs, id, kind);
-        PROF_ADD(c_flat) PROF_CNT(n_flat)
-    } else if (kind >= 4) {
-        c = dec_color_small(e, xs, id);
-        PROF_ADD(c_small) PROF_CNT(n_small)
-    } else {  // no statistics yet: the byte is stored raw (screencap.h:324-325)
-        c = (int)(rd_peek(e) & 0xFFu);
-        rd_skip(e, 8);
-        if (e.lane == 0) cc_update_raw(e.m->color[id], c, e.f0);
-        color_refresh(e.m, e.sb, e.lane, id);
-        PROF_ADD(c_raw) PROF_CNT(n_raw)
+    if (tag != (uint32_t)id) {
+        const int kind = (int)lds8(e.sb + S_KMAP + id);
+        if (kind >= 6) {
+            c = dec_color_flat(e, reinterpret_cast<uint8_t*>(&e.m->color[id]), id, kind);
+            rdec_count(e);
+            PROF_ADD(c_flat) PROF_CNT(n_flat) PROF_ADD(c_color) PROF_CNT(n_color)
+            return c;
+        }
+        if (kind < 4) {  // no statistics yet: the byte is stored raw (screencap.h:324-325)
+            c = (int)(rd_peek(e) & 0xFFu);
+            rd_skip(e, 8);
+            if (e.lane == 0) cc_update_raw(e.m->color[id], c, e.f0);
+            color_refresh(e.m, e.sb, e.lane, id);
+            rdec_count(e);
+            PROF_ADD(c_raw) PROF_CNT(n_raw) PROF_ADD(c_color) PROF_CNT(n_color)
+            return c;
+        }
+        cache_load(e.m, e.sb, e.lane, h, id);
+        ent = lds32(e.sb + S_CENT + 64 * h + 4 * (e.lane & 15));
+        hd = lds64(e.sb + S_CHDR + 8 * h);
+        PROF_CNT(n_miss)
     }
+    c = dec_color_small(e, id, h, ent, hd);
     rdec_count(e);
-    PROF_ADD(c_color) PROF_CNT(n_color)
+    PROF_ADD(c_small) PROF_CNT(n_small) PROF_ADD(c_color) PROF_CNT(n_color)
     return c;
 }
 __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
@@ -999,7 +1024,7 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
 }
 
 // one warp per chain
-__global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
+__global__ void __launch_bounds__(32, 1) k_dec_chain(DecWork w) {
     extern __shared__ __align__(16) uint8_t s_mem[];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_mem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));  // keep the base in a register: otherwise it is rematerialised (S2R) at every use
@@ -1023,7 +1048,7 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
     e.cx = e.cx1 = 0;
     e.nleft = RANS_BLOCK;
     e.x = 0;
-    e.w0 = e.w1 = e.w2 = e.k8 = 0;
+    e.w0 = e.w1 = e.k8 = 0;
     e.wp = nullptr;
     e.sb = sb;
     e.lane = lane;
@@ -1040,6 +1065,7 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
         }
     }
     for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, reinterpret_cast<const uint32_t*>(e.m->kmap)[i]);
+    for (int i = lane; i < NCACHE; i += 32) sts32(sb + S_CTAG + 4 * i, 0xFFFFFFFFu);
     __syncwarp();
     for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
     for (int f = ch.first; f < ch.first + ch.count; f++) {
@@ -1051,6 +1077,7 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
             if (df.kind == DK_I || df.renew) {  // RenewI
                 for (int i = lane; i < NUM_COLOR_CX; i += 32) e.m->color[i].kind = 0;
                 for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, 0);
+                for (int i = lane; i < NCACHE; i += 32) sts32(sb + S_CTAG + 4 * i, 0xFFFFFFFFu);  // cached contexts are void
                 for (int t = 0; t < NUM_FIXED_CX; t++) {  // FixedSizeRansCtx::renew, ans_contexts.h:1114-1131
                     const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
                     const int fr = PROB_SCALE / nsym, c0 = fr - (fr >> 1);
@@ -1091,8 +1118,9 @@ __global__ void __launch_bounds__(32) k_dec_chain(DecWork w) {
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
                e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw);
 #endif
-    // leave the fixed tables and the kinds behind for the next call
+    // leave the cached contexts, the fixed tables and the kinds behind for the next call
     __syncwarp();
+    for (uint32_t h = 0; h < NCACHE; h++) cache_writeback(e.m, sb, lane, h);
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         FixedState& g0 = e.m->fx[t];
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
