@@ -51,50 +51,71 @@ struct DecWork {
     int f0;
     uint8_t* out;       // n output frames
     const uint8_t* prev0;   // frame decoded last by the previous call (output format, pitch g.pitch)
-    int* src_cur;       // per chain: nb ints, frame that holds each block's current pixels (-1 = prev0)
-    int* src_prev;      // per chain: same, as of the previous frame
-    int* stamp;         // per chain: frame in which src_cur was last changed
+    uint32_t* gmap;     // per chain: nb block-source words when they do not fit in shared memory (see BlockMap)
     uint8_t* upd;       // n * nb flags: block written by the chain kernel in this frame
     int16_t* fill_src;  // n * nb: source frame of every block (k_dec_sources)
     int n;
 };
 
-// ---- pixel access through the block-source map ----------------------------------------------------
-struct ChainCtx {
-    const DecWork* w;
-    int* src_cur; int* src_prev; int* stamp;
-    int f;              // frame being decoded
+// ---- block-source map ------------------------------------------------------------------------------
+// For every 16x16 block one word: (source as of the previous frame) << 16 | (current source).  A source
+// is a 16-bit code: 0xFFFF = prev0 (the frame the previous call left behind), otherwise the index of the
+// frame of this call that last wrote the block, with bit 14 set when that frame is a flat frame (its
+// pixels are the frame's colour; k_dec_fill paints it later).  A frame writes a block at most once, so
+// "the source as of the previous frame" is the high half exactly when the low half names the frame being
+// decoded.  The map lives in shared memory when the frame is small enough (SM = true), else in global
+// memory; it is only ever touched by the warps of one CTA.
+constexpr uint32_t SRC_PREV0 = 0xFFFFu, SRC_FLAT = 0x4000u, SRC_IDX = 0x3FFFu;
+constexpr int DEC_MAX_FRAMES = 16000;  // frames per launch (14-bit frame index in the map)
+template <bool SM>
+struct BlockMap {
+    uint32_t sbase;   // shared address (SM)
+    uint32_t* g;      // global words (!SM)
+    __device__ __forceinline__ uint32_t get(int b) const {
+        if (SM) {
+            uint32_t v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + 4u * (uint32_t)b));
+            return v;
+        }
+        return *reinterpret_cast<volatile uint32_t*>(g + b);
+    }
+    __device__ __forceinline__ void set(int b, uint32_t v) const {
+        if (SM)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + 4u * (uint32_t)b), "r"(v));
+        else
+            *reinterpret_cast<volatile uint32_t*>(g + b) = v;
+    }
+    // block b is written by frame code `fc` (frame index, | SRC_FLAT for a flat frame)
+    __device__ __forceinline__ void write(int b, uint32_t fc) const { set(b, (get(b) << 16) | fc); }
 };
-
-__device__ __forceinline__ uint32_t frame_px(const DecWork& w, int src, int x, int y) {
-    if (src >= 0 && w.frames[src].kind == DK_FLAT) return w.frames[src].flat_clr;
-    const uint8_t* base = src >= 0 ? w.out + (size_t)src * w.g.frame_bytes : w.prev0;
-    return load_px(base, w.g, x, y);
+__device__ __forceinline__ uint32_t src_now(uint32_t m) { return m & 0xFFFFu; }
+__device__ __forceinline__ uint32_t src_before(uint32_t m, int f) {  // as of frame f - 1
+    const uint32_t cur = m & 0xFFFFu;
+    return (cur != SRC_PREV0 && (cur & SRC_IDX) == (uint32_t)f) ? (m >> 16) : cur;
 }
+
 struct PixSrc {
     const uint8_t* base;
     uint32_t clr;
     bool flat;
 };
-__device__ __forceinline__ PixSrc resolve_src(const DecWork& w, int src) {
+__device__ __forceinline__ PixSrc resolve_src(const DecWork& w, uint32_t code) {
     PixSrc s;
-    s.flat = src >= 0 && w.frames[src].kind == DK_FLAT;
-    s.clr = s.flat ? w.frames[src].flat_clr : 0u;
-    s.base = src >= 0 ? w.out + (size_t)src * w.g.frame_bytes : w.prev0;
+    s.flat = false;
+    s.clr = 0u;
+    if (code == SRC_PREV0) {
+        s.base = w.prev0;
+    } else {
+        const uint32_t idx = code & SRC_IDX;
+        s.base = w.out + (size_t)idx * w.g.frame_bytes;
+        if (code & SRC_FLAT) {
+            s.flat = true;
+            s.clr = w.frames[idx].flat_clr;
+        }
+    }
     return s;
 }
 __device__ __forceinline__ uint32_t src_px(const PixSrc& s, const Geo& g, int x, int y) { return s.flat ? s.clr : load_px(s.base, g, x, y); }
-// pixel of the frame being decoded (only valid for pixels already reconstructed or unchanged)
-__device__ __forceinline__ uint32_t cur_px(const ChainCtx& c, int x, int y) {
-    const int b = (y >> 4) * c.w->g.nbx + (x >> 4);
-    return frame_px(*c.w, c.src_cur[b], x, y);
-}
-// pixel of the previous frame
-__device__ __forceinline__ uint32_t prev_px(const ChainCtx& c, int x, int y) {
-    const int b = (y >> 4) * c.w->g.nbx + (x >> 4);
-    const int s = c.stamp[b] == c.f ? c.src_prev[b] : c.src_cur[b];
-    return frame_px(*c.w, s, x, y);
-}
 __device__ __forceinline__ void store_px(uint8_t* frame, const Geo& g, int x, int y, uint32_t v) {
     uint8_t* p = frame + (uint32_t)(y * g.pitch + x * g.bpp);
     if (g.bpp == 4)
@@ -160,8 +181,13 @@ constexpr uint32_t S_TILE = S_KMAP + NUM_COLOR_CX;       // u32[17][17]
 constexpr uint32_t S_CTAG = S_TILE + 1168;               // u32[NCACHE]: context id held by a cache entry (~0 = none)
 constexpr uint32_t S_CHDR = S_CTAG + NCACHE * 4;         // uint2[NCACHE]: totFr | maxpos<<16 | d<<20 | shift<<28, bonus | sfreq[maxpos]<<16
 constexpr uint32_t S_CENT = S_CHDR + NCACHE * 8;         // u32[NCACHE][16]: entry k = ssym | sfreq << 8 | start << 20
-constexpr uint32_t S_BTS = S_CENT + NCACHE * 64;         // u8[nb]
-static_assert(S_HEADS % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0 && S_CTAG % 16 == 0, "shared layout alignment");
+constexpr int RING = 256;                                // MV-copy commands in flight (see "helper warps" below)
+constexpr uint32_t S_RING = S_CENT + NCACHE * 64;        // uint4[RING]
+constexpr uint32_t S_SYNC = S_RING + RING * 16;          // u32: head, next, done, quit
+constexpr uint32_t S_BTS = S_SYNC + 16;                  // u8[nb], padded to 16; then (SM maps) u32[nb]
+static_assert(S_HEADS % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0 && S_CTAG % 16 == 0 && S_RING % 16 == 0, "shared layout alignment");
+constexpr int DEC_WARPS = 8;                             // warp 0 = the chain, warp 4 (same scheduler as warp 0) idles, the rest copy
+__host__ __device__ constexpr uint32_t s_map_off(int nb) { return S_BTS + (((uint32_t)nb + 15u) & ~15u); }
 __host__ __device__ constexpr int fx_off(int t) {
     return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
 }
@@ -184,14 +210,15 @@ struct Ent {
 #ifdef SCPR_PROF
     long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
               c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0,
-              c_raw = 0, n_raw = 0, n_miss = 0;
+              c_raw = 0, n_raw = 0, n_miss = 0, c_drain = 0;
 #endif
     uint32_t x;
     uint32_t w0, w1, k8;      // window: stream bytes from bit k8 of w0 on
     const uint32_t* wp;       // address of w1
     int nleft;                // symbols until the next RansDecInit
-    uint32_t cx, cx1;
+    uint32_t lastpx;          // the pixel before the next run: the colour contexts are functions of it (screencap.cpp:371-372, 616-624)
     uint32_t sb;              // shared-memory base address
+    uint32_t head;            // motion-vector copies posted so far
     ModelState* m;
     int f0;
     int lane;
@@ -216,8 +243,11 @@ __device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
     e.x = rd_peek(e);
     rd_skip(e, 32);
 }
+// CNT = false: the caller has checked that the block cannot end within the symbols it is about to decode
+// and subtracts them from nleft itself (one subtraction per pixel run instead of a test per symbol)
+template <bool CNT = true>
 __device__ __forceinline__ void rdec_count(Ent& e) {  // re-init every 131072 symbols (screencap.h:327-331)
-    if (--e.nleft == 0) {
+    if (CNT && --e.nleft == 0) {
         rdec_init(e);
         e.nleft = RANS_BLOCK;
     }
@@ -332,11 +362,12 @@ __device__ __noinline__ void fixed_rebuild(uint32_t sb, int t, int lane, bool re
 // common tail of a fixed-table symbol: count it (every lane of the converged warp performs the same
 // read-modify-write with the same values: no lane predicate, no divergence, no barrier on the per-symbol
 // path), run the countdown (`left` was loaded from `la` before the search), rebuild the table when it expires
+template <bool CNT>
 __device__ __forceinline__ void fx_update(Ent& e, int t, uint32_t la, uint32_t left, int idx) {
     const uint32_t ca = e.sb + S_CNT + (uint32_t)idx * 2u;
     sts16(ca, lds16(ca) + 16);
     sts32(la, left - 1);
-    rdec_count(e);
+    rdec_count<CNT>(e);
     if (left == 1) {
         __syncwarp();
 #ifdef SCPR_PROF
@@ -351,6 +382,7 @@ __device__ __forceinline__ void fx_update(Ent& e, int t, uint32_t la, uint32_t l
 }
 
 // run length through ntab[ptype] (decodeN, screencap.h:346-359, 361)
+template <bool CNT = true>
 __device__ __forceinline__ int dec_n(Ent& e, int ptype) {
     PROF_T0
     const uint32_t la = e.sb + S_LEFT + (uint32_t)ptype * 4u;
@@ -359,12 +391,12 @@ __device__ __forceinline__ int dec_n(Ent& e, int ptype) {
     const uint32_t en = lds32(e.sb + S_LUT32 + ((uint32_t)ptype << 14) + (v << 2));
     const int sym = (int)(en >> 24);
     rdec_advance(e, v - (en & 0xFFFu), (en >> 12) & 0xFFFu);
-    fx_update(e, ptype, la, left, (ptype << 8) + sym);
+    fx_update<CNT>(e, ptype, la, left, (ptype << 8) + sym);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return sym;
 }
 // decodeF for every other table: NSYM symbols, table t at fc[off]
-template <int NSYM>
+template <int NSYM, bool CNT = true>
 __device__ __forceinline__ int dec_tab(Ent& e, int t, int off) {
     PROF_T0
     const uint32_t la = e.sb + S_LEFT + (uint32_t)t * 4u;
@@ -385,13 +417,14 @@ __device__ __forceinline__ int dec_tab(Ent& e, int t, int off) {
     const uint32_t xk = f * (e.x >> PROB_BITS) + d;
     rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, j));
     const int sym = (int)base + j;
-    fx_update(e, t, la, left, off + sym);
+    fx_update<CNT>(e, t, la, left, off + sym);
     PROF_ADD(c_fixed) PROF_CNT(n_fixed)
     return sym;
 }
 template <int NSYM, int T>
 __device__ __forceinline__ int dec_fxc(Ent& e) { return dec_tab<NSYM>(e, T, fx_off(T)); }
-__device__ __forceinline__ int dec_ptype(Ent& e, int last) { return dec_tab<6>(e, 15 + last, 3144 + 8 * last); }  // decodeP
+template <bool CNT = true>
+__device__ __forceinline__ int dec_ptype(Ent& e, int last) { return dec_tab<6, CNT>(e, 15 + last, 3144 + 8 * last); }  // decodeP
 __device__ __forceinline__ int dec_bool(Ent& e) {  // decodeBool
     const uint32_t v = e.x & (PROB_SCALE - 1);
     const int flag = v >= PROB_SCALE / 2;
@@ -633,6 +666,7 @@ __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int k
     }
     return c;
 }
+template <bool CNT>
 __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screencap.h:318-333
     PROF_T0
     const uint32_t h = cache_slot(id);
@@ -644,7 +678,7 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         const int kind = (int)lds8(e.sb + S_KMAP + id);
         if (kind >= 6) {
             c = dec_color_flat(e, reinterpret_cast<uint8_t*>(&e.m->color[id]), id, kind);
-            rdec_count(e);
+            rdec_count<CNT>(e);
             PROF_ADD(c_flat) PROF_CNT(n_flat) PROF_ADD(c_color) PROF_CNT(n_color)
             return c;
         }
@@ -653,7 +687,7 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
             rd_skip(e, 8);
             if (e.lane == 0) cc_update_raw(e.m->color[id], c, e.f0);
             color_refresh(e.m, e.sb, e.lane, id);
-            rdec_count(e);
+            rdec_count<CNT>(e);
             PROF_ADD(c_raw) PROF_CNT(n_raw) PROF_ADD(c_color) PROF_CNT(n_color)
             return c;
         }
@@ -663,25 +697,42 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         PROF_CNT(n_miss)
     }
     c = dec_color_small(e, id, h, ent, hd);
-    rdec_count(e);
+    rdec_count<CNT>(e);
     PROF_ADD(c_small) PROF_CNT(n_small) PROF_ADD(c_color) PROF_CNT(n_color)
     return c;
 }
+// The context of a colour byte is made of the two bytes coded before it, quantised to 6 bits: for byte 0 those
+// are bytes 2 and 1 of the pixel before the run (MAKECX1, screencap.h:36; :371-372, 488-493, 1417-1419).
+template <bool CNT = true>
 __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
     uint32_t px = 0;
+    uint32_t cx = (e.lastpx >> 18) & 63u, cx1 = (e.lastpx >> 4) & 0xFC0u;
 #pragma unroll 1
     for (int ch = 0; ch < 3; ch++) {  // one copy of the colour decoder in the instruction stream
-        const uint32_t v = (uint32_t)dec_color(e, ch * 4096 + (int)(e.cx + e.cx1)) & 255u;
-        e.cx1 = (e.cx << 6) & 0xFC0;
-        e.cx = v >> 2;
+        const uint32_t v = (uint32_t)dec_color<CNT>(e, ch * 4096 + (int)(cx + cx1)) & 255u;
+        cx1 = cx << 6;
+        cx = v >> 2;
         px |= v << (8 * ch);
     }
+    e.lastpx = px;
     return px;
 }
-__device__ __forceinline__ void set_cx_from(Ent& e, uint32_t px) {  // screencap.cpp:488-493, 1417-1419
-    e.cx = ((px >> 8) & 255) >> 2;
-    e.cx1 = (e.cx << 6) & 0xFC0;
-    e.cx = ((px >> 16) & 255) >> 2;
+
+// the symbols of one pixel run: type, colour of a literal, length (screencap.cpp:478-486, 1400-1412).  At most five
+// symbols: when the rANS block cannot end within them they are counted with one subtraction.
+__device__ __forceinline__ int dec_run(Ent& e, int& ptype, uint32_t& c) {
+    int n;
+    if (e.nleft > 8) {
+        ptype = dec_ptype<false>(e, ptype);
+        if (!ptype) c = dec_rgb<false>(e);
+        n = dec_n<false>(e, ptype);
+        e.nleft -= ptype ? 2 : 5;
+    } else {
+        ptype = dec_ptype<true>(e, ptype);
+        if (!ptype) c = dec_rgb<true>(e);
+        n = dec_n<true>(e, ptype);
+    }
+    return n;
 }
 
 __device__ __forceinline__ uint32_t grad_px(uint32_t l, uint32_t t, uint32_t tl) {  // type 4, truncated to bytes
@@ -757,9 +808,7 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     __syncwarp();
     while (p.y < Y) {
         uint32_t c = lastv;  // type 1: the previous pixel in raster order, whatever the row
-        ptype = dec_ptype(e, ptype);
-        if (!ptype) c = dec_rgb(e);
-        const int n = dec_n(e, ptype);
+        const int n = dec_run(e, ptype, c);
         if (n <= 0) return;
         PROF_T0
         if (ptype == 0 || ptype == 1) {
@@ -796,15 +845,120 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
             const IPos l = ipos_prev(p, X);
             lastv = l.y < Y ? load_px(frame, g, l.x, l.y) : 0u;
         }
-        set_cx_from(e, lastv);
+        e.lastpx = lastv;
         PROF_ADD(c_ifill)
     }
+}
+
+// ---- helper warps: motion-vector copies -------------------------------------------------------------------
+// A motion-vector block is a pure gather from the previous frame (screencap.cpp:1333-1368): nothing the entropy
+// walk needs comes out of it, but done by the chain warp it costs three dependent memory round trips per block,
+// and scrolling content produces thousands of such blocks per frame.  The chain warp therefore only decodes the
+// block's symbols and posts a command; the other warps of the CTA execute the copies concurrently.
+//   * All commands of a frame read frames before it and write that frame: they are independent of each other.
+//   * The chain warp waits for the queue to drain (a) before the first map update of every frame (a copy resolves
+//     its sources "as of the previous frame", which the two-deep map can only answer while that frame is the
+//     newest) and (b) before it reads pixels itself (tile loads of pixel-coded blocks).
+// Command (uint4): x = bi | frame << 16;  y = sub-rect inside the block, x1 | y1 << 4 | (x2-1) << 8 | (y2-1) << 12;
+// z = (mx & 0xFFFF) | my << 16.  S_SYNC: head (commands published), next (commands taken), done, quit.
+__device__ __forceinline__ uint32_t ldv_shared(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stv_shared(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t a, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
+    return r;
+}
+
+template <bool SM>
+__device__ void mv_copy(const DecWork& w, const BlockMap<SM>& map, int f, int bi, uint32_t rect, int mx, int my, int lane) {
+    const Geo& g = w.g;
+    const int by = bi / g.nbx, bx = bi - by * g.nbx;
+    const int bx0 = bx * 16, by0 = by * 16;
+    const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
+    const int x1 = bx0 + (int)(rect & 15u), y1 = by0 + (int)((rect >> 4) & 15u);
+    const int x2 = bx0 + (int)((rect >> 8) & 15u) + 1, y2 = by0 + (int)((rect >> 12) & 15u) + 1;
+    uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
+    const int gx = min(max(x1 + mx, 0), g.X - 1), gy = min(max(y1 + my, 0), g.Y - 1);  // corrupt input guard
+    const int cbx = gx >> 4, cby = gy >> 4;
+    PixSrc sq[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {  // the source rectangle spans at most 2 x 2 blocks of the previous frame
+        const int qx = min(cbx + (q & 1), g.nbx - 1), qy = min(cby + (q >> 1), g.nby - 1);
+        sq[q] = resolve_src(w, src_before(map.get(qy * g.nbx + qx), f));
+    }
+    const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
+    uint32_t px[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
+        const int x = bx0 + xx, y = by0 + yy;
+        px[u] = 0;
+        if (xx < bw && yy < bh) {
+            if (x >= x1 && x < x2 && y >= y1 && y < y2) {
+                const int sx = min(max(x + mx, 0), g.X - 1), sy = min(max(y + my, 0), g.Y - 1);
+                const int q = ((sx >> 4) > cbx ? 1 : 0) + ((sy >> 4) > cby ? 2 : 0);
+                px[u] = src_px(q == 0 ? sq[0] : q == 1 ? sq[1] : q == 2 ? sq[2] : sq[3], g, sx, sy);
+            } else
+                px[u] = src_px(sP, g, x, y);  // the rest of a partial block: the previous frame, same place
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
+        if (xx < bw && yy < bh) store_px(frame, g, bx0 + xx, by0 + yy, px[u]);
+    }
+    if (lane == 0) w.upd[(size_t)f * g.nb + bi] = 1;
+}
+
+template <bool SM>
+__device__ void helper_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t sb, int lane) {
+    const uint32_t sy = sb + S_SYNC;
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atom_add_shared(sy + 4, 1u);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        for (;;) {
+            if ((int)(ldv_shared(sy) - idx) > 0) break;
+            if (ldv_shared(sy + 12)) return;  // quit is only raised after a drain: nothing published is left behind
+            __nanosleep(200);
+        }
+        __threadfence_block();
+        const uint4 cmd = lds128(sb + S_RING + 16u * (idx % RING));
+        mv_copy<SM>(w, map, (int)(cmd.x >> 16), (int)(cmd.x & 0xFFFFu), cmd.y, (int)(int16_t)(cmd.z & 0xFFFFu), (int)(int16_t)(cmd.z >> 16), lane);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atom_add_shared(sy + 8, 1u);
+    }
+}
+// chain warp side.  Completion may be out of order by at most the number of helper warps, so a ring slot is
+// reused only while fewer than RING - DEC_WARPS commands are outstanding.
+__device__ __forceinline__ void cmd_push(Ent& e, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t sy = e.sb + S_SYNC;
+    while (e.head - ldv_shared(sy + 8) > (uint32_t)(RING - DEC_WARPS)) __nanosleep(100);
+    sts128(e.sb + S_RING + 16u * (e.head % RING), x, y, z, 0u);
+    __threadfence_block();
+    e.head++;
+    stv_shared(sy, e.head);
+}
+__device__ __forceinline__ void cmd_drain(Ent& e) {
+    const uint32_t sy = e.sb + S_SYNC;
+    if (ldv_shared(sy + 8) != e.head) {
+        PROF_T0
+        while (ldv_shared(sy + 8) != e.head) __nanosleep(100);
+        PROF_ADD(c_drain)
+    }
+    __threadfence_block();
 }
 
 // ---- P frame (DecompressP, screencap.cpp:1275-1432) ------------------------------------------------
 __device__ __forceinline__ uint32_t tile_at(uint32_t tb, int ty, int tx) { return lds32(tb + (uint32_t)(ty * 17 + tx) * 4u); }
 
-__device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame, int f, int lane) {
+template <bool SM>
+__device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint8_t* frame, int f, int lane) {
     const Geo& g = w.g;
     const uint32_t tb = e.sb + S_TILE, btsb = e.sb + S_BTS;
 #ifdef SCPR_PROF
@@ -827,7 +981,8 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
 #ifdef SCPR_PROF
     e.c_hdr += clock64() - thdr__;
 #endif
-    e.cx = e.cx1 = 0;
+    cmd_drain(e);  // the copies of the previous frame are complete before this frame touches the map
+    e.lastpx = 0;  // cx = cx1 = 0, screencap.cpp:1319
     int lastmx = 0, lastmy = 0;
     uint8_t* upd = w.upd + (size_t)f * g.nb;
     // visit changed blocks only: 32 block types per step, ballot, iterate the set bits
@@ -844,9 +999,7 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
         PROF_CNT(n_blocks)
         if ((bt - 1) & 2) {
-            // ---- motion-vector block: a pure gather from the previous frame, written straight to the
-            // frame (no tile, no neighbours): sub-rect from prev at (x+mx, y+my), the rest of a partial
-            // block from prev at the same place (screencap.cpp:1333-1368)
+            // ---- motion-vector block: decode its symbols, post the copy (screencap.cpp:1333-1368)
             PROF_T0
             if ((bt - 1) & 1) {
                 x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
@@ -864,45 +1017,10 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                 my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
             }
             lastmx = mx; lastmy = my;
-            const int gx = min(max(x1 + mx, 0), g.X - 1), gy = min(max(y1 + my, 0), g.Y - 1);  // corrupt input guard
-            const int cbx = gx >> 4, cby = gy >> 4;
-            PixSrc sq[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {  // the source rectangle spans at most 2 x 2 blocks of the previous frame
-                const int qx = min(cbx + (q & 1), g.nbx - 1), qy = min(cby + (q >> 1), g.nby - 1);
-                const int b = qy * g.nbx + qx;
-                sq[q] = resolve_src(w, cc.stamp[b] == f ? cc.src_prev[b] : cc.src_cur[b]);
-            }
-            const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
-            uint32_t px[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {  // all loads first (a source block may be this very block)
-                const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
-                const int x = bx0 + xx, y = by0 + yy;
-                px[u] = 0;
-                if (xx < bw && yy < bh) {
-                    if (x >= x1 && x < x2 && y >= y1 && y < y2) {
-                        const int sx = min(max(x + mx, 0), g.X - 1), sy = min(max(y + my, 0), g.Y - 1);
-                        const int q = ((sx >> 4) > cbx ? 1 : 0) + ((sy >> 4) > cby ? 2 : 0);
-                        px[u] = src_px(q == 0 ? sq[0] : q == 1 ? sq[1] : q == 2 ? sq[2] : sq[3], g, sx, sy);
-                    } else
-                        px[u] = src_px(sP, g, x, y);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
-                if (xx < bw && yy < bh) store_px(frame, g, bx0 + xx, by0 + yy, px[u]);
-            }
-            if (lane == 0) {
-                if (cc.stamp[bi] != f) {
-                    cc.src_prev[bi] = cc.src_cur[bi];
-                    cc.stamp[bi] = f;
-                }
-                cc.src_cur[bi] = f;
-                upd[bi] = 1;
-            }
-            __syncwarp();
+            map.write(bi, (uint32_t)f);
+            cmd_push(e, (uint32_t)bi | ((uint32_t)f << 16),
+                     (uint32_t)(x1 - bx0) | ((uint32_t)(y1 - by0) << 4) | ((uint32_t)(x2 - 1 - bx0) << 8) | ((uint32_t)(y2 - 1 - by0) << 12),
+                     ((uint32_t)mx & 0xFFFFu) | ((uint32_t)my << 16));
             PROF_ADD(c_mv)
             continue;
         }
@@ -913,11 +1031,12 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
         // they are in flight.
         uint32_t tv[10];
         { PROF_T0
+            cmd_drain(e);  // neighbours may be motion-vector blocks of this frame
             const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
-            const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? cc.src_cur[bA] : -1);
-            const PixSrc sT = resolve_src(w, by > 0 ? cc.src_cur[bT] : -1);
-            const PixSrc sL = resolve_src(w, bx > 0 ? cc.src_cur[bL] : -1);
-            const PixSrc sP = resolve_src(w, cc.stamp[bi] == f ? cc.src_prev[bi] : cc.src_cur[bi]);
+            const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? src_now(map.get(bA)) : SRC_PREV0);
+            const PixSrc sT = resolve_src(w, by > 0 ? src_now(map.get(bT)) : SRC_PREV0);
+            const PixSrc sL = resolve_src(w, bx > 0 ? src_now(map.get(bL)) : SRC_PREV0);
+            const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
 #pragma unroll
             for (int u = 0; u < 10; u++) {
                 const int p = lane + 32 * u;
@@ -955,46 +1074,79 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
             int pos = 0, ptype = 0;
             const int npx = sw * sh;
             const int ox = 1 + x1 - bx0, oy = 1 + y1 - by0;
+            int xx0 = 0, yy0 = 0;                                   // the run's first pixel in the sub-rect ...
+            uint32_t ca = tb + (uint32_t)(oy * 17 + ox) * 4u;       // ... and its tile address
             while (pos < npx) {
                 uint32_t c = 0;
-                ptype = dec_ptype(e, ptype);
-                if (!ptype) c = dec_rgb(e);
-                int n = dec_n(e, ptype);
+                int n = dec_run(e, ptype, c);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
-                const int yy0 = (int)(((uint32_t)pos * swinv) >> 16), xx0 = pos - yy0 * sw;
-                if (ptype == 4) {  // gradient chains through the left pixel: serial
-                    if (lane == 0) {
-                        int xx = xx0, yy = yy0;
-                        for (int i = 0; i < n; i++) {
-                            const uint32_t a = tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u;
-                            sts32(a, grad_px(lds32(a - 4), lds32(a - 68), lds32(a - 72)));
-                            if (++xx == sw) {
-                                xx = 0;
-                                yy++;
+                const int xe = xx0 + n;
+                uint32_t vlast;
+                if (xe <= sw && ptype != 4) {
+                    // the run stays in its row (the common case; at most 16 pixels): every source is one fixed step
+                    // away -- left: the pixel before the run; top: one tile row up; top-left: one row up, one left;
+                    // type 3 keeps the previous frame's pixel that is already in the tile
+                    const uint32_t al = ca + 4u * (uint32_t)(n - 1);
+                    const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
+                    uint32_t v = c;
+                    vlast = c;
+                    if (ptype == 1) {
+                        v = vlast = lds32(ca - 4u);
+                    } else if (ptype == 2) {
+                        v = lds32(a - 68u);
+                        vlast = lds32(al - 68u);
+                    } else if (ptype == 5) {
+                        v = lds32(a - 72u);
+                        vlast = lds32(al - 72u);
+                    } else if (ptype == 3) {
+                        vlast = lds32(al);
+                    }
+                    if (ptype != 3 && lane < n) sts32(a, v);
+                    __syncwarp();
+                } else {
+                    if (ptype == 4) {  // gradient chains through the left pixel: serial
+                        if (lane == 0) {
+                            int xx = xx0, yy = yy0;
+                            for (int i = 0; i < n; i++) {
+                                const uint32_t a = tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u;
+                                sts32(a, grad_px(lds32(a - 4), lds32(a - 68), lds32(a - 72)));
+                                if (++xx == sw) {
+                                    xx = 0;
+                                    yy++;
+                                }
                             }
                         }
-                    }
-                } else if (ptype != 3) {
-                    for (int i = lane; i < n; i += 32) {
-                        const int idx = pos + i;
-                        const int yy = (int)(((uint32_t)idx * swinv) >> 16), xx = idx - yy * sw;
-                        uint32_t v = c;
-                        if (ptype == 1) {  // left: the pixel before the row segment the pixel lies in
-                            v = yy == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + yy, ox - 1);
-                        } else if (ptype == 2) {  // top: the pixel above the run's first row in this column
-                            v = tile_at(tb, oy + (xx >= xx0 ? yy0 : yy0 + 1) - 1, ox + xx);
-                        } else if (ptype == 5) {  // top-left: walk the diagonal until it leaves the run or the sub-rect
-                            const int k = min((int)(((uint32_t)i * sw1inv) >> 16) + 1, xx + 1);
-                            v = tile_at(tb, oy + yy - k, ox + xx - k);
+                    } else if (ptype != 3) {
+                        for (int i = lane; i < n; i += 32) {
+                            const int idx = pos + i;
+                            const int yy = (int)(((uint32_t)idx * swinv) >> 16), xx = idx - yy * sw;
+                            uint32_t v = c;
+                            if (ptype == 1) {  // left: the pixel before the row segment the pixel lies in
+                                v = yy == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + yy, ox - 1);
+                            } else if (ptype == 2) {  // top: the pixel above the run's first row in this column
+                                v = tile_at(tb, oy + (xx >= xx0 ? yy0 : yy0 + 1) - 1, ox + xx);
+                            } else if (ptype == 5) {  // top-left: walk the diagonal until it leaves the run or the sub-rect
+                                const int k = min((int)(((uint32_t)i * sw1inv) >> 16) + 1, xx + 1);
+                                v = tile_at(tb, oy + yy - k, ox + xx - k);
+                            }
+                            sts32(tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u, v);
                         }
-                        sts32(tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u, v);
                     }
+                    __syncwarp();
+                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                    vlast = tile_at(tb, oy + ly, ox + li - ly * sw);
                 }
-                __syncwarp();
+                e.lastpx = vlast;
                 pos += n;
-                const int li = pos - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
-                set_cx_from(e, tile_at(tb, oy + ly, ox + li - ly * sw));
+                xx0 = xe;
+                ca += 4u * (uint32_t)n;
+                if (xx0 >= sw) {  // next row(s)
+                    const int q = (int)(((uint32_t)xx0 * swinv) >> 16);
+                    xx0 -= q * sw;
+                    yy0 += q;
+                    ca = tb + (uint32_t)((oy + yy0) * 17 + ox + xx0) * 4u;
+                }
             }
             PROF_ADD(c_runs)
         }
@@ -1009,43 +1161,40 @@ __device__ void decode_p(const DecWork& w, ChainCtx& cc, Ent& e, uint8_t* frame,
                 store_px(frame, g, bx0 + xx, by0 + yy, tile_at(tb, 1 + yy, 1 + xx));
             }
         }
-        if (lane == 0) {
-            if (cc.stamp[bi] != f) {
-                cc.src_prev[bi] = cc.src_cur[bi];
-                cc.stamp[bi] = f;
-            }
-            cc.src_cur[bi] = f;
-            upd[bi] = 1;
-        }
+        map.write(bi, (uint32_t)f);
+        if (lane == 0) upd[bi] = 1;
         __syncwarp();
         PROF_ADD(c_blkwr) }
       }
     }
 }
 
-// one warp per chain
-__global__ void __launch_bounds__(32, 1) k_dec_chain(DecWork w) {
+// One CTA per chain: warp 0 walks the chain, the other warps copy motion-vector blocks (warp 4 shares warp 0's
+// scheduler and leaves at once).
+template <bool SM>
+__global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     extern __shared__ __align__(16) uint8_t s_mem[];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_mem);
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));  // keep the base in a register: otherwise it is rematerialised (S2R) at every use
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const DecChain ch = w.chains[blockIdx.x];
     const Geo& g = w.g;
-    ChainCtx cc;
-    cc.w = &w;
-    cc.src_cur = w.src_cur + (size_t)blockIdx.x * g.nb;
-    cc.src_prev = w.src_prev + (size_t)blockIdx.x * g.nb;
-    cc.stamp = w.stamp + (size_t)blockIdx.x * g.nb;
-    for (int i = lane; i < g.nb; i += 32) {
-        cc.src_cur[i] = -1;
-        cc.src_prev[i] = -1;
-        cc.stamp[i] = -1;
+    BlockMap<SM> map;
+    map.sbase = sb + s_map_off(g.nb);
+    map.g = SM ? nullptr : w.gmap + (size_t)blockIdx.x * g.nb;
+    if (threadIdx.x < 4) sts32(sb + S_SYNC + 4u * threadIdx.x, 0u);
+    for (int i = threadIdx.x; i < g.nb; i += 32 * DEC_WARPS) map.set(i, 0xFFFFFFFFu);  // everything lives in prev0
+    __threadfence_block();
+    __syncthreads();
+    if (warp != 0) {
+        if (warp != 4) helper_loop<SM>(w, map, sb, lane);
+        return;
     }
-    __syncwarp();
     Ent e;
     e.m = reinterpret_cast<ModelState*>(w.states + (size_t)ch.state * sizeof(ModelState));
     e.f0 = w.f0;
-    e.cx = e.cx1 = 0;
+    e.lastpx = 0;
+    e.head = 0;
     e.nleft = RANS_BLOCK;
     e.x = 0;
     e.w0 = e.w1 = e.k8 = 0;
@@ -1071,7 +1220,6 @@ __global__ void __launch_bounds__(32, 1) k_dec_chain(DecWork w) {
     for (int f = ch.first; f < ch.first + ch.count; f++) {
         const DecFrame df = w.frames[f];
         uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
-        cc.f = f;
         if (df.kind == DK_PSAME) continue;  // every block keeps its source (memcpy(pDst, prev), screencap.cpp:1288-1291)
         if (df.kind == DK_FLAT || df.kind == DK_I) {
             if (df.kind == DK_I || df.renew) {  // RenewI
@@ -1089,16 +1237,14 @@ __global__ void __launch_bounds__(32, 1) k_dec_chain(DecWork w) {
                 __syncwarp();
                 for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
             }
-            for (int i = lane; i < g.nb; i += 32) {  // the whole frame is new
-                cc.src_prev[i] = cc.src_cur[i];
-                cc.stamp[i] = f;
-                cc.src_cur[i] = f;
-            }
+            cmd_drain(e);
+            const uint32_t code = (uint32_t)f | (df.kind == DK_FLAT ? SRC_FLAT : 0u);
+            for (int i = lane; i < g.nb; i += 32) map.write(i, code);  // the whole frame is new
             __syncwarp();
             if (df.kind == DK_I) {
                 rd_seek(e, w.stream + df.src_off + 1);
                 e.nleft = RANS_BLOCK;
-                e.cx = e.cx1 = 0;
+                e.lastpx = 0;
                 rdec_init(e);
                 decode_i(w, e, frame, lane);
             }
@@ -1107,16 +1253,18 @@ __global__ void __launch_bounds__(32, 1) k_dec_chain(DecWork w) {
         rd_seek(e, w.stream + df.src_off + 1);
         e.nleft = RANS_BLOCK;
         rdec_init(e);
-        decode_p(w, cc, e, frame, f, lane);
+        decode_p<SM>(w, map, e, frame, f, lane);
         __threadfence_block();
     }
+    cmd_drain(e);
+    stv_shared(sb + S_SYNC + 12, 1u);  // helpers leave
 #ifdef SCPR_PROF
     if (lane == 0)
         printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc; %lld serial, %lld rescales) | "
-               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld\n",
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f\n",
                (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
-               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw);
+               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6);
 #endif
     // leave the cached contexts, the fixed tables and the kinds behind for the next call
     __syncwarp();
@@ -1228,7 +1376,7 @@ static int ensure_dec_states(scpr_codec* c, int n) {
 }
 
 // n frames, bitstreams on the host, decoded frames to device memory `d_out` (pitch bytes per row)
-static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
+static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
                         int pitch) {
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->st;
@@ -1294,8 +1442,16 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     // ---- device buffers ---------------------------------------------------------------------------
     TRY(c->dec_stream.ensure((size_t)off + 64));
     TRY(c->dec_desc.ensure((size_t)n * sizeof(DecFrame) + (size_t)n_chains * sizeof(DecChain)));
-    const size_t map_bytes = (size_t)n_chains * g.nb * 4;
-    TRY(c->dec_ws.ensure(3 * map_bytes + (size_t)n * g.nb * 3 + 64));
+    // the block-source map sits in shared memory when it fits next to the tables, else in global memory
+    const size_t smem_sm = (size_t)s_map_off(g.nb) + (size_t)g.nb * 4 + 16, smem_gm = (size_t)s_map_off(g.nb) + 16;
+    const bool map_shared = smem_sm <= 227 * 1024;
+    const size_t smem = map_shared ? smem_sm : smem_gm;
+    if (smem > 227 * 1024) {
+        set_error("frame has too many blocks for the decoder's shared-memory block map");
+        return SCPR_E_PARAM;
+    }
+    const size_t map_bytes = map_shared ? 0 : (size_t)n_chains * g.nb * 4;
+    TRY(c->dec_ws.ensure(map_bytes + (size_t)n * g.nb * 3 + 64));
     if (c->dec_prev_pitch != pitch) {  // previous frame is kept in output format
         TRY(c->dec_prev.ensure(g.frame_bytes));
         if (c->dec_prev_pitch == 0) CK(cudaMemsetAsync(c->dec_prev.p, 0, g.frame_bytes, st));
@@ -1321,21 +1477,19 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.out = d_out;
     w.prev0 = (const uint8_t*)c->dec_prev.p;
     uint8_t* ws = (uint8_t*)c->dec_ws.p;
-    w.src_cur = (int*)ws;
-    w.src_prev = (int*)(ws + map_bytes);
-    w.stamp = (int*)(ws + 2 * map_bytes);
-    w.upd = ws + 3 * map_bytes;
-    w.fill_src = (int16_t*)(ws + 3 * map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
+    w.gmap = (uint32_t*)ws;
+    w.upd = ws + map_bytes;
+    w.fill_src = (int16_t*)(ws + map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
     w.n = n;
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
-    const size_t smem = (size_t)S_BTS + (size_t)g.nb + 16;
-    if (smem > 227 * 1024) {
-        set_error("frame has too many blocks for the decoder's shared-memory block map");
-        return SCPR_E_PARAM;
-    }
-    CK(cudaFuncSetAttribute(k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageTimer tm(st);
-    k_dec_chain<<<n_chains, 32, smem, st>>>(w);
+    if (map_shared) {
+        CK(cudaFuncSetAttribute(k_dec_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dec_chain<true><<<n_chains, 32 * DEC_WARPS, smem, st>>>(w);
+    } else {
+        CK(cudaFuncSetAttribute(k_dec_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dec_chain<false><<<n_chains, 32 * DEC_WARPS, smem, st>>>(w);
+    }
     tm.mark("chain");
     k_dec_sources<<<(g.nb + 127) / 128, 128, 0, st>>>(w);
     const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
@@ -1346,6 +1500,19 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     CK(cudaMemcpyAsync(c->dec_prev.p, d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    return 1;
+}
+
+// any number of frames: launches of at most DEC_MAX_FRAMES frames (the open chain carries over, as between calls)
+static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
+                        int pitch) {
+    const size_t frame_bytes = (size_t)pitch * c->g.Y;
+    for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
+        const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
+        const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, d_out + (size_t)f0 * frame_bytes, pitch);
+        if (r != 1) return r;
+        for (int f = f0; f < f0 + m; f++) stream += sizes[f];
+    }
     return 1;
 }
 

@@ -9,7 +9,8 @@
 // does not depend on x is taken off that chain: the warp stages tiles of 1024 intervals in shared
 // memory with coalesced loads and computes, per interval, the exact 32-bit reciprocal of its
 // frequency (Alverson-style: m = ceil(2^(31+s)/f), s = ceil(log2 f); x/f == mulhi(x, m) >> (s-1) for
-// x < 2^31), so the serial lane does compare / mul-hi / multiply-add per symbol and no division.
+// x < 2^31), so the serial lane does compare / mul-hi / multiply-add per symbol and no division, and its
+// renormalisation is branch-free.
 // Output bytes are produced backwards into a shared-memory tile and flushed with coalesced stores.
 #include "codec.h"
 
@@ -19,12 +20,10 @@ constexpr int RTILE = 1024;
 
 __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__ intervals, RansBlk* __restrict__ blks,
                                                     uint8_t* __restrict__ scratch) {
-    // per interval, everything the serial lane needs that does not depend on the state:
-    //   s_a = reciprocal m;  s_b = x_max = freq << 19 (0 marks a raw byte);
-    //   s_c = (4096 - freq) << 18 | shift << 13 | bias, bias = start (+ 4095 for freq 1, see below)
-    __shared__ uint32_t s_a[RTILE];
-    __shared__ uint32_t s_b[RTILE];
-    __shared__ uint32_t s_c[RTILE];
+    // per interval, everything the serial lane needs that does not depend on the state, as one 64-bit operand:
+    //   .x = reciprocal m;  .y = (4096 - freq) << 18 | shift << 13 | bias, bias = start (+ 4095 for freq 1, see below).
+    //   x_max = freq << 19 is recovered from .y; freq 0 (raw byte, .y = 4096 << 18 | byte) gives x_max = 0.
+    __shared__ uint2 s_op[RTILE];
     __shared__ uint8_t s_out[2 * RTILE + 8];
     const int lane = threadIdx.x;
     RansBlk& blk = blks[blockIdx.x];
@@ -49,31 +48,34 @@ __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__
                 m = 0xFFFFFFFFu;
                 bias = start + 4095u;
             }
-            s_a[i] = m;
-            s_b[i] = f << 19;
-            s_c[i] = f ? (((1u << PROB_BITS) - f) << 18) | (sh << 13) | bias : start;
+            s_op[i] = make_uint2(m, (((1u << PROB_BITS) - f) << 18) | (f ? (sh << 13) | bias : start));
         }
         __syncwarp();
         int nout = 0;
         if (lane == 0) {
             int pi = (int)sizeof(s_out);  // write index into s_out, moves down
-            uint32_t a = s_a[cnt - 1], b = s_b[cnt - 1], c = s_c[cnt - 1];
+            uint2 op = s_op[cnt - 1];
+#pragma unroll 4
             for (int i = cnt - 1; i >= 0; i--) {
-                // the next interval's operands are fetched before this state update (they do not depend on x)
-                const int in = i > 0 ? i - 1 : 0;
-                const uint32_t an = s_a[in], bn = s_b[in], cn = s_c[in];
-                if (b) {  // RansEncPut (rans_byte.h:76-84) with RansEncRenorm (:59-71)
-                    while (x >= b) {
-                        s_out[--pi] = (uint8_t)x;
-                        x >>= 8;
-                    }
-                    const uint32_t q = __umulhi(x, a) >> ((c >> 13) & 31);  // x / freq
-                    x = x + (c & 0x1FFFu) + q * (c >> 18);                  // (q << 12) + (x - q*freq) + start
+                // the next interval's operand is fetched before this state update (it does not depend on x)
+                const uint2 nx = s_op[i > 0 ? i - 1 : 0];
+                const uint32_t cmpl = op.y >> 18;
+                const uint32_t xmax = ((1u << PROB_BITS) - cmpl) << 19;
+                if (xmax) {
+                    // RansEncRenorm (rans_byte.h:59-71) without branches: the state is below 2^31 and x_max at least
+                    // 2^19, so at most two bytes leave; both are stored, the cursor moves by the number that count
+                    const uint32_t x8 = x >> 8;
+                    const int r1 = x >= xmax, r2 = x8 >= xmax;
+                    s_out[pi - 1] = (uint8_t)x;
+                    s_out[pi - 2] = (uint8_t)x8;
+                    pi -= r1 + r2;
+                    x = r2 ? (x >> 16) : (r1 ? x8 : x);
+                    // RansEncPut (rans_byte.h:76-84): (q << 12) + (x - q * freq) + start
+                    const uint32_t q = __umulhi(x, op.x) >> ((op.y >> 13) & 31);
+                    x = x + (op.y & 0x1FFFu) + q * cmpl;
                 } else
-                    s_out[--pi] = (uint8_t)c;  // raw byte, ransmt.h:127-128
-                a = an;
-                b = bn;
-                c = cn;
+                    s_out[--pi] = (uint8_t)op.y;  // raw byte, ransmt.h:127-128
+                op = nx;
             }
             if (lo == 0) {  // RansEncFlush, rans_byte.h:87-100
                 pi -= 4;
