@@ -176,7 +176,7 @@ def run_cuda(args):
         c.Init(CodecParameters(W, H, 32))
         c.set_stream(stream.cuda_stream)
     enc.reserve_clip_output(64 << 20)
-    stage = {"enc_ms": 0.0, "dec_ms": 0.0}
+    stage = {"enc_ms": 0.0, "dec_ms": 0.0, "e2e_enc_s": 0.0, "e2e_dec_s": 0.0}
 
     def fresh():
         # a new clip: Deinit + Init semantics (prev, models, frame counters), device workspaces are kept
@@ -198,9 +198,14 @@ def run_cuda(args):
 
     def step_host():
         fresh()
+        t0 = time.perf_counter()
         s, sizes, fts = enc.CompressClip(h_in.numpy(), keys)
+        t1 = time.perf_counter()
         out = dec._lib.scpr_decompress_clip(dec._h, s.ctypes.data, sizes.ctypes.data, fts.ctypes.data, frames, h_out.data_ptr(), W * 4)
+        t2 = time.perf_counter()
         assert out == 1, out
+        stage["e2e_enc_s"] += t1 - t0  # both calls are synchronous: host clocks bracket them exactly
+        stage["e2e_dec_s"] += t2 - t1
         return s, sizes
 
     def barrier():
@@ -245,7 +250,10 @@ def run_cuda(args):
     step_host()
     torch.cuda.synchronize()
     assert np.array_equal(h_out.numpy(), h_in.numpy()), "decode(encode(x)) != x on the host-buffer path"
+    stage["e2e_enc_s"] = stage["e2e_dec_s"] = 0.0
     ms_e2e, (s2, sizes2) = timed(step_host, args.steps)
+    e2e_enc_fps = frames * args.steps / stage["e2e_enc_s"]
+    e2e_dec_fps = frames * args.steps / stage["e2e_dec_s"]
     e2e = world * frames * args.steps / (ms_e2e / 1e3)
     stream_bytes = int(sizes.sum())
 
@@ -320,7 +328,9 @@ def run_cuda(args):
                                "bit-exact round trip asserted", "l2": "inputs (5 GB/step) exceed L2; no flush needed",
                    "gops_per_clip": int(keys.sum()), "stream_bytes_per_clip": stream_bytes},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
-                "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps,
+                "encode_fps": e2e_enc_fps, "decode_fps": e2e_dec_fps,
+                "note": "this rank's host-buffer calls: pinned frames in -> bitstream out, bitstream in -> pinned frames out"},
         "gpu_launches": launches,
         "encode_fps": enc_fps, "decode_fps": dec_fps,
         "multi_clip": multi,
@@ -332,7 +342,8 @@ def run_cuda(args):
                      "note": "the HBM-bound stage (delta / changed-block detection); the step itself is dominated by the "
                              "decoder's serial GOP chain, see dominant_kernel"},
         "dominant_kernel": {"kernel": "k_dec_chain", "share_of_step": (stage["dec_ms"] / args.steps) / (ms / args.steps),
-                            "bound": "serial dependency chain of one GOP (one warp, ~6 cycles per issued instruction, profiles/)",
+                            "bound": "serial dependency chain of one GOP: one chain warp per GOP (~6 cycles per issued instruction) + helper warps for "
+                                     "motion-vector copies; see profiles/ and multi_clip for the throughput with more chains in flight",
                             "algorithmic_decode_bytes_per_step": frames * W * H * 8,
                             "achieved_GBps": frames * W * H * 8 / (stage["dec_ms"] / args.steps / 1e3) / 1e9},
         "cpu_baseline": cpu,
@@ -351,7 +362,7 @@ def main():
     ap.add_argument("--frames", type=int, default=synth.CONFIGS[WORKLOAD].frames)
     ap.add_argument("--ref-frames", type=int, default=200, help="bounded sample for the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi", type=int, default=0, help="also measure N independent clips in flight on one GPU")
+    ap.add_argument("--multi", type=int, default=8, help="also measure N independent clips in flight on one GPU (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,6 +85,27 @@ int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* s
 int scpr_decompress_clip_dev(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes,
                              int n, uint8_t* d_frames, int pitch);
 
+/* ---- frame-range sharding and checkpoint / resume of the encoder (no reference equivalent) ------
+ * A clip is cut into contiguous frame ranges that are encoded by different codec objects (one per GPU) and the
+ * bitstreams concatenated on the host.  What the reference's encoder carries from one frame to
+ * the next, and what a byte-identical continuation therefore needs:
+ *   - always: the persistent motion-vector array mvs[] -- never cleared, not even by an I frame (screencap.cpp:96-97,
+ *     715-735) --, the frame counter and the last flat colour (screencap.cpp:1488-1511);
+ *   - for a range that starts on a P frame also the previous frame and the adaptive models (20 MB), i.e. full = 1.
+ * export after the last frame of a range, import into the codec that encodes the next range (created with the same
+ * parameters) before its first frame.  A range that starts on a keyframe only needs the small blob (full = 0,
+ * 8 bytes per 16x16 block).  full = 1 doubles as checkpoint / resume of an encode. */
+/* Pipelining across ranges: mvs[] of a range is final as soon as its in-order motion-vector resolve has run, long
+ * before its entropy stages finish.  With hooks set, every compress call invokes wait(user) on the calling thread
+ * right before that resolve is enqueued (frame scan, motion search and candidate matching are already running) and
+ * ready(user) right after it completed.  wait typically receives the previous range's blob and calls
+ * scpr_import_range_state (which then takes only the vectors); ready calls scpr_export_range_state(full = 0) and
+ * sends it on.  Range k's resolve thus starts when range k-1's ends and everything else overlaps. */
+int scpr_set_mvs_hooks(scpr_codec* c, void (*wait)(void* user), void (*ready)(void* user), void* user);
+size_t scpr_range_state_size(const scpr_codec* c, int full);
+int64_t scpr_export_range_state(scpr_codec* c, uint8_t* blob, size_t cap, int full);   /* bytes written or < 0 */
+int scpr_import_range_state(scpr_codec* c, const uint8_t* blob, size_t len);
+
 /* ---- plumbing ------------------------------------------------------------------------------ */
 /* CUDA stream (cudaStream_t) all kernels of this codec are launched on; default: the legacy stream. */
 int scpr_set_stream(scpr_codec* c, void* cuda_stream);

@@ -106,6 +106,14 @@ def load_library() -> C.CDLL:
     lib.scpr_debug_events.argtypes = [vp, i32, vp, vp, C.c_size_t]
     lib.scpr_debug_blocks.restype = i32
     lib.scpr_debug_blocks.argtypes = [vp, i32, vp, vp, vp]
+    lib.scpr_range_state_size.restype = C.c_size_t
+    lib.scpr_range_state_size.argtypes = [vp, i32]
+    lib.scpr_export_range_state.restype = i64
+    lib.scpr_export_range_state.argtypes = [vp, vp, C.c_size_t, i32]
+    lib.scpr_import_range_state.restype = i32
+    lib.scpr_import_range_state.argtypes = [vp, vp, C.c_size_t]
+    lib.scpr_set_mvs_hooks.restype = i32
+    lib.scpr_set_mvs_hooks.argtypes = [vp, vp, vp, vp]
     lib.scpr_bench_frame_scan.restype = C.c_float
     lib.scpr_bench_frame_scan.argtypes = [vp, vp, i32, i32]
     _lib = lib
@@ -231,6 +239,26 @@ class ScreenCodec:
             raise ScprError(0, "P frame before any I frame")
         self._check(r)
         return out
+
+    # ---- frame-range sharding / checkpoint (include/scpr_c.h) ----------------------------------------
+    def ExportRangeState(self, full: bool = False) -> np.ndarray:
+        """Encoder state the next frame range needs: mvs[] + counters (full=False, ranges that start on a keyframe)
+        or everything including the previous frame and the adaptive models (full=True, any cut / checkpoint)."""
+        blob = np.empty(self._lib.scpr_range_state_size(self._h, int(full)), dtype=np.uint8)
+        n = self._check(self._lib.scpr_export_range_state(self._h, _ptr(blob), blob.size, int(full)))
+        return blob[:n]
+
+    def ImportRangeState(self, blob: np.ndarray) -> None:
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self._lib.scpr_import_range_state(self._h, _ptr(blob), blob.size))
+
+    def set_mvs_hooks(self, wait=None, ready=None) -> None:
+        """Python callables invoked around the in-order motion-vector resolve of every compress call (scpr_set_mvs_hooks):
+        `wait()` before it (import the previous range's vectors there), `ready()` after it (export and pass them on)."""
+        HOOK = C.CFUNCTYPE(None, C.c_void_p)
+        self._hooks = (HOOK(lambda _u: wait()) if wait else None, HOOK(lambda _u: ready()) if ready else None)  # keep alive
+        self._check(self._lib.scpr_set_mvs_hooks(self._h, C.cast(self._hooks[0], C.c_void_p) if wait else None,
+                                                 C.cast(self._hooks[1], C.c_void_p) if ready else None, None))
 
     # ---- plumbing / test hooks -------------------------------------------------------------------
     def set_stream(self, cuda_stream: int) -> None:

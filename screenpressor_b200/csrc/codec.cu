@@ -167,6 +167,8 @@ void scpr_destroy(scpr_codec* c) {
                    &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
                    &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym, &c->summary2};
     for (DBuf* b : all) b->release();
+    for (cudaEvent_t e : c->copy_ev) cudaEventDestroy(e);
+    if (c->copy_st) cudaStreamDestroy(c->copy_st);
     delete c;
 }
 
@@ -198,8 +200,9 @@ uint64_t scpr_kernel_launches(const scpr_codec* c) { return c ? c->launches : 0;
 // ------------------------------------------------------------------------------------------------
 // batch encoder: n device-resident frames -> host bitstreams
 // ------------------------------------------------------------------------------------------------
+// hooks: bit 0 = this batch opens a compress call (fire mvs_wait), bit 1 = it closes one (fire mvs_ready)
 static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags, uint8_t* dst,
-                            size_t dst_cap, uint32_t* sizes, uint8_t* ftypes_out) {
+                            size_t dst_cap, uint32_t* sizes, uint8_t* ftypes_out, int hooks = 3) {
     const Geo& g = c->g;
     cudaStream_t st = c->st;
     CK(cudaSetDevice(c->device));
@@ -344,8 +347,17 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         pw.bts_rle = (uint32_t*)c->bts_rle.p;
         pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * 32;
         pw.cands0 = (int*)c->cands.p + (size_t)n_p * 33; pw.ncands0 = (int*)c->cands.p + (size_t)n_p * 65;
+        pw.pre_resolve = (hooks & 1) ? c->mvs_wait : nullptr;
+        pw.post_resolve = (hooks & 2) ? c->mvs_ready : nullptr;
+        pw.hook_user = c->mvs_user;
+        pw.in_hook = &c->in_hook;
         launch_p_stage_a(pw, st, &c->launches);
         tm.mark("p_stage_a");
+    } else {  // no motion search in this batch: mvs[] passes through unchanged
+        c->in_hook = true;
+        if ((hooks & 1) && c->mvs_wait) c->mvs_wait(c->mvs_user);
+        if ((hooks & 2) && c->mvs_ready) c->mvs_ready(c->mvs_user);
+        c->in_hook = false;
     }
     IWork iw;
     memset(&iw, 0, sizeof(iw));
@@ -541,10 +553,39 @@ int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const ui
     if (!c || !frames || !keyflags || !dst || n < 0) return SCPR_E_PARAM;
     if (n == 0) return 0;
     CK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)n * c->g.frame_bytes;
-    TRY(c->frames.ensure(bytes));
-    CK(cudaMemcpyAsync(c->frames.p, frames, bytes, cudaMemcpyHostToDevice, c->st));
-    return encode_batch(c, (const uint8_t*)c->frames.p, n, keyflags, dst, dst_cap, sizes, ftypes);
+    const size_t fb = c->g.frame_bytes;
+    TRY(c->frames.ensure((size_t)n * fb));
+    // Host frames: the clip is encoded as a few sub-batches (any frame boundary is a valid cut -- previous frame,
+    // open model chain, mvs[] and frame counter carry over exactly as between calls) so that the upload of
+    // sub-batch k+1 on a copy stream overlaps the kernels of sub-batch k.  Pinned host memory makes the
+    // copies asynchronous; pageable memory degrades to copy-then-compute.
+    const int per = n > 48 ? (n + 7) / 8 : n;
+    const int nsub = (n + per - 1) / per;
+    if (!c->copy_st) CK(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+    while ((int)c->copy_ev.size() < nsub) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->copy_ev.push_back(e);
+    }
+    for (int k = 0; k < nsub; k++) {
+        const int f0 = k * per, m = n - f0 < per ? n - f0 : per;
+        CK(cudaMemcpyAsync((uint8_t*)c->frames.p + (size_t)f0 * fb, frames + (size_t)f0 * fb, (size_t)m * fb, cudaMemcpyHostToDevice,
+                           c->copy_st));
+        CK(cudaEventRecord(c->copy_ev[k], c->copy_st));
+    }
+    int64_t used = 0;
+    for (int k = 0; k < nsub; k++) {
+        const int f0 = k * per, m = n - f0 < per ? n - f0 : per;
+        CK(cudaStreamWaitEvent(c->st, c->copy_ev[k], 0));
+        const int64_t r = encode_batch(c, (const uint8_t*)c->frames.p + (size_t)f0 * fb, m, keyflags + f0, dst + used, dst_cap - (size_t)used,
+                                       sizes ? sizes + f0 : nullptr, ftypes ? ftypes + f0 : nullptr, (k == 0 ? 1 : 0) | (k == nsub - 1 ? 2 : 0));
+        if (r < 0) {
+            cudaStreamSynchronize(c->copy_st);
+            return r;
+        }
+        used += r;
+    }
+    return used;
 }
 
 int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss) {
@@ -558,6 +599,101 @@ int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst
     if (r < 0) return (int)r;
     *ftype = ft;
     return (int)size;
+}
+
+// ---- encoder state hand-off between frame ranges (DESIGN.md "Multi-GPU") ---------------------
+// Blob: RangeHdr, mvs[] (nb x int2), then -- full blobs only -- the previous frame and the open chain's ModelState.
+struct RangeHdr {
+    uint32_t magic, nb, full, fn;
+    uint8_t last_was_flat, last_flat_clr[3];
+    uint32_t have_models;
+    uint64_t frame_bytes, state_bytes;
+};
+static const uint32_t RANGE_MAGIC = 0x52435053u;  // "SPCR"
+
+size_t scpr_range_state_size(const scpr_codec* c, int full) {
+    if (!c) return 0;
+    size_t n = sizeof(RangeHdr) + (size_t)c->g.nb * sizeof(int2);
+    if (full) n += c->g.frame_bytes + model_state_bytes();
+    return n;
+}
+
+int64_t scpr_export_range_state(scpr_codec* c, uint8_t* blob, size_t cap, int full) {
+    if (!c || !blob) return SCPR_E_PARAM;
+    const size_t need = scpr_range_state_size(c, full);
+    if (cap < need) return SCPR_E_DSTSIZE;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));
+    RangeHdr h;
+    memset(&h, 0, sizeof(h));
+    h.magic = RANGE_MAGIC;
+    h.nb = (uint32_t)c->g.nb;
+    h.full = full ? 1u : 0u;
+    h.fn = c->fn;
+    h.last_was_flat = c->last_was_flat;
+    memcpy(h.last_flat_clr, c->last_flat_clr, 3);
+    h.have_models = c->have_models && c->n_states > 0;
+    h.frame_bytes = c->g.frame_bytes;
+    h.state_bytes = model_state_bytes();
+    memcpy(blob, &h, sizeof(h));
+    uint8_t* p = blob + sizeof(h);
+    CK(cudaMemcpy(p, c->mvs.p, (size_t)c->g.nb * sizeof(int2), cudaMemcpyDeviceToHost));
+    p += (size_t)c->g.nb * sizeof(int2);
+    if (full) {
+        CK(cudaMemcpy(p, c->prev.p, c->g.frame_bytes, cudaMemcpyDeviceToHost));
+        p += c->g.frame_bytes;
+        if (h.have_models)
+            CK(cudaMemcpy(p, (const uint8_t*)c->states.p + (size_t)c->cur_state * model_state_bytes(), model_state_bytes(),
+                          cudaMemcpyDeviceToHost));
+        else
+            memset(p, 0, model_state_bytes());
+    }
+    return (int64_t)need;
+}
+
+int scpr_import_range_state(scpr_codec* c, const uint8_t* blob, size_t len) {
+    if (!c || !blob || len < sizeof(RangeHdr)) return SCPR_E_PARAM;
+    RangeHdr h;
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != RANGE_MAGIC || h.nb != (uint32_t)c->g.nb || len < scpr_range_state_size(c, (int)h.full) ||
+        (h.full && (h.frame_bytes != c->g.frame_bytes || h.state_bytes != model_state_bytes()))) {
+        set_error("range state blob does not match this codec");
+        return SCPR_E_PARAM;
+    }
+    CK(cudaSetDevice(c->device));
+    const uint8_t* p = blob + sizeof(h);
+    if (c->in_hook) {
+        // inside the mvs_wait hook of a running compress call: frame types are already planned and kernels that do
+        // not read mvs[] are in flight -- only the vectors are taken, ordered on the stream before the resolve
+        CK(cudaMemcpyAsync(c->mvs.p, p, (size_t)c->g.nb * sizeof(int2), cudaMemcpyHostToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));  // the blob is the caller's memory
+        return SCPR_OK;
+    }
+    CK(cudaStreamSynchronize(c->st));
+    c->fn = h.fn;
+    c->last_was_flat = h.last_was_flat != 0;
+    memcpy(c->last_flat_clr, h.last_flat_clr, 3);
+    CK(cudaMemcpy(c->mvs.p, p, (size_t)c->g.nb * sizeof(int2), cudaMemcpyHostToDevice));
+    p += (size_t)c->g.nb * sizeof(int2);
+    if (h.full) {
+        CK(cudaMemcpy(c->prev.p, p, c->g.frame_bytes, cudaMemcpyHostToDevice));
+        p += c->g.frame_bytes;
+        c->have_models = h.have_models != 0;
+        if (h.have_models) {
+            TRY(ensure_states(c, 1));
+            CK(cudaMemcpy((uint8_t*)c->states.p + (size_t)c->cur_state * model_state_bytes(), p, model_state_bytes(),
+                          cudaMemcpyHostToDevice));
+        }
+    }
+    return SCPR_OK;
+}
+
+int scpr_set_mvs_hooks(scpr_codec* c, void (*wait)(void*), void (*ready)(void*), void* user) {
+    if (!c) return SCPR_E_PARAM;
+    c->mvs_wait = wait;
+    c->mvs_ready = ready;
+    c->mvs_user = user;
+    return SCPR_OK;
 }
 
 int64_t scpr_debug_events(scpr_codec* c, int frame, uint32_t* ev, uint32_t* iv, size_t cap) {

@@ -32,6 +32,8 @@ struct scpr_codec {
     scpr_params p;
     int device = 0;
     cudaStream_t st = 0;
+    cudaStream_t copy_st = nullptr;         // uploads of host frames, overlapped with the kernels (scpr_compress_clip)
+    std::vector<cudaEvent_t> copy_ev;
     scpr::Geo g;
     uint64_t launches = 0;
 
@@ -45,6 +47,12 @@ struct scpr_codec {
     scpr::DBuf mvs;                  // int2 per block, never cleared
     scpr::DBuf states;               // pool of ModelState; states[cur_state] belongs to the open chain
     int n_states = 0, cur_state = 0;
+
+    // frame-range pipelining (scpr_set_mvs_hooks): called on the compress call's thread around the in-order MV resolve
+    void (*mvs_wait)(void*) = nullptr;
+    void (*mvs_ready)(void*) = nullptr;
+    void* mvs_user = nullptr;
+    bool in_hook = false;
 
     // ---- encoder workspaces ---------------------------------------------------------------------
     scpr::DBuf summary2;

@@ -921,10 +921,11 @@ __device__ void helper_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t 
         uint32_t idx = 0;
         if (lane == 0) idx = atom_add_shared(sy + 4, 1u);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-        for (;;) {
+        for (uint32_t ns = 64;;) {  // idle most of the time on sparse content: back off so the polls stay out of the chain warp's way
             if ((int)(ldv_shared(sy) - idx) > 0) break;
             if (ldv_shared(sy + 12)) return;  // quit is only raised after a drain: nothing published is left behind
-            __nanosleep(200);
+            __nanosleep(ns);
+            ns = min(ns * 2u, 2048u);
         }
         __threadfence_block();
         const uint4 cmd = lds128(sb + S_RING + 16u * (idx % RING));

@@ -83,6 +83,8 @@ struct PWork {
     const uint32_t* frame_ev_off;          // per batch frame: first event (batch-wide index)
     uint32_t* events; uint32_t* intervals;
     struct StageTimer* tm;
+    // host-side hooks around the in-order resolve (frame-range pipelining, include/scpr_c.h scpr_set_mvs_hooks)
+    void (*pre_resolve)(void*); void (*post_resolve)(void*); void* hook_user; bool* in_hook;
 };
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches);   // search, resolve, runs, counts
 void launch_p_emit(const PWork& w, cudaStream_t st, uint64_t* launches);      // events

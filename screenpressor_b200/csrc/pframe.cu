@@ -167,6 +167,38 @@ __device__ __forceinline__ bool warp_match(const uint8_t* cur, const uint8_t* pr
     }
     return true;
 }
+// the same test for the serial resolve, where the latency of a compare is on the critical path: the first 32 pixels
+// decide most mismatches (one round trip, few instructions -- a lone warp pays ~6 cycles per instruction); only when
+// they agree are the remaining pixels fetched, all loads in flight at once
+__device__ __forceinline__ bool warp_match_full(const uint8_t* cur, const uint8_t* prv, const Geo& g, const SubRect& r, int mx,
+                                                int my, int lane) {
+    const int npx = r.w * r.h;  // <= 256
+    const uint32_t winv = (65536u + (uint32_t)r.w - 1) / (uint32_t)r.w;  // p / w == (p * winv) >> 16 for p < 256
+    {
+        bool same = true;
+        if (lane < npx) {
+            const int yy = (int)(((uint32_t)lane * winv) >> 16), xx = lane - yy * r.w;
+            same = load_px(cur, g, r.x1 + xx, r.y1 + yy) == load_px(prv, g, r.x1 + mx + xx, r.y1 + my + yy);
+        }
+        if (!__all_sync(0xFFFFFFFFu, same)) return false;
+        if (npx <= 32) return true;
+    }
+    uint32_t a[7], b[7];
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+        const int p = lane + 32 * (u + 1);
+        a[u] = b[u] = 0;
+        if (p < npx) {
+            const int yy = (int)(((uint32_t)p * winv) >> 16), xx = p - yy * r.w;
+            a[u] = load_px(cur, g, r.x1 + xx, r.y1 + yy);
+            b[u] = load_px(prv, g, r.x1 + mx + xx, r.y1 + my + yy);
+        }
+    }
+    bool same = true;
+#pragma unroll
+    for (int u = 0; u < 7; u++) same = same && a[u] == b[u];
+    return __all_sync(0xFFFFFFFFu, same);
+}
 __device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& win, int mx, int my) {
     const int sx = r.x1 + mx, sy = r.y1 + my;
     return sx >= win.fx1 && sx < win.fx2 && sy >= win.fy1 && sy < win.fy2;
@@ -178,7 +210,12 @@ __device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& w
 // lane k keeps candidate k.  Also records each block's index into that list (fidx, 0xFF = none).
 // ------------------------------------------------------------------------------------------------
 constexpr int MAXC = 32;
-__device__ unsigned long long g_mv_stats[4];  // steps, c1 direct compares, c2 direct compares, blocks
+__device__ unsigned long long g_mv_stats[4];  // steps, c1 direct compares, c2 direct compares, blocks (-DSCPR_MVSTATS builds only)
+#ifdef SCPR_MVSTATS
+#define MV_STAT(...) __VA_ARGS__
+#else
+#define MV_STAT(...)
+#endif
 __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
     const int lane = threadIdx.x;
     const int f = w.pframes[blockIdx.x];
@@ -217,12 +254,13 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
 
 // k_mv_cands_merge: the vector stored for the block above (candidate 2) is often a leftover of an
 // earlier frame, so each frame's list is topped up with the lists of the preceding P frames.
+constexpr int MERGE_BACK = 192;  // a drag or scroll session ends, the vectors it left in mvs[] stay for a long time
 __global__ void __launch_bounds__(32) k_mv_cands_merge(PWork w) {
     const int lane = threadIdx.x;
     const int pi = blockIdx.x;
     int cand = w.cands0[(size_t)pi * MAXC + lane];
     int ncand = w.ncands0[pi];
-    for (int back = 1; back <= 12 && pi - back >= 0 && ncand < MAXC; back++) {
+    for (int back = 1; back <= MERGE_BACK && pi - back >= 0 && ncand < MAXC; back++) {
         const int pv = w.cands0[(size_t)(pi - back) * MAXC + lane];
         const int pn = w.ncands0[pi - back];
         for (int k = 0; k < pn && ncand < MAXC; k++) {
@@ -280,10 +318,38 @@ __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
 // A step never contains a block together with its upper neighbour (their indices differ by nbx),
 // so the upper MV can be read from mvs[] when the step is loaded.
 // ------------------------------------------------------------------------------------------------
+// Two things keep memory latency off the serial path: the persistent mvs[] array is held in shared memory while
+// the kernel runs (SMV; written through to global memory), and the block records of a frame are read 64 ahead into
+// two register windows, a step picking its 32 records out of them with shuffles.
+struct MvRec {
+    uint32_t bi, info, mmask;
+    int fidx, fv;
+};
+__device__ __forceinline__ MvRec load_mvrec(const ChgBlock* blocks, int k, int nchg) {
+    MvRec r;
+    r.bi = r.info = r.mmask = 0;
+    r.fidx = 0x100;
+    r.fv = 0;
+    if (k < nchg) {
+        const ChgBlock& b = blocks[k];
+        r.bi = b.bi; r.info = b.info; r.mmask = b.mmask; r.fidx = b.has_f ? b.fidx : 0x100;
+        r.fv = ((int)b.fmx & 0xFFFF) | ((int)b.fmy << 16);
+    }
+    return r;
+}
+template <bool SMV>
 __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
+    extern __shared__ uint32_t s_mvs[];  // SMV: packed vector of every block
     const int lane = threadIdx.x;
     const uint32_t lt = (1u << lane) - 1;
     const Geo& g = w.g;
+    if (SMV) {
+        for (int i = lane; i < g.nb; i += 32) {
+            const int2 u = w.mvs[i];
+            s_mvs[i] = ((uint32_t)u.x & 0xFFFFu) | ((uint32_t)u.y << 16);
+        }
+        __syncwarp();
+    }
     for (int pi = 0; pi < w.n_pframes; pi++) {
         const int f = w.pframes[pi];
         const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
@@ -295,16 +361,31 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
         int cv = 0;              // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
         int prev_nonmv = -1;
         int k0 = 0;
+        int w0 = 0;              // records [w0, w0 + 32) are in r0, [w0 + 32, w0 + 64) in r1
+        MvRec r0 = load_mvrec(w.blocks + off, lane, nchg), r1 = load_mvrec(w.blocks + off, 32 + lane, nchg);
         while (k0 < nchg) {
+            if (k0 - w0 >= 32) {
+                r0 = r1;
+                w0 += 32;
+                r1 = load_mvrec(w.blocks + off, w0 + 32 + lane, nchg);
+            }
             const int k = k0 + lane;
-            uint32_t bi = 0, info = 0;
-            uint32_t mmask = 0;
-            int fidx = 0x100, fv = 0, uv = 0;
-            if (k < nchg) {
-                const ChgBlock& b = w.blocks[off + k];
-                bi = b.bi; info = b.info; mmask = b.mmask; fidx = b.has_f ? b.fidx : 0x100;
-                fv = ((int)b.fmx & 0xFFFF) | ((int)b.fmy << 16);
-                if (bi >= (uint32_t)g.nbx) {
+            const int jw = k0 - w0 + lane, js = jw & 31;
+            const bool lo = jw < 32;
+            uint32_t bi, info, mmask;
+            int fidx, fv, uv = 0;
+            {
+                const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, r0.bi, js), a1 = __shfl_sync(0xFFFFFFFFu, r1.bi, js);
+                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, r0.info, js), b1 = __shfl_sync(0xFFFFFFFFu, r1.info, js);
+                const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, r0.mmask, js), c1 = __shfl_sync(0xFFFFFFFFu, r1.mmask, js);
+                const int d0 = __shfl_sync(0xFFFFFFFFu, r0.fidx, js), d1 = __shfl_sync(0xFFFFFFFFu, r1.fidx, js);
+                const int e0 = __shfl_sync(0xFFFFFFFFu, r0.fv, js), e1 = __shfl_sync(0xFFFFFFFFu, r1.fv, js);
+                bi = lo ? a0 : a1; info = lo ? b0 : b1; mmask = lo ? c0 : c1; fidx = lo ? d0 : d1; fv = lo ? e0 : e1;
+            }
+            if (k < nchg && bi >= (uint32_t)g.nbx) {
+                if (SMV)
+                    uv = (int)s_mvs[bi - g.nbx];
+                else {
                     const int2 u = w.mvs[bi - g.nbx];
                     uv = (u.x & 0xFFFF) | (u.y << 16);
                 }
@@ -318,27 +399,32 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
             if (lidx >= 0)
                 found = in && ((mmask >> lidx) & 1);
             else if (lidx == -2) {  // last_mv is not in the candidate list: direct compares, lane by lane
-                if (lane == 0) atomicAdd(&g_mv_stats[1], (unsigned long long)cnt);
+                MV_STAT(if (lane == 0) atomicAdd(&g_mv_stats[1], (unsigned long long)cnt);)
                 for (int i = 0; i < cnt; i++) {
                     const SubRect r = subrect_of(__shfl_sync(0xFFFFFFFFu, bi, i), __shfl_sync(0xFFFFFFFFu, info, i), g);
                     const Windows win = windows_of(r, g);
                     const int mx = (int)(int16_t)(lv & 0xFFFF), my = lv >> 16;
-                    const bool hit = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                    const bool hit = in_far_window(r, win, mx, my) && warp_match_full(cur, prv, g, r, mx, my, lane);
                     if (lane == i) found = hit;
                 }
             }
             if (found) mv = lv;
             // ---- candidate 2: the vector stored for the block above, if it differs from last_mv ----
             const bool try2 = in && !found && bi >= (uint32_t)g.nbx && uv != lv && uv != 0;
-            int uidx = -1;
-            for (int kc = 0; kc < nc; kc++)
-                if (__shfl_sync(0xFFFFFFFFu, cand, kc) == uv) uidx = kc;
+            int uidx = -1;  // its index in the candidate list: one ballot per distinct vector among the lanes that need it
+            for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, try2); todo;) {
+                const int v = __shfl_sync(0xFFFFFFFFu, uv, __ffs(todo) - 1);
+                const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < nc && cand == v);
+                const bool mine = uv == v;
+                if (mine) uidx = hit ? __ffs(hit) - 1 : -1;
+                todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
+            }
             bool f2 = try2 && uidx >= 0 && ((mmask >> uidx) & 1);
             uint32_t slow = __ballot_sync(0xFFFFFFFFu, try2 && uidx < 0);
-            if (lane == 0) {
+            MV_STAT(if (lane == 0) {
                 atomicAdd(&g_mv_stats[0], 1ull);
                 atomicAdd(&g_mv_stats[2], (unsigned long long)__popc(slow));
-            }
+            })
             while (slow) {  // a stale vector that is not one of this frame's candidates: compare directly
                 const int i = __ffs(slow) - 1;
                 slow &= slow - 1;
@@ -346,7 +432,7 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
                 const Windows win = windows_of(r, g);
                 const int u = __shfl_sync(0xFFFFFFFFu, uv, i);
                 const int mx = (int)(int16_t)(u & 0xFFFF), my = u >> 16;
-                const bool hit = in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane);
+                const bool hit = in_far_window(r, win, mx, my) && warp_match_full(cur, prv, g, r, mx, my, lane);
                 if (lane == i) f2 = hit;
             }
             if (f2) {
@@ -385,12 +471,15 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
                 b.mx = (int16_t)(mv & 0xFFFF);
                 b.my = (int16_t)(mv >> 16);
                 b.prev_nonmv = found ? -1 : my_prev_nonmv;
-                if (found) w.mvs[bi] = make_int2((int)(int16_t)(mv & 0xFFFF), mv >> 16);
+                if (found) {
+                    if (SMV) s_mvs[bi] = (uint32_t)mv;
+                    w.mvs[bi] = make_int2((int)(int16_t)(mv & 0xFFFF), mv >> 16);
+                }
             }
             if (fm) cv = __shfl_sync(0xFFFFFFFFu, mv, 31 - __clz(fm));
             if (nm) prev_nonmv = k0 + 31 - __clz(nm);
             __syncwarp();
-            if (lane == 0) atomicAdd(&g_mv_stats[3], (unsigned long long)cnt);
+            MV_STAT(if (lane == 0) atomicAdd(&g_mv_stats[3], (unsigned long long)cnt);)
             k0 += cnt;
         }
         __threadfence();  // mvs[] of this frame visible before the next frame reads it
@@ -672,6 +761,9 @@ __global__ void __launch_bounds__(128) k_p_emit(PWork w) {
 }
 
 void mv_stats_report() {
+#ifndef SCPR_MVSTATS
+    return;
+#endif
     unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
     cudaMemcpyFromSymbol(h, g_mv_stats, sizeof(h));
     cudaMemcpyToSymbol(g_mv_stats, z, sizeof(z));
@@ -688,11 +780,33 @@ void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
         k_mv_prematch<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
         *launches += 2;
         if (w.tm) w.tm->mark("mv_prematch");
-        k_mv_resolve<<<1, 32, 0, st>>>(w);
+        if (w.pre_resolve) {  // everything enqueued so far is independent of mvs[]: it runs while the host waits for the hand-off
+            *w.in_hook = true;
+            w.pre_resolve(w.hook_user);
+            *w.in_hook = false;
+        }
+        const size_t mv_smem = (size_t)w.g.nb * 4;
+        if (mv_smem <= 200 * 1024) {
+            cudaFuncSetAttribute(k_mv_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mv_smem);
+            k_mv_resolve<true><<<1, 32, mv_smem, st>>>(w);
+        } else
+            k_mv_resolve<false><<<1, 32, 0, st>>>(w);
         if (w.tm) w.tm->mark("mv_resolve");
+        if (w.post_resolve) {  // mvs[] is final for this call: the next range may start its resolve
+            cudaStreamSynchronize(st);
+            *w.in_hook = true;
+            w.post_resolve(w.hook_user);
+            *w.in_hook = false;
+        }
         k_p_runs<<<(w.total_blocks + 3) / 4, 128, 0, st>>>(w);
         if (w.tm) w.tm->mark("p_runs");
         *launches += 3;
+    }
+    else {  // nothing to resolve: mvs[] passes through
+        if (w.pre_resolve || w.post_resolve) *w.in_hook = true;
+        if (w.pre_resolve) w.pre_resolve(w.hook_user);
+        if (w.post_resolve) w.post_resolve(w.hook_user);
+        if (w.pre_resolve || w.post_resolve) *w.in_hook = false;
     }
     if (w.n_pframes > 0) {
         k_p_count<<<w.n_pframes, 256, 0, st>>>(w);

@@ -100,3 +100,85 @@ def test_reference_arm_other_ranks_exit_silently():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                          text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+# ---- frame-range sharding (screenpressor_b200/shard.py): partition + relay order under a 2-rank gloo group -----------
+class _StubCodec:
+    """Stands in for the CUDA codec on CPU: the 'bitstream' of frame i is (i, state) so the test can see which state
+    every range was encoded with; state = number of frames encoded by the ranges before (travels in the blob)."""
+
+    def __init__(self):
+        self.state = np.zeros(4, np.uint8)
+        self.hooks = (None, None)
+
+    def ExportRangeState(self, full=False):
+        return self.state.copy()
+
+    def ImportRangeState(self, blob):
+        self.state = np.array(blob, np.uint8)
+
+    def set_mvs_hooks(self, wait=None, ready=None):
+        self.hooks = (wait, ready)
+
+    def CompressClip(self, frames, keys, device_ptr=None, n=None):
+        if self.hooks[0]:
+            self.hooks[0]()
+        seen = int(self.state[0])
+        self.state = self.state.copy()
+        self.state[0] = seen + n
+        if self.hooks[1]:
+            self.hooks[1]()
+        stream = np.repeat(np.uint8(seen), n)
+        return stream, np.ones(n, np.uint32), (1 - np.asarray(keys, np.uint8))
+
+
+def test_assign_ranges_cuts_only_at_keyframes():
+    from screenpressor_b200 import shard, synth
+
+    k = synth.keyframe_flags(3600, 450)
+    for world in (1, 2, 4, 8, 16):
+        r = shard.assign_ranges(k, world)
+        assert r[0].first == 0 and sum(x.count for x in r) == 3600 and len(r) == min(world, 8)
+        assert all(k[x.first] for x in r) and all(a.first + a.count == b.first for a, b in zip(r, r[1:]))
+    r = shard.assign_ranges(synth.keyframe_flags(600, 500), 8)   # cfg 2 has two GOPs: ranks beyond them stay idle
+    assert [(x.first, x.count) for x in r] == [(0, 500), (500, 100)]
+    assert shard.gop_ranges(np.array([0, 0, 1, 0, 1], np.uint8)) == [(0, 2), (2, 2), (4, 1)]
+
+
+def _shard_rank_main(rank, world, port, q, pipelined):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from screenpressor_b200 import shard, synth
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys = synth.keyframe_flags(40, 10)
+    rng, stream, sizes, fts = shard.encode_sharded(_StubCodec(), None, keys, rank, world, dist, pipelined=pipelined)
+    q.put((rank, (rng.first, rng.count), stream.tolist(), fts.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_sharded_encode_relays_state_in_rank_order_gloo(pipelined):
+    import torch.multiprocessing as mp
+
+    from screenpressor_b200 import shard
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + int(pipelined)
+    procs = [ctx.Process(target=_shard_rank_main, args=(r, 2, port, q, pipelined)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == (0, 20) and res[1][1] == (20, 20)
+    assert set(res[0][2]) == {0} and set(res[1][2]) == {20}      # rank 1 encoded with the state rank 0 left behind
+    assert res[1][3][0] == 0                                        # a range starts on a keyframe
+    parts = [(shard.FrameRange(f, c, r), np.array(s, np.uint8), np.ones(c, np.uint32), np.array(t, np.uint8)) for r, (f, c), s, t in res]
+    stream, sizes, fts = shard.gather_streams(parts[::-1])
+    assert stream.tolist() == [0] * 20 + [20] * 20 and sizes.size == 40
