@@ -22,9 +22,10 @@ extern "C" {
 /* replaces struct CodecParameters (reference screencap.h:49-55) */
 typedef struct scpr_params {
     uint32_t width, height;
-    uint8_t bits_per_pixel;                  /* 24 or 32 (16 is not built yet: returns SCPR_E_UNSUPPORTED) */
-    uint16_t redmask, greenmask, bluemask;   /* 16 bpp only */
-    uint32_t high_range_x, high_range_y;     /* motion search ranges; v4 clamps these to 256 (screencap.cpp:79) */
+    uint8_t bits_per_pixel;                  /* 16, 24 or 32 */
+    uint16_t redmask, greenmask, bluemask;   /* 16 bpp only: channel masks, e.g. 0x7C00 / 0x3E0 / 0x1F (screencap.cpp:1575-1583) */
+    uint32_t high_range_x, high_range_y;     /* motion search ranges; v3/v4 clamp these to 256 (screencap.cpp:79); a v2 stream's
+                                                motion vectors are offset by them (1..256) */
     uint32_t low_range_x, low_range_y;       /* 8, 8 (screenpressor.cpp:377-378) */
     uint32_t loss;                           /* bits of loss, 0..4 (quality -> loss, screenpressor.cpp:418-422) */
 } scpr_params;
@@ -35,7 +36,7 @@ enum {
     SCPR_OK = 0,
     SCPR_E_CUDA = -1000,        /* a CUDA call failed; scpr_last_error() has the text */
     SCPR_E_PARAM = -1001,       /* bad argument */
-    SCPR_E_UNSUPPORTED = -1002, /* feature outside the built hot path (16 bpp, v2 streams) */
+    SCPR_E_UNSUPPORTED = -1002, /* feature outside the built hot path (a v2 stream with a motion range above 256) */
     SCPR_E_DSTSIZE = -1003,     /* destination buffer too small */
     SCPR_E_NODEVICE = -1004     /* no CUDA device: this library never computes on the CPU */
 };
@@ -50,7 +51,7 @@ void scpr_destroy(scpr_codec* c);
 int scpr_reset(scpr_codec* c);
 
 /* replaces ScreenCodec::CompressFrame (screencap.cpp:1632-1692).
- * src: host frame, rows top to bottom, pitch width*4 (32 bpp) or (width*3+3)&~3 (24 bpp).
+ * src: host frame, rows top to bottom, pitch width*4 (32 bpp), (width*3+3)&~3 (24 bpp) or width*2 (16 bpp).
  * *ftype in: 0 = I requested, 1 = P requested; out: type actually coded (first and flat frames
  * are always I, screencap.cpp:1488-1511).  loss = bits of loss for this frame (the clip entry points use
  * the value given at creation); in lossy mode the `_dev` clip variant masks the caller's frames in place,
@@ -58,9 +59,9 @@ int scpr_reset(scpr_codec* c);
 int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss);
 
 /* replaces ScreenCodec::DecompressFrame (screencap.cpp:1695-1743).
- * Returns 1 on success, 0 for "P frame before any I frame", -v (v = 1..16) for a stream version
- * this build cannot decode (the reference throws BadVersionException(v), screencap.cpp:1589-1590;
- * v2 range-coder streams are out of scope here), or an SCPR_E_* code. */
+ * Stream generations 2 (range coder, ScreenPressor 2.x), 3 and 4 (ANS) are decoded, as by the reference.
+ * Returns 1 on success, 0 for "P frame before any I frame", -v (v = 1, 5..16) for a stream version
+ * nobody can decode (the reference throws BadVersionException(v), screencap.cpp:1589-1590), or an SCPR_E_* code. */
 int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_t* dst, int pitch, int ftype);
 
 /* ---- throughput entry points (no reference equivalent): many frames per call -------------

@@ -143,7 +143,8 @@ class ScreenCodec:
                     params.low_range_y, params.loss)
         self._check(self._lib.scpr_create(C.byref(p), self.device, C.byref(self._h)))
         self.params = params
-        self.pitch = params.width * 4 if params.bits_per_pixel == 32 else (params.width * 3 + 3) & ~3
+        # bytes per row of a frame handed to CompressFrame: implicit in the reference (screencap.cpp:1655, 1668)
+        self.pitch = {32: params.width * 4, 16: params.width * 2}.get(params.bits_per_pixel, (params.width * 3 + 3) & ~3)
         self.frame_bytes = self.pitch * params.height
         self.max_size = params.width * params.height * 6  # CompressGetSize, screenpressor.cpp:386-388
         self._dst = np.empty(self.max_size + 64, dtype=np.uint8)

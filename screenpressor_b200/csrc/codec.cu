@@ -111,9 +111,13 @@ int scpr_create(const scpr_params* p, int device, scpr_codec** out) {
         set_error("unsupported frame size %ux%u", p->width, p->height);
         return SCPR_E_PARAM;
     }
-    if (p->bits_per_pixel != 24 && p->bits_per_pixel != 32) {
-        set_error("bits_per_pixel %d: only 24 and 32 are built", (int)p->bits_per_pixel);
-        return SCPR_E_UNSUPPORTED;
+    if (p->bits_per_pixel != 16 && p->bits_per_pixel != 24 && p->bits_per_pixel != 32) {
+        set_error("bits_per_pixel %d: 16, 24 or 32 expected", (int)p->bits_per_pixel);  // BadVersionException(48), screencap.cpp:1607-1609
+        return SCPR_E_PARAM;
+    }
+    if (p->bits_per_pixel == 16 && (!p->redmask || !p->greenmask || !p->bluemask)) {
+        set_error("16 bpp needs the three channel masks");
+        return SCPR_E_PARAM;
     }
     if (p->loss > 5) {
         set_error("loss must be 0..5 bits");
@@ -133,8 +137,15 @@ int scpr_create(const scpr_params* p, int device, scpr_codec** out) {
     Geo& g = c->g;
     g.X = (int)p->width;
     g.Y = (int)p->height;
-    g.bpp = p->bits_per_pixel / 8;
+    g.bpp = p->bits_per_pixel == 32 ? 4 : 3;
     g.pitch = g.bpp == 4 ? g.X * 4 : ((g.X * 3 + 3) & ~3);
+    if (p->bits_per_pixel == 16) {  // ScreenCodec::Init, screencap.cpp:1575-1583
+        c->rgb16 = true;
+        c->m16.rmask = p->redmask; c->m16.gmask = p->greenmask; c->m16.bmask = p->bluemask;
+        while (!((1u << c->m16.rshift) & p->redmask)) c->m16.rshift++;
+        while (!((1u << c->m16.gshift) & p->greenmask)) c->m16.gshift++;
+        while (!((1u << c->m16.bshift) & p->bluemask)) c->m16.bshift++;
+    }
     g.nbx = (g.X + 15) / 16;
     g.nby = (g.Y + 15) / 16;
     g.nb = g.nbx * g.nby;
@@ -165,7 +176,8 @@ void scpr_destroy(scpr_codec* c) {
                    &c->ftype, &c->blocks, &c->pframes, &c->runs, &c->bts_rle, &c->ihdr, &c->desc, &c->exit_tab, &c->entry,
                    &c->starts, &c->chunk_cnt, &c->frame_ev_off, &c->events, &c->intervals, &c->sorted, &c->seg_off,
                    &c->chunk_hist, &c->chunk_base, &c->chains, &c->rblks, &c->scratch, &c->out, &c->dec_ws, &c->dec_stream,
-                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym, &c->summary2};
+                   &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym, &c->summary2, &c->raw16,
+                   &c->dec24};
     for (DBuf* b : all) b->release();
     for (cudaEvent_t e : c->copy_ev) cudaEventDestroy(e);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
@@ -545,6 +557,12 @@ extern "C" {
 int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags, uint8_t* dst,
                                size_t dst_cap, uint32_t* sizes, uint8_t* ftypes) {
     if (!c || !d_frames || !keyflags || !dst || n < 0) return SCPR_E_PARAM;
+    if (c->rgb16 && n > 0) {  // device frames of 2*X bytes per row -> the RGB24 image the codec works on
+        CK(cudaSetDevice(c->device));
+        TRY(c->frames.ensure((size_t)n * c->g.frame_bytes));
+        launch_unpack16(d_frames, (uint8_t*)c->frames.p, n, c->g, c->m16, c->st, &c->launches);
+        d_frames = (const uint8_t*)c->frames.p;
+    }
     return encode_batch(c, d_frames, n, keyflags, dst, dst_cap, sizes, ftypes);
 }
 
@@ -554,7 +572,10 @@ int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const ui
     if (n == 0) return 0;
     CK(cudaSetDevice(c->device));
     const size_t fb = c->g.frame_bytes;
+    const size_t in_fb = c->rgb16 ? (size_t)c->g.X * 2 * c->g.Y : fb;  // bytes per frame on the caller's side
     TRY(c->frames.ensure((size_t)n * fb));
+    if (c->rgb16) TRY(c->raw16.ensure((size_t)n * in_fb));
+    uint8_t* const up = c->rgb16 ? (uint8_t*)c->raw16.p : (uint8_t*)c->frames.p;
     // Host frames: the clip is encoded as a few sub-batches (any frame boundary is a valid cut -- previous frame,
     // open model chain, mvs[] and frame counter carry over exactly as between calls) so that the upload of
     // sub-batch k+1 on a copy stream overlaps the kernels of sub-batch k.  Pinned host memory makes the
@@ -569,14 +590,15 @@ int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const ui
     }
     for (int k = 0; k < nsub; k++) {
         const int f0 = k * per, m = n - f0 < per ? n - f0 : per;
-        CK(cudaMemcpyAsync((uint8_t*)c->frames.p + (size_t)f0 * fb, frames + (size_t)f0 * fb, (size_t)m * fb, cudaMemcpyHostToDevice,
-                           c->copy_st));
+        CK(cudaMemcpyAsync(up + (size_t)f0 * in_fb, frames + (size_t)f0 * in_fb, (size_t)m * in_fb, cudaMemcpyHostToDevice, c->copy_st));
         CK(cudaEventRecord(c->copy_ev[k], c->copy_st));
     }
     int64_t used = 0;
     for (int k = 0; k < nsub; k++) {
         const int f0 = k * per, m = n - f0 < per ? n - f0 : per;
         CK(cudaStreamWaitEvent(c->st, c->copy_ev[k], 0));
+        if (c->rgb16)
+            launch_unpack16(up + (size_t)f0 * in_fb, (uint8_t*)c->frames.p + (size_t)f0 * fb, m, c->g, c->m16, c->st, &c->launches);
         const int64_t r = encode_batch(c, (const uint8_t*)c->frames.p + (size_t)f0 * fb, m, keyflags + f0, dst + used, dst_cap - (size_t)used,
                                        sizes ? sizes + f0 : nullptr, ftypes ? ftypes + f0 : nullptr, (k == 0 ? 1 : 0) | (k == nsub - 1 ? 2 : 0));
         if (r < 0) {

@@ -34,7 +34,10 @@ struct scpr_codec {
     cudaStream_t st = 0;
     cudaStream_t copy_st = nullptr;         // uploads of host frames, overlapped with the kernels (scpr_compress_clip)
     std::vector<cudaEvent_t> copy_ev;
-    scpr::Geo g;
+    scpr::Geo g;                     // geometry of the resident frames (16 bpp clients: the RGB24 image the codec works on)
+    bool rgb16 = false;              // the caller's frames are 16 bpp (converted on the device on the way in and out)
+    scpr::Rgb16 m16 = {0, 0, 0, 0, 0, 0};
+    scpr::DBuf raw16, dec24;         // 16 bpp staging: uploaded input frames / decoded RGB24 frames
     uint64_t launches = 0;
 
     // ---- encoder state carried between calls (CScreenCapt members, screencap.h:445-463) ----------

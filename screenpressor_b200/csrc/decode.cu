@@ -55,6 +55,7 @@ struct DecWork {
     uint8_t* upd;       // n * nb flags: block written by the chain kernel in this frame
     int16_t* fill_src;  // n * nb: source frame of every block (k_dec_sources)
     int n;
+    int msr_x, msr_y;   // v2 streams: motion range the vectors are offset by (screencap.cpp:77)
 };
 
 // ---- block-source map ------------------------------------------------------------------------------
@@ -219,6 +220,11 @@ struct Ent {
     uint32_t lastpx;          // the pixel before the next run: the colour contexts are functions of it (screencap.cpp:371-372, 616-624)
     uint32_t sb;              // shared-memory base address
     uint32_t head;            // motion-vector copies posted so far
+    // v2 streams: range coder state (RangeCoderSub, sub.h:21-45) and the count tables
+    uint32_t rc_code, rc_range;
+    const uint8_t* rc_p;
+    uint32_t* v2;
+    int msr_x, msr_y;
     ModelState* m;
     int f0;
     int lane;
@@ -718,9 +724,149 @@ __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.c
     return px;
 }
 
+// ---- v2 streams: the range coder of ScreenPressor 2.x (decode compatibility) -----------------
+// Replaces RangeCoderSub::DecodeBegin / GetFreq / Decode / DecodeVal / DecodeValUni (sub.h:30-42, sub.cpp:44-61, 88-113,
+// 146-178) and UseRC's table set (screencap.h:105-265).  Every model is a plain count table cnt[maxc] + total with a
+// per-model increment; a symbol is found by cumulating the counts in index order.  DecodeValUni's 16 group sums only
+// accelerate that same search (they are kept consistent with the counts at all times), so colour bytes go through the
+// same routine and the group sums are not stored.  Tables live in the chain's state slot in global memory (12.6 MB);
+// this is a compatibility path for old files, written for exactness, not speed: the 32 lanes cumulate a table together.
+constexpr uint32_t RC_TOP = 1u << 24, RC_BOT = 1u << 16;                       // sub.h:15-18
+constexpr int V2_N = 0, V2_N2 = 6 * 257, V2_XX = V2_N2 + 257, V2_BT = V2_XX + 257, V2_SXY = V2_BT + 6, V2_MV = V2_SXY + 4 * 17,
+              V2_PT = V2_MV + 2 * 513, V2_C = 3200, V2_WORDS = V2_C + 3 * 4096 * 257;
+static_assert(V2_PT + 6 * 7 <= V2_C && (size_t)V2_WORDS * 4 <= sizeof(ModelState), "v2 tables fit a model state slot");
+__device__ __forceinline__ void rc_begin(Ent& e, const uint8_t* p) {  // DecodeBegin: five bytes, the first is the encoder's empty cache
+    e.rc_code = 0;
+    e.rc_range = 0xFFFFFFFFu;
+    for (int i = 0; i < 5; i++) e.rc_code = (e.rc_code << 8) | p[i];
+    e.rc_p = p + 5;
+}
+// DecodeVal(c, cnt, totfr = cnt[maxc], maxc, step).  CAP = 512 / 256 / 32 bounds maxc at compile time.
+template <int CAP>
+__device__ __noinline__ int rc_val(Ent& e, uint32_t* cnt, int maxc, uint32_t step) {
+    constexpr int PER = CAP / 32;
+    const int lane = e.lane;
+    uint32_t v[PER], sum = 0;
+    const uint32_t tot = cnt[maxc];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int idx = lane * PER + j;
+        v[j] = idx < maxc ? cnt[idx] : 0u;
+        sum += v[j];
+    }
+    const uint32_t r = e.rc_range / tot;      // GetFreq: code / (range /= totFreq)
+    const uint32_t value = e.rc_code / r;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl > value);
+    const int L = hit ? __ffs(hit) - 1 : (maxc - 1) / PER;  // a corrupt stream may point past the table: last symbol
+    uint32_t cum = incl - sum;
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < PER - 1; k++)
+        if (j == k && value >= cum + v[k] && lane * PER + k + 1 < maxc) {
+            cum += v[k];
+            j = k + 1;
+        }
+    uint32_t f = v[0];
+#pragma unroll
+    for (int k = 1; k < PER; k++)
+        if (j == k) f = v[k];
+    const int c = __shfl_sync(0xFFFFFFFFu, lane * PER + j, L);
+    cum = __shfl_sync(0xFFFFFFFFu, cum, L);
+    f = __shfl_sync(0xFFFFFFFFu, f, L);
+    // Decode (sub.cpp:49-61)
+    uint32_t code = e.rc_code - cum * r, range = r * f;
+    while (range < RC_TOP) {
+        code = (code << 8) | *e.rc_p++;
+        range <<= 8;
+    }
+    e.rc_code = code;
+    e.rc_range = range;
+    // count it; halve everything once the total passes 2^16 (sub.cpp:100-111)
+    if (tot + step > RC_BOT) {
+        uint32_t ns = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int idx = lane * PER + k;
+            if (idx < maxc) {
+                const uint32_t nv = ((v[k] + (idx == c ? step : 0u)) >> 1) + 1u;
+                cnt[idx] = nv;
+                ns += nv;
+            }
+        }
+        ns = __reduce_add_sync(0xFFFFFFFFu, ns);
+        if (lane == 0) cnt[maxc] = ns;
+    } else if (lane == 0) {
+        cnt[c] += step;
+        cnt[maxc] = tot + step;
+    }
+    __syncwarp();
+    return c;
+}
+// table t of the v4 numbering (0-5 ntab, 6 ntab2, 7 xx, 8 bt, 9-12 sxy, 13-14 mv, 15-20 ptype) in its v2 form
+template <int T>
+__device__ __forceinline__ int rc_fx(Ent& e) {
+    if (T < 6) return rc_val<256>(e, e.v2 + V2_N + T * 257, 256, 400);           // SC_NSTEP
+    if (T == 6) return rc_val<256>(e, e.v2 + V2_N2, 256, 20);                    // SC_BTNSTEP
+    if (T == 7) return rc_val<256>(e, e.v2 + V2_XX, 256, 1);                     // SC_XXSTEP
+    if (T == 8) return rc_val<32>(e, e.v2 + V2_BT, 5, 10);                       // SC_BTSTEP
+    if (T < 13) return rc_val<32>(e, e.v2 + V2_SXY + (T - 9) * 17, 16, 100);     // SC_SXYSTEP
+    if (T == 13) return rc_val<512>(e, e.v2 + V2_MV, 2 * e.msr_x, 100);          // SC_MSTEP
+    return rc_val<512>(e, e.v2 + V2_MV + 513, 2 * e.msr_y, 100);
+}
+__device__ __forceinline__ int rc_n(Ent& e, int ptype) { return rc_val<256>(e, e.v2 + V2_N + ptype * 257, 256, 400); }
+__device__ __forceinline__ uint32_t rc_rgb(Ent& e) {  // DecodeRGB with decodeC = DecodeValUni(cntab, step SC_STEP)
+    uint32_t px = 0;
+    uint32_t cx = (e.lastpx >> 18) & 63u, cx1 = (e.lastpx >> 4) & 0xFC0u;
+#pragma unroll 1
+    for (int ch = 0; ch < 3; ch++) {
+        const uint32_t v = (uint32_t)rc_val<256>(e, e.v2 + V2_C + (size_t)(ch * 4096 + (int)(cx + cx1)) * 257, 256, 400) & 255u;
+        cx1 = cx << 6;
+        cx = v >> 2;
+        px |= v << (8 * ch);
+    }
+    e.lastpx = px;
+    return px;
+}
+__device__ __forceinline__ int rc_run(Ent& e, int& ptype, uint32_t& c) {
+    ptype = rc_val<32>(e, e.v2 + V2_PT + ptype * 7, 6, 1000);  // SC_UNSTEP
+    if (!ptype) c = rc_rgb(e);
+    return rc_n(e, ptype);
+}
+__device__ void rc_renew(Ent& e) {  // RenewI for UseRC: every count 1, totals = table sizes (screencap.h:147-262)
+    for (int i = e.lane; i < V2_C; i += 32) e.v2[i] = 1u;
+    __syncwarp();
+    if (e.lane == 0) {
+        for (int t = 0; t < 6; t++) e.v2[V2_N + t * 257 + 256] = 256u;
+        e.v2[V2_N2 + 256] = 256u;
+        e.v2[V2_XX + 256] = 256u;
+        e.v2[V2_BT + 5] = 5u;
+        for (int k = 0; k < 4; k++) e.v2[V2_SXY + k * 17 + 16] = 16u;
+        e.v2[V2_MV + 2 * e.msr_x] = 2u * (uint32_t)e.msr_x;
+        e.v2[V2_MV + 513 + 2 * e.msr_y] = 2u * (uint32_t)e.msr_y;
+        for (int l = 0; l < 6; l++) e.v2[V2_PT + l * 7 + 6] = 6u;
+    }
+    for (int i = e.lane; i < 3 * 4096 * 257; i += 32) e.v2[V2_C + i] = (i % 257 == 256) ? 256u : 1u;
+    __syncwarp();
+}
+
+// ---- the parse below is shared by both stream generations: these pick the coder ---------------------------------------
+template <bool V2, int NSYM, int T>
+__device__ __forceinline__ int sym_fx(Ent& e) {
+    if (V2) return rc_fx<T>(e);
+    return dec_fxc<NSYM, T>(e);
+}
+
 // the symbols of one pixel run: type, colour of a literal, length (screencap.cpp:478-486, 1400-1412).  At most five
 // symbols: when the rANS block cannot end within them they are counted with one subtraction.
+template <bool V2 = false>
 __device__ __forceinline__ int dec_run(Ent& e, int& ptype, uint32_t& c) {
+    if (V2) return rc_run(e, ptype, c);
     int n;
     if (e.nleft > 8) {
         ptype = dec_ptype<false>(e, ptype);
@@ -784,6 +930,7 @@ __device__ __forceinline__ uint32_t tl_at(const uint8_t* frame, const Geo& g, IP
     return tl_padded(frame, g, p.y);
 }
 
+template <bool V2>
 __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     const Geo& g = w.g;
     const int X = g.X, Y = g.Y;
@@ -794,8 +941,8 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     uint32_t lastv = 0;  // the pixel before p in raster order
     // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
     while (hdr > 0) {
-        const uint32_t c = dec_rgb(e);
-        const int n = dec_n(e, 0);
+        const uint32_t c = V2 ? rc_rgb(e) : dec_rgb(e);
+        const int n = V2 ? rc_n(e, 0) : dec_n(e, 0);
         if (n <= 0) return;
         for (int i = lane; i < n; i += 32) {
             const IPos q = ipos_add(p, i, X);
@@ -808,7 +955,7 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
     __syncwarp();
     while (p.y < Y) {
         uint32_t c = lastv;  // type 1: the previous pixel in raster order, whatever the row
-        const int n = dec_run(e, ptype, c);
+        const int n = dec_run<V2>(e, ptype, c);
         if (n <= 0) return;
         PROF_T0
         if (ptype == 0 || ptype == 1) {
@@ -958,22 +1105,22 @@ __device__ __forceinline__ void cmd_drain(Ent& e) {
 // ---- P frame (DecompressP, screencap.cpp:1275-1432) ------------------------------------------------
 __device__ __forceinline__ uint32_t tile_at(uint32_t tb, int ty, int tx) { return lds32(tb + (uint32_t)(ty * 17 + tx) * 4u); }
 
-template <bool SM>
+template <bool SM, bool V2>
 __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint8_t* frame, int f, int lane) {
     const Geo& g = w.g;
     const uint32_t tb = e.sb + S_TILE, btsb = e.sb + S_BTS;
 #ifdef SCPR_PROF
     const long long thdr__ = clock64();
 #endif
-    int t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
-    const int xx1 = (dec_fxc<256, CX_XX - CX_NTAB>(e) << 8) + t0;
-    t0 = dec_fxc<256, CX_XX - CX_NTAB>(e);
-    int xx2 = (dec_fxc<256, CX_XX - CX_NTAB>(e) << 8) + t0;
+    int t0 = sym_fx<V2, 256, CX_XX - CX_NTAB>(e);
+    const int xx1 = (sym_fx<V2, 256, CX_XX - CX_NTAB>(e) << 8) + t0;
+    t0 = sym_fx<V2, 256, CX_XX - CX_NTAB>(e);
+    int xx2 = (sym_fx<V2, 256, CX_XX - CX_NTAB>(e) << 8) + t0;
     if (xx2 >= g.nb) xx2 = g.nb - 1;  // corrupt input guard
     // block types of [xx1, xx2] as (type, run) pairs (screencap.cpp:1306-1313)
     for (int x = xx1; x <= xx2;) {
-        const int c = dec_fxc<5, CX_BT - CX_NTAB>(e);
-        const int n = dec_fxc<256, CX_NTAB2 - CX_NTAB>(e);
+        const int c = sym_fx<V2, 5, CX_BT - CX_NTAB>(e);
+        const int n = sym_fx<V2, 256, CX_NTAB2 - CX_NTAB>(e);
         if (n <= 0) break;
         for (int i = lane; i < n && x + i < g.nb; i += 32) sts8(btsb + x + i, c);
         x += n;
@@ -1003,17 +1150,20 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             // ---- motion-vector block: decode its symbols, post the copy (screencap.cpp:1333-1368)
             PROF_T0
             if ((bt - 1) & 1) {
-                x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
-                y1 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 1>(e);
-                x2 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 2>(e) + 1;
-                y2 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 3>(e) + 1;
+                x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
+                y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
+                x2 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) + 1;
+                y2 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) + 1;
                 if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
                 if (y2 > by0 + bh) y2 = by0 + bh;
                 if (x1 >= x2) x1 = x2 - 1;
                 if (y1 >= y2) y1 = y2 - 1;
             }
             int mx = lastmx, my = lastmy;
-            if (!dec_bool(e)) {
+            if (V2) {  // no repeat flag before v3, vectors offset by the stream's own motion range (screencap.cpp:1358-1361)
+                mx = rc_fx<13>(e) - e.msr_x;
+                my = rc_fx<14>(e) - e.msr_y;
+            } else if (!dec_bool(e)) {
                 mx = dec_fxc<512, CX_MV - CX_NTAB + 0>(e) - 256;
                 my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
             }
@@ -1049,10 +1199,10 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             }
           PROF_ADD(c_tile) }
         if ((bt - 1) & 1) {
-            x1 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 0>(e);
-            y1 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 1>(e);
-            x2 = bx0 + dec_fxc<16, CX_SXY - CX_NTAB + 2>(e) + 1;
-            y2 = by0 + dec_fxc<16, CX_SXY - CX_NTAB + 3>(e) + 1;
+            x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
+            y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
+            x2 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) + 1;
+            y2 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) + 1;
             if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
             if (y2 > by0 + bh) y2 = by0 + bh;
             if (x1 >= x2) x1 = x2 - 1;
@@ -1079,7 +1229,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             uint32_t ca = tb + (uint32_t)(oy * 17 + ox) * 4u;       // ... and its tile address
             while (pos < npx) {
                 uint32_t c = 0;
-                int n = dec_run(e, ptype, c);
+                int n = dec_run<V2>(e, ptype, c);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
                 const int xe = xx0 + n;
@@ -1172,7 +1322,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
 
 // One CTA per chain: warp 0 walks the chain, the other warps copy motion-vector blocks (warp 4 shares warp 0's
 // scheduler and leaves at once).
-template <bool SM>
+template <bool SM, bool V2>
 __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     extern __shared__ __align__(16) uint8_t s_mem[];
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_mem);
@@ -1202,10 +1352,16 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     e.wp = nullptr;
     e.sb = sb;
     e.lane = lane;
+    e.v2 = reinterpret_cast<uint32_t*>(e.m);
+    e.msr_x = w.msr_x;
+    e.msr_y = w.msr_y;
+    e.rc_code = e.rc_range = 0;
+    e.rc_p = nullptr;
 #ifdef SCPR_PROF
     const long long tk0 = clock64();
 #endif
     // fixed tables and context kinds of the chain's model state -> shared memory (a renewing first frame overwrites them)
+    if (!V2)
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         const FixedState& g0 = e.m->fx[t];
         const int off = fx_off(t), nsym = fixed_nsym(CX_NTAB + t);
@@ -1214,16 +1370,19 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
             sts32(sb + S_FC + (off + i) * 4, ((uint32_t)g0.freq[i] << 16) | g0.cum[i]);
         }
     }
-    for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, reinterpret_cast<const uint32_t*>(e.m->kmap)[i]);
-    for (int i = lane; i < NCACHE; i += 32) sts32(sb + S_CTAG + 4 * i, 0xFFFFFFFFu);
-    __syncwarp();
-    for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
+    if (!V2) {
+        for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, reinterpret_cast<const uint32_t*>(e.m->kmap)[i]);
+        for (int i = lane; i < NCACHE; i += 32) sts32(sb + S_CTAG + 4 * i, 0xFFFFFFFFu);
+        __syncwarp();
+        for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
+    }
     for (int f = ch.first; f < ch.first + ch.count; f++) {
         const DecFrame df = w.frames[f];
         uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
         if (df.kind == DK_PSAME) continue;  // every block keeps its source (memcpy(pDst, prev), screencap.cpp:1288-1291)
         if (df.kind == DK_FLAT || df.kind == DK_I) {
-            if (df.kind == DK_I || df.renew) {  // RenewI
+            if (V2 && (df.kind == DK_I || df.renew)) rc_renew(e);
+            if (!V2 && (df.kind == DK_I || df.renew)) {  // RenewI
                 for (int i = lane; i < NUM_COLOR_CX; i += 32) e.m->color[i].kind = 0;
                 for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) sts32(sb + S_KMAP + 4 * i, 0);
                 for (int i = lane; i < NCACHE; i += 32) sts32(sb + S_CTAG + 4 * i, 0xFFFFFFFFu);  // cached contexts are void
@@ -1243,18 +1402,26 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
             for (int i = lane; i < g.nb; i += 32) map.write(i, code);  // the whole frame is new
             __syncwarp();
             if (df.kind == DK_I) {
-                rd_seek(e, w.stream + df.src_off + 1);
-                e.nleft = RANS_BLOCK;
                 e.lastpx = 0;
-                rdec_init(e);
-                decode_i(w, e, frame, lane);
+                if (V2)
+                    rc_begin(e, w.stream + df.src_off + 1);
+                else {
+                    rd_seek(e, w.stream + df.src_off + 1);
+                    e.nleft = RANS_BLOCK;
+                    rdec_init(e);
+                }
+                decode_i<V2>(w, e, frame, lane);
             }
             continue;
         }
-        rd_seek(e, w.stream + df.src_off + 1);
-        e.nleft = RANS_BLOCK;
-        rdec_init(e);
-        decode_p<SM>(w, map, e, frame, f, lane);
+        if (V2)
+            rc_begin(e, w.stream + df.src_off + 1);
+        else {
+            rd_seek(e, w.stream + df.src_off + 1);
+            e.nleft = RANS_BLOCK;
+            rdec_init(e);
+        }
+        decode_p<SM, V2>(w, map, e, frame, f, lane);
         __threadfence_block();
     }
     cmd_drain(e);
@@ -1267,8 +1434,9 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
                e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6);
 #endif
-    // leave the cached contexts, the fixed tables and the kinds behind for the next call
+    // leave the cached contexts, the fixed tables and the kinds behind for the next call (v2 tables are already in place)
     __syncwarp();
+    if (!V2) {
     for (uint32_t h = 0; h < NCACHE; h++) cache_writeback(e.m, sb, lane, h);
     for (int t = 0; t < NUM_FIXED_CX; t++) {
         FixedState& g0 = e.m->fx[t];
@@ -1288,6 +1456,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
         }
     }
     for (int i = lane; i < NUM_COLOR_CX / 4; i += 32) reinterpret_cast<uint32_t*>(e.m->kmap)[i] = lds32(sb + S_KMAP + 4 * i);
+    }
 }
 
 // source frame of every block of every frame: thread per block, frames in order
@@ -1401,7 +1570,11 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
         if (!c->dec_created) {
             if (ftypes[f] > 0) return 0;  // P frame before any I frame
             const int version = (s[0] >> 4) + 1;
-            if (version != 3 && version != 4) return -version;  // BadVersionException; v2 = range coder, out of scope
+            if (version < 2 || version > 4) return -version;  // BadVersionException (screencap.cpp:1589-1590)
+            if (version == 2 && (c->p.high_range_x < 1 || c->p.high_range_x > 256 || c->p.high_range_y < 1 || c->p.high_range_y > 256)) {
+                set_error("v2 stream: motion range %u x %u outside 1..256", c->p.high_range_x, c->p.high_range_y);
+                return SCPR_E_UNSUPPORTED;
+            }
             c->dec_version = version;
             c->dec_created = true;
         }
@@ -1482,15 +1655,21 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.upd = ws + map_bytes;
     w.fill_src = (int16_t*)(ws + map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
     w.n = n;
+    w.msr_x = (int)c->p.high_range_x;
+    w.msr_y = (int)c->p.high_range_y;
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
     StageTimer tm(st);
-    if (map_shared) {
-        CK(cudaFuncSetAttribute(k_dec_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dec_chain<true><<<n_chains, 32 * DEC_WARPS, smem, st>>>(w);
-    } else {
-        CK(cudaFuncSetAttribute(k_dec_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dec_chain<false><<<n_chains, 32 * DEC_WARPS, smem, st>>>(w);
-    }
+    const bool v2 = c->dec_version == 2;
+#define LAUNCH_CHAIN(SMV, V2V)                                                                                      \
+    do {                                                                                                            \
+        CK(cudaFuncSetAttribute(k_dec_chain<SMV, V2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        k_dec_chain<SMV, V2V><<<n_chains, 32 * DEC_WARPS, smem, st>>>(w);                                           \
+    } while (0)
+    if (map_shared && !v2) LAUNCH_CHAIN(true, false);
+    else if (!map_shared && !v2) LAUNCH_CHAIN(false, false);
+    else if (map_shared) LAUNCH_CHAIN(true, true);
+    else LAUNCH_CHAIN(false, true);
+#undef LAUNCH_CHAIN
     tm.mark("chain");
     k_dec_sources<<<(g.nb + 127) / 128, 128, 0, st>>>(w);
     const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
@@ -1507,6 +1686,21 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
 // any number of frames: launches of at most DEC_MAX_FRAMES frames (the open chain carries over, as between calls)
 static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
                         int pitch) {
+    if (c->rgb16) {  // decode to RGB24 on the device, then put the 16-bit words together (screencap.cpp:1726-1734)
+        if (pitch < c->g.X * 2) return SCPR_E_PARAM;
+        CK(cudaSetDevice(c->device));
+        uint8_t* const d16 = d_out;
+        for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
+            const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
+            TRY(c->dec24.ensure((size_t)m * c->g.frame_bytes));
+            const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, (uint8_t*)c->dec24.p, c->g.pitch);
+            if (r != 1) return r;
+            launch_pack16((const uint8_t*)c->dec24.p, d16 + (size_t)f0 * pitch * c->g.Y, m, c->g, pitch, c->m16, c->st, &c->launches);
+            CK(cudaStreamSynchronize(c->st));
+            for (int f = f0; f < f0 + m; f++) stream += sizes[f];
+        }
+        return 1;
+    }
     const size_t frame_bytes = (size_t)pitch * c->g.Y;
     for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
         const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
@@ -1533,7 +1727,7 @@ int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* s
     const size_t bytes = (size_t)n * pitch * c->g.Y;
     TRY(c->dec_frames.ensure(bytes));
     // row padding of the caller's buffer is not produced by the kernels: start from zeros
-    if (pitch != c->g.X * c->g.bpp) CK(cudaMemsetAsync(c->dec_frames.p, 0, bytes, c->st));
+    if (pitch != c->g.X * (c->rgb16 ? 2 : c->g.bpp)) CK(cudaMemsetAsync(c->dec_frames.p, 0, bytes, c->st));
     const int r = decode_batch(c, stream, sizes, ftypes, n, (uint8_t*)c->dec_frames.p, pitch);
     if (r != 1) return r;
     CK(cudaMemcpyAsync(frames, c->dec_frames.p, bytes, cudaMemcpyDeviceToHost, c->st));

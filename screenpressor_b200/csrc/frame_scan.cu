@@ -252,6 +252,48 @@ void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const
     }
 }
 
+// ---- 16 bpp input / output (ScreenCodec::CompressFrame, screencap.cpp:1665-1678; DecompressFrame, :1726-1734) --------
+// The codec proper only knows RGB24.  A 16-bit pixel is split with the caller's channel masks into three *unscaled*
+// bytes (5- or 6-bit values), rows of the RGB24 image are padded with zeros to a multiple of four bytes; decoding puts
+// the three bytes back with the same shifts.  One thread per pixel pair keeps the 16-bit side 32-bit coalesced.
+__global__ void k_unpack16(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, Geo g, Rgb16 m) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = g.pitch;  // one thread per output byte column group of 3 (pixel) + padding bytes
+    const long rows = (long)n * g.Y;
+    const long row = t / per_row;
+    if (row >= rows) return;
+    const int col = (int)(t - row * per_row);
+    const int f = (int)(row / g.Y), y = (int)(row - (long)f * g.Y);
+    uint8_t v = 0;
+    if (col < 3 * g.X) {
+        const int x = col / 3, ch = col - 3 * x;
+        const uint16_t w = *reinterpret_cast<const uint16_t*>(src + ((size_t)f * g.Y + y) * (size_t)(2 * g.X) + 2 * (size_t)x);
+        v = ch == 0 ? (uint8_t)((w & m.rmask) >> m.rshift) : ch == 1 ? (uint8_t)((w & m.gmask) >> m.gshift) : (uint8_t)((w & m.bmask) >> m.bshift);
+    }
+    dst[(size_t)f * g.frame_bytes + (size_t)y * g.pitch + col] = v;
+}
+__global__ void k_pack16(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, Geo g, int out_pitch, Rgb16 m) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long px = (long)n * g.Y * g.X;
+    if (t >= px) return;
+    const int x = (int)(t % g.X);
+    const long row = t / g.X;
+    const int f = (int)(row / g.Y), y = (int)(row - (long)f * g.Y);
+    const uint8_t* p = src + (size_t)f * g.frame_bytes + (size_t)y * g.pitch + 3 * (size_t)x;
+    const uint32_t w = ((uint32_t)p[0] << m.rshift) + ((uint32_t)p[1] << m.gshift) + ((uint32_t)p[2] << m.bshift);
+    *reinterpret_cast<uint16_t*>(dst + ((size_t)f * g.Y + y) * (size_t)out_pitch + 2 * (size_t)x) = (uint16_t)w;
+}
+void launch_unpack16(const uint8_t* src16, uint8_t* dst24, int n, const Geo& g, const Rgb16& m, cudaStream_t st, uint64_t* launches) {
+    const long total = (long)n * g.Y * g.pitch;
+    k_unpack16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src16, dst24, n, g, m);
+    ++*launches;
+}
+void launch_pack16(const uint8_t* src24, uint8_t* dst16, int n, const Geo& g, int out_pitch, const Rgb16& m, cudaStream_t st, uint64_t* launches) {
+    const long total = (long)n * g.Y * g.X;
+    k_pack16<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src24, dst16, n, g, out_pitch, m);
+    ++*launches;
+}
+
 void launch_compact_changed(const uint32_t* blkinfo, const uint8_t* ftype, int n, const Geo& g, uint32_t* chg_list,
                             PFrameHdr* hdr, cudaStream_t st, uint64_t* launches) {
     k_compact_changed<<<n, 256, 0, st>>>(blkinfo, ftype, g, chg_list, hdr);

@@ -66,6 +66,13 @@ struct RansBlk {
 void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
                        FrameSummary* summary, cudaStream_t st, uint64_t* launches);
 void launch_apply_loss(uint8_t* frames, int n, const Geo& g, const FrameSummary* summary, int loss, cudaStream_t st, uint64_t* launches);
+// 16 bpp <-> RGB24 (channel masks of CodecParameters; shifts = position of each mask's lowest set bit, screencap.cpp:1575-1583)
+struct Rgb16 {
+    uint32_t rmask, gmask, bmask;
+    int rshift, gshift, bshift;
+};
+void launch_unpack16(const uint8_t* src16, uint8_t* dst24, int n, const Geo& g, const Rgb16& m, cudaStream_t st, uint64_t* launches);
+void launch_pack16(const uint8_t* src24, uint8_t* dst16, int n, const Geo& g, int out_pitch, const Rgb16& m, cudaStream_t st, uint64_t* launches);
 void launch_compact_changed(const uint32_t* blkinfo, const uint8_t* ftype, int n, const Geo& g, uint32_t* chg_list,
                             PFrameHdr* hdr, cudaStream_t st, uint64_t* launches);
 

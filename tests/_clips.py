@@ -78,3 +78,27 @@ def fuzz_clip(w: int, h: int, n: int, seed: int, bpp: int = 32, levels: int = 25
             fr[:, : w * 3] = rgb.reshape(h, w * 3)
         out.append(fr)
     return np.stack(out), keys
+
+
+def motion_clip(w: int, h: int, n: int, seed: int):
+    """noise-textured window dragged over a textured desktop and dropped now and then: many motion-vector blocks next
+    to pixel-coded ones, and non-zero vectors left behind in the reference's persistent mvs[] array (32 bpp)."""
+    rng = np.random.default_rng(seed)
+    bg = rng.integers(0, 4, (h, w, 1), dtype=np.uint8) * 60 + np.zeros((1, 1, 3), np.uint8)
+    win = rng.integers(0, 256, (h // 3, w // 3, 3), dtype=np.uint8)
+    clip = np.zeros((n, h, w, 4), np.uint8)
+    clip[..., 3] = 255
+    for i in range(n):
+        f = bg.copy()
+        x, y = (16 + 5 * i) % (w - w // 3 - 1), (8 + 3 * i) % (h - h // 3 - 1)
+        if i % 12 < 9:
+            f[y:y + h // 3, x:x + w // 3] = win
+        f[(7 * i) % h, (11 * i) % w] = (i, 255 - i, 3 * i % 256)
+        clip[i, ..., :3] = f
+    return clip
+
+
+def to_rgb555(clip32: np.ndarray) -> np.ndarray:
+    """(n, h, w, 4) BGRA bytes -> (n, h, w) uint16 words, 5 bits per channel under the masks 0x7C00 / 0x3E0 / 0x1F"""
+    c = clip32.astype(np.uint16)
+    return ((c[..., 0] >> 3) << 10) | ((c[..., 1] >> 3) << 5) | (c[..., 2] >> 3)

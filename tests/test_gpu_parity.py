@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import _golden
-from _clips import fuzz_clip
+from _clips import fuzz_clip, motion_clip
 
 pytestmark = pytest.mark.gpu
 
@@ -210,30 +210,13 @@ def test_lossy_modes_match_oracle(scpr, oracle_built, loss):
             assert np.array_equal(dec.DecompressFrame(data, None, ft), dorc.decompress(data, ft)), (loss, i)
 
 
-def _motion_clip(w, h, n, seed):
-    """noise-textured window dragged over a textured desktop, then dropped: leaves non-zero vectors in mvs[]"""
-    rng = np.random.default_rng(seed)
-    bg = rng.integers(0, 4, (h, w, 1), dtype=np.uint8) * 60 + np.zeros((1, 1, 3), np.uint8)
-    win = rng.integers(0, 256, (h // 3, w // 3, 3), dtype=np.uint8)
-    clip = np.zeros((n, h, w, 4), np.uint8)
-    clip[..., 3] = 255
-    for i in range(n):
-        f = bg.copy()
-        x, y = (16 + 5 * i) % (w - w // 3 - 1), (8 + 3 * i) % (h - h // 3 - 1)
-        if i % 12 < 9:
-            f[y:y + h // 3, x:x + w // 3] = win
-        f[(7 * i) % h, (11 * i) % w] = (i, 255 - i, 3 * i % 256)
-        clip[i, ..., :3] = f
-    return clip
-
-
 def test_frame_range_sharding_is_byte_identical(scpr):
     """a clip cut at keyframes and encoded by different codec objects equals the single-codec stream once
     the persistent mvs[] array is handed over -- serially, and pipelined through the resolve hooks"""
     from screenpressor_b200 import shard
 
     w, h, n = 320, 192, 48
-    clip = _motion_clip(w, h, n, 5)
+    clip = motion_clip(w, h, n, 5)
     keys = np.zeros(n, np.uint8)
     keys[[0, 13, 30]] = 1
     whole = _split(*_new(scpr, w, h, 32).CompressClip(clip, keys))
@@ -293,6 +276,69 @@ def test_full_state_checkpoint_resume_at_any_frame(scpr):
         _new(scpr, w + 16, h, 32).ImportRangeState(blob)
 
 
+def _legacy_cases():
+    import os
+
+    path = os.path.join(_golden.GOLDEN_DIR, "legacy_streams.npz")
+    st = np.load(path)
+    return st, sorted({"/".join(k.split("/")[:2]) for k in st.files})
+
+
+@pytest.mark.parametrize("version", [3, 2])
+def test_decodes_legacy_stream_generations(scpr, version):
+    """old files: v3 (same ANS coder, Cx6 start frequency 64) and v2 (range coder, no MV-repeat flag) streams written by
+    the reference itself (tests/golden/make_legacy_golden.py) decode to the source clips, per frame and per clip"""
+    import sys
+    sys.path.insert(0, _golden.GOLDEN_DIR)
+    import make_legacy_golden as mk
+
+    st, keys = _legacy_cases()
+    cases = mk.cases()
+    seen = 0
+    for key in keys:
+        ver, name = key.split("/")
+        if ver != f"v{version}":
+            continue
+        w, h, bpp, clip, _ = cases[name]
+        data, sizes, types = st[key + "/data"], st[key + "/sizes"].astype(np.uint32), st[key + "/types"]
+        assert data[0] == 2 + (version - 1) * 16
+        out = _new(scpr, w, h, bpp).DecompressClip(data, sizes, types)
+        assert np.array_equal(out.reshape(len(clip), -1), clip.reshape(len(clip), -1)), key
+        dec, pos = _new(scpr, w, h, bpp), 0
+        for i in range(len(clip)):
+            fr = dec.DecompressFrame(bytes(data[pos:pos + int(sizes[i])]), None, int(types[i]))
+            assert np.array_equal(fr, np.ascontiguousarray(clip[i]).reshape(-1)), (key, i)
+            pos += int(sizes[i])
+        seen += 1
+    assert seen == 5
+
+
+def test_rgb16_clients_match_reference(scpr):
+    """16 bpp frames (5-5-5 masks): bitstream bytes equal the reference's, decode returns the words, any output pitch"""
+    import sys
+    sys.path.insert(0, _golden.GOLDEN_DIR)
+    import make_legacy_golden as mk
+
+    st, _ = _legacy_cases()
+    for name, (w, h, bpp, clip, keys) in mk.cases16().items():
+        key = "v4rgb16/" + name
+        data, sizes, types = st[key + "/data"], st[key + "/sizes"].astype(np.uint32), st[key + "/types"]
+        n = len(clip)
+        enc = _new(scpr, w, h, 16)
+        stream, gsizes, gtypes = enc.CompressClip(clip.view(np.uint8).reshape(n, -1), keys)
+        assert np.array_equal(gsizes, sizes) and np.array_equal(gtypes, types) and np.array_equal(stream, data), name
+        enc2, pos = _new(scpr, w, h, 16), 0
+        for i in range(n):   # the per-frame drop-in call
+            d, ft = enc2.CompressFrame(clip[i].view(np.uint8).reshape(-1), 0 if keys[i] else 1)
+            assert d == bytes(data[pos:pos + int(sizes[i])]) and ft == types[i], (name, i)
+            pos += int(sizes[i])
+        out = _new(scpr, w, h, 16).DecompressClip(data, sizes, types)
+        assert np.array_equal(out.view(np.uint16).reshape(clip.shape), clip), name
+        pitch = (w * 2 + 3 & ~3) + 8
+        out = _new(scpr, w, h, 16).DecompressClip(data, sizes, types, pitch=pitch)
+        assert np.array_equal(out.reshape(n, h, pitch)[:, :, : 2 * w].copy().view(np.uint16), clip), name
+
+
 def test_error_behaviour(scpr):
     dec = _new(scpr, 64, 48, 32)
     with pytest.raises(scpr.ScprError):          # P before any I: the reference returns 0 (screencap.cpp:1699)
@@ -300,12 +346,12 @@ def test_error_behaviour(scpr):
     with pytest.raises(scpr.BadVersionException) as e:   # version nibble 7 -> BadVersionException(8)
         dec.DecompressFrame(b"\x72abcdefgh", None, 0)
     assert e.value.version == 8
-    with pytest.raises(scpr.BadVersionException) as e:   # v2 range-coder stream: out of scope here
-        dec.DecompressFrame(b"\x12abcdefgh", None, 0)
-    assert e.value.version == 2
+    with pytest.raises(scpr.BadVersionException) as e:   # version nibble 0 -> BadVersionException(1): the pre-2.0 coder
+        dec.DecompressFrame(b"\x02abcdefgh", None, 0)
+    assert e.value.version == 1
     sc = scpr.ScreenCodec(0)
-    with pytest.raises(scpr.ScprError):
-        sc.Init(scpr.CodecParameters(64, 48, 16))
+    with pytest.raises(scpr.ScprError):          # BadVersionException(48) in the reference (screencap.cpp:1607-1609)
+        sc.Init(scpr.CodecParameters(64, 48, 8))
 
 
 def test_smoke_entry(scpr):

@@ -67,3 +67,35 @@ def test_stage_hooks_reproduce_frame_bytes(oracle_built):
     lib.orc_rans_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     sz = lib.orc_rans_encode(fq.ctypes.data, n, out.ctypes.data)
     assert data[0] == 0x32 and bytes(out[:sz]) == data[1:]
+
+
+def test_legacy_generation_fixtures(oracle_built):
+    """tests/golden/legacy_streams.npz (v3 and v2 streams written by the reference): the C oracle decodes the v3 ones
+    (same ANS coder, f0 = 64), and the compiled reference -- when oracle/_ref is present -- decodes both generations.
+    The CUDA decoder is checked against the same fixtures in tests/test_gpu_parity.py."""
+    import os
+    import sys
+
+    sys.path.insert(0, _golden.GOLDEN_DIR)
+    import make_legacy_golden as mk
+
+    st = np.load(os.path.join(_golden.GOLDEN_DIR, "legacy_streams.npz"))
+    cases = mk.cases()
+    keys = sorted({"/".join(k.split("/")[:2]) for k in st.files if k.startswith(("v2/", "v3/"))})
+    assert len(keys) == 10
+    for key in keys:
+        ver, name = key.split("/")
+        w, h, bpp, clip, _ = cases[name]
+        data, sizes, types = st[key + "/data"].tobytes(), st[key + "/sizes"], st[key + "/types"]
+        assert data[0] == 2 + (int(ver[1]) - 1) * 16
+        decs = []
+        if ver == "v3":
+            decs.append(oracle_built.OracleCodec(w, h, bpp))
+        if oracle_built.have_ref():
+            decs.append(oracle_built.RefCodec(w, h, bpp))
+        for dec in decs:
+            pos = 0
+            for i in range(len(clip)):
+                out = dec.decompress(data[pos:pos + int(sizes[i])], int(types[i]))
+                assert np.array_equal(out, np.ascontiguousarray(clip[i]).reshape(-1)), (key, i, type(dec).__name__)
+                pos += int(sizes[i])
