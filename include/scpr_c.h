@@ -107,6 +107,43 @@ size_t scpr_range_state_size(const scpr_codec* c, int full);
 int64_t scpr_export_range_state(scpr_codec* c, uint8_t* blob, size_t cap, int full);   /* bytes written or < 0 */
 int scpr_import_range_state(scpr_codec* c, const uint8_t* blob, size_t len);
 
+/* ---- host layer above the codec object: VfW policy and the AVI container (csrc/vfw_host.cpp) -------------------
+ * What CodecInst does around ScreenCodec (screenpressor.cpp:343-437, 579-620), for hosts that are not VfW. */
+typedef struct scpr_policy {
+    int force_interval;   /* 1: a keyframe every kf_interval frames, host requests ignored (Configuration::ForceInterval, default 1) */
+    int kf_interval;      /* default 500 (conf.h:7) */
+    int force_loss;       /* 1: always conf_loss; 0: derived from the host's quality value (default 1) */
+    int conf_loss;        /* bits of loss, default 0 */
+} scpr_policy;
+typedef struct scpr_session scpr_session;
+void scpr_policy_default(scpr_policy* p);
+int scpr_quality_to_loss(uint32_t quality);                          /* 0..10000 -> 4..0 bits (screenpressor.cpp:410-422) */
+int scpr_infer_frame_type(uint8_t first_byte, uint32_t data_size);   /* 0 = I, 1 = P, -1 = cannot tell (screenpressor.cpp:579-589) */
+int scpr_session_create(const scpr_params* p, int device, const scpr_policy* policy /* NULL = defaults */, scpr_session** out);
+void scpr_session_destroy(scpr_session* s);
+/* CodecInst::Compress: frame type from the policy (and host_keyframe = ICCOMPRESS_KEYFRAME when the interval is not forced),
+ * loss from the policy or quality, then scpr_compress_frame.  *is_key = the AVIIF_KEYFRAME flag of the chunk. */
+int scpr_session_compress(scpr_session* s, const uint8_t* src, uint8_t* dst, int dst_cap, int host_keyframe, uint32_t quality, int* is_key);
+/* CodecInst::Decompress: not_keyframe = ICDECOMPRESS_NOTKEYFRAME; overridden by what the data itself says. */
+int scpr_session_decompress(scpr_session* s, const uint8_t* src, int src_len, uint8_t* dst, int pitch, int not_keyframe);
+
+/* RIFF AVI (1.0, < 4 GB) with one video stream, handler / biCompression 'SCPR' (screenpressor.h:6), '00dc' chunks and an
+ * 'idx1' index carrying AVIIF_KEYFRAME: the files VfW hosts write with the reference codec, and read with it. */
+typedef struct scpr_avi_info {
+    uint32_t width, height, bits_per_pixel;      /* of the uncompressed frames (16 / 24 / 32) */
+    uint32_t redmask, greenmask, bluemask;       /* 16 bpp: stored after the BITMAPINFOHEADER (screenpressor.cpp:318-336) */
+    uint32_t fps_num, fps_den;
+    uint32_t frames;                             /* reader: number of video chunks */
+    uint32_t fourcc;                             /* reader: biCompression of the stream ('SCPR' = 0x52504353) */
+} scpr_avi_info;
+typedef struct scpr_avi scpr_avi;
+int scpr_avi_create(const char* path, const scpr_avi_info* info, scpr_avi** out);
+int scpr_avi_write_frame(scpr_avi* a, const uint8_t* data, uint32_t len, int is_key);
+int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info);
+/* buf = NULL: returns the chunk size.  *is_key from the index (0 when the file has none). */
+int64_t scpr_avi_read_frame(scpr_avi* a, uint32_t i, uint8_t* buf, size_t cap, int* is_key);
+int scpr_avi_close(scpr_avi* a);   /* writer: appends the index and patches the headers */
+
 /* ---- plumbing ------------------------------------------------------------------------------ */
 /* CUDA stream (cudaStream_t) all kernels of this codec are launched on; default: the legacy stream. */
 int scpr_set_stream(scpr_codec* c, void* cuda_stream);

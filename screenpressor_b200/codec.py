@@ -48,6 +48,16 @@ class _Params(C.Structure):
     ]
 
 
+class _Policy(C.Structure):
+    _fields_ = [("force_interval", C.c_int), ("kf_interval", C.c_int), ("force_loss", C.c_int), ("conf_loss", C.c_int)]
+
+
+class _AviInfo(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("bits_per_pixel", C.c_uint32), ("redmask", C.c_uint32),
+                ("greenmask", C.c_uint32), ("bluemask", C.c_uint32), ("fps_num", C.c_uint32), ("fps_den", C.c_uint32),
+                ("frames", C.c_uint32), ("fourcc", C.c_uint32)]
+
+
 @dataclass
 class CodecParameters:
     """reference screencap.h:49-55; defaults from screenpressor.cpp:374-379"""
@@ -114,6 +124,30 @@ def load_library() -> C.CDLL:
     lib.scpr_import_range_state.argtypes = [vp, vp, C.c_size_t]
     lib.scpr_set_mvs_hooks.restype = i32
     lib.scpr_set_mvs_hooks.argtypes = [vp, vp, vp, vp]
+    lib.scpr_quality_to_loss.restype = i32
+    lib.scpr_quality_to_loss.argtypes = [C.c_uint32]
+    lib.scpr_infer_frame_type.restype = i32
+    lib.scpr_infer_frame_type.argtypes = [C.c_uint8, C.c_uint32]
+    lib.scpr_policy_default.restype = None
+    lib.scpr_policy_default.argtypes = [C.POINTER(_Policy)]
+    lib.scpr_session_create.restype = i32
+    lib.scpr_session_create.argtypes = [C.POINTER(_Params), i32, C.POINTER(_Policy), C.POINTER(vp)]
+    lib.scpr_session_destroy.restype = None
+    lib.scpr_session_destroy.argtypes = [vp]
+    lib.scpr_session_compress.restype = i32
+    lib.scpr_session_compress.argtypes = [vp, vp, vp, i32, i32, C.c_uint32, C.POINTER(i32)]
+    lib.scpr_session_decompress.restype = i32
+    lib.scpr_session_decompress.argtypes = [vp, vp, i32, vp, i32, i32]
+    lib.scpr_avi_create.restype = i32
+    lib.scpr_avi_create.argtypes = [C.c_char_p, C.POINTER(_AviInfo), C.POINTER(vp)]
+    lib.scpr_avi_write_frame.restype = i32
+    lib.scpr_avi_write_frame.argtypes = [vp, vp, C.c_uint32, i32]
+    lib.scpr_avi_open.restype = i32
+    lib.scpr_avi_open.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(_AviInfo)]
+    lib.scpr_avi_read_frame.restype = i64
+    lib.scpr_avi_read_frame.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(i32)]
+    lib.scpr_avi_close.restype = i32
+    lib.scpr_avi_close.argtypes = [vp]
     lib.scpr_bench_frame_scan.restype = C.c_float
     lib.scpr_bench_frame_scan.argtypes = [vp, vp, i32, i32]
     _lib = lib
@@ -294,3 +328,125 @@ class ScreenCodec:
         if r < 0:
             raise ScprError(int(r), self._lib.scpr_last_error().decode())
         return int(r)
+
+
+# ---- host layer: the VfW policy around the codec object, and the AVI container (csrc/vfw_host.cpp) -----------------
+FOURCC_SCPR = 0x52504353  # mmioFOURCC('S','C','P','R'), screenpressor.h:6
+
+
+def quality_to_loss(quality: int) -> int:
+    return int(load_library().scpr_quality_to_loss(quality))
+
+
+def infer_frame_type(first_byte: int, data_size: int) -> int:
+    return int(load_library().scpr_infer_frame_type(first_byte, data_size))
+
+
+class CodecInst:
+    """Mirror of the reference's CodecInst::Compress / Decompress (screenpressor.cpp:392-437, 592-620): keyframe interval
+    policy, quality -> loss, frame type inferred from the data on decode."""
+
+    def __init__(self, params: CodecParameters, device: int = 0, force_interval: bool = True, kf_interval: int = 500,
+                 force_loss: bool = True, conf_loss: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        p = _Params(params.width, params.height, params.bits_per_pixel, params.redmask, params.greenmask, params.bluemask,
+                    params.high_range_x, params.high_range_y, params.low_range_x, params.low_range_y, params.loss)
+        pol = _Policy(int(force_interval), kf_interval, int(force_loss), conf_loss)
+        r = self._lib.scpr_session_create(C.byref(p), device, C.byref(pol), C.byref(self._h))
+        if r < 0:
+            raise ScprError(r, self._lib.scpr_last_error().decode())
+        self.params = params
+        self._dst = np.empty(params.width * params.height * 6 + 64, dtype=np.uint8)
+
+    def close(self):
+        if self._h:
+            self._lib.scpr_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Compress(self, frame: np.ndarray, host_keyframe: bool = False, quality: int = 10000):
+        """-> (bytes, is_keyframe)"""
+        frame = np.ascontiguousarray(frame).reshape(-1).view(np.uint8)
+        key = C.c_int(0)
+        n = self._lib.scpr_session_compress(self._h, _ptr(frame), _ptr(self._dst), self._dst.size, int(host_keyframe), quality, C.byref(key))
+        if n < 0:
+            raise ScprError(n, self._lib.scpr_last_error().decode())
+        return bytes(self._dst[:n]), bool(key.value)
+
+    def Decompress(self, data: bytes, pitch: int, not_keyframe: bool) -> np.ndarray:
+        src = np.frombuffer(data, dtype=np.uint8)
+        out = np.zeros(self.params.height * pitch, dtype=np.uint8)
+        r = self._lib.scpr_session_decompress(self._h, _ptr(np.ascontiguousarray(src)), len(data), _ptr(out), pitch, int(not_keyframe))
+        if -16 <= r < 0:
+            raise BadVersionException(-r)
+        if r != 1:
+            raise ScprError(r, self._lib.scpr_last_error().decode() if r < 0 else "P frame before any I frame")
+        return out
+
+
+class AviWriter:
+    def __init__(self, path: str, width: int, height: int, bits_per_pixel: int = 32, fps: tuple[int, int] = (30, 1),
+                 masks: tuple[int, int, int] = (0x7C00, 0x3E0, 0x1F)):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        info = _AviInfo(width, height, bits_per_pixel, masks[0], masks[1], masks[2], fps[0], fps[1], 0, FOURCC_SCPR)
+        r = self._lib.scpr_avi_create(path.encode(), C.byref(info), C.byref(self._h))
+        if r < 0:
+            raise ScprError(r, self._lib.scpr_last_error().decode())
+
+    def write(self, data: bytes, is_key: bool) -> None:
+        buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+        r = self._lib.scpr_avi_write_frame(self._h, _ptr(np.ascontiguousarray(buf)), len(data), int(is_key))
+        if r < 0:
+            raise ScprError(r, self._lib.scpr_last_error().decode())
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.scpr_avi_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class AviReader:
+    def __init__(self, path: str):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.info = _AviInfo()
+        r = self._lib.scpr_avi_open(path.encode(), C.byref(self._h), C.byref(self.info))
+        if r < 0:
+            raise ScprError(r, self._lib.scpr_last_error().decode())
+
+    def __len__(self):
+        return int(self.info.frames)
+
+    def read(self, i: int):
+        """-> (bytes, is_keyframe)"""
+        key = C.c_int(0)
+        n = self._lib.scpr_avi_read_frame(self._h, i, None, 0, C.byref(key))
+        if n < 0:
+            raise ScprError(int(n), "no such frame")
+        buf = np.empty(max(int(n), 1), dtype=np.uint8)
+        self._lib.scpr_avi_read_frame(self._h, i, _ptr(buf), buf.size, C.byref(key))
+        return bytes(buf[:n]), bool(key.value)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.scpr_avi_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

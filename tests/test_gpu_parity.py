@@ -339,6 +339,45 @@ def test_rgb16_clients_match_reference(scpr):
         assert np.array_equal(out.reshape(n, h, pitch)[:, :, : 2 * w].copy().view(np.uint16), clip), name
 
 
+def test_vfw_session_and_avi_container(scpr, tmp_path):
+    """the layer above the codec object: forced keyframe interval (npframes + 1 >= interval, screenpressor.cpp:402-406),
+    quality -> loss, AVI written with AVIIF_KEYFRAME where Compress said so, decoded back through Decompress with the
+    frame type inferred from the data"""
+    from screenpressor_b200 import synth
+
+    w, h, n = 200, 120, 30
+    clip, _ = fuzz_clip(w, h, n, 41, 32, 16)
+    inst = scpr.CodecInst(scpr.CodecParameters(w, h, 32), kf_interval=8)
+    path = str(tmp_path / "cap.avi")
+    produced = []
+    with scpr.AviWriter(path, w, h, 32) as wr:
+        for i in range(n):
+            data, key = inst.Compress(clip[i])
+            wr.write(data, key)
+            produced.append((data, 0 if key else 1))
+    keys = synth.keyframe_flags(n, 8)
+    # flat frames are I frames whatever was asked (screencap.cpp:1488-1499): the session's counter restarts there too
+    want = _split(*_new(scpr, w, h, 32).CompressClip(clip, keys))
+    flat = [i for i in range(n) if len(want[i][0]) == 4 and want[i][1] == 0]
+    if not flat:
+        assert produced == want
+    assert [p[1] for p in produced][:9] == [0, 1, 1, 1, 1, 1, 1, 1, 0][:9] or flat
+    dec = scpr.CodecInst(scpr.CodecParameters(w, h, 32))
+    with scpr.AviReader(path) as rd:
+        assert len(rd) == n and rd.info.fourcc == scpr.FOURCC_SCPR and (rd.info.width, rd.info.height) == (w, h)
+        for i in range(n):
+            data, key = rd.read(i)
+            assert (data, 0 if key else 1) == produced[i]
+            out = dec.Decompress(data, w * 4, not key)
+            assert np.array_equal(out, clip[i].reshape(-1)), i
+    # quality drives the loss when it is not forced: 5000 -> 2 bits
+    lossy = scpr.CodecInst(scpr.CodecParameters(w, h, 32), force_loss=False)
+    ref = scpr.ScreenCodec(0)
+    ref.Init(scpr.CodecParameters(w, h, 32))
+    for i in range(4):
+        assert lossy.Compress(clip[i], quality=5000)[0] == ref.CompressFrame(clip[i], 0 if i == 0 else 1, loss=2)[0]
+
+
 def test_error_behaviour(scpr):
     dec = _new(scpr, 64, 48, 32)
     with pytest.raises(scpr.ScprError):          # P before any I: the reference returns 0 (screencap.cpp:1699)
