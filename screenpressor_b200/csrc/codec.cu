@@ -179,6 +179,7 @@ void scpr_destroy(scpr_codec* c) {
                    &c->dec_desc, &c->dec_frames, &c->dec_state, &c->dec_prev, &c->cands, &c->sorted_sym, &c->summary2, &c->raw16,
                    &c->dec24};
     for (DBuf* b : all) b->release();
+    if (c->dec_progress) cudaFreeHost((void*)c->dec_progress);
     for (cudaEvent_t e : c->copy_ev) cudaEventDestroy(e);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
     delete c;

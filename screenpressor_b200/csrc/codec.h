@@ -73,6 +73,8 @@ struct scpr_codec {
     scpr::DBuf dec_prev;             // last decoded frame, output format
     int dec_prev_pitch = 0;
     scpr::DBuf dec_mvs, dec_ws, dec_stream, dec_desc, dec_frames;
+    volatile int* dec_progress = nullptr;   // mapped host memory: per chain, frames below this index are complete
+    int dec_progress_cap = 0;
 
     // ---- debug hooks -----------------------------------------------------------------------------
     int dbg_n = 0;

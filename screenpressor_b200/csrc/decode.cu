@@ -56,6 +56,9 @@ struct DecWork {
     int16_t* fill_src;  // n * nb: source frame of every block (k_dec_sources)
     int n;
     int msr_x, msr_y;   // v2 streams: motion range the vectors are offset by (screencap.cpp:77)
+    volatile int* progress;  // per chain (mapped host memory, may be null): every frame below this index is complete
+    int16_t* fill_last; // per chain x nb: source of every block after the last range k_dec_sources processed
+    int f_begin, f_end, chain;  // range arguments of k_dec_sources / k_dec_fill
 };
 
 // ---- block-source map ------------------------------------------------------------------------------
@@ -1092,6 +1095,14 @@ __device__ __forceinline__ void cmd_push(Ent& e, uint32_t x, uint32_t y, uint32_
     e.head++;
     stv_shared(sy, e.head);
 }
+// every frame below f is final (its copies have drained): tell the host, which overlaps the gather of untouched blocks
+// and the download of finished frames with the rest of the chain
+__device__ __forceinline__ void publish_progress(const DecWork& w, int f, int lane) {
+    if (w.progress && lane == 0) {
+        __threadfence_system();
+        w.progress[blockIdx.x] = f;
+    }
+}
 __device__ __forceinline__ void cmd_drain(Ent& e) {
     const uint32_t sy = e.sb + S_SYNC;
     if (ldv_shared(sy + 8) != e.head) {
@@ -1130,6 +1141,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
     e.c_hdr += clock64() - thdr__;
 #endif
     cmd_drain(e);  // the copies of the previous frame are complete before this frame touches the map
+    publish_progress(w, f, lane);
     e.lastpx = 0;  // cx = cx1 = 0, screencap.cpp:1319
     int lastmx = 0, lastmy = 0;
     uint8_t* upd = w.upd + (size_t)f * g.nb;
@@ -1398,6 +1410,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
                 for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
             }
             cmd_drain(e);
+            publish_progress(w, f, lane);
             const uint32_t code = (uint32_t)f | (df.kind == DK_FLAT ? SRC_FLAT : 0u);
             for (int i = lane; i < g.nb; i += 32) map.write(i, code);  // the whole frame is new
             __syncwarp();
@@ -1425,6 +1438,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
         __threadfence_block();
     }
     cmd_drain(e);
+    __threadfence();
+    publish_progress(w, ch.first + ch.count, lane);
     stv_shared(sb + S_SYNC + 12, 1u);  // helpers leave
 #ifdef SCPR_PROF
     if (lane == 0)
@@ -1460,15 +1475,17 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
 }
 
 // source frame of every block of every frame: thread per block, frames in order
-__global__ void k_dec_sources(DecWork w) {
+__global__ void k_dec_sources(DecWork w) {  // frames [f_begin, f_end) of chain w.chain, resuming from the previous range
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.g.nb) return;
-    int last = -1;
-    for (int f = 0; f < w.n; f++) {
+    int16_t* keep = w.fill_last + (size_t)w.chain * w.g.nb;
+    int last = w.f_begin == w.chains[w.chain].first ? -1 : keep[b];
+    for (int f = w.f_begin; f < w.f_end; f++) {
         const uint8_t k = w.frames[f].kind;
         if (k == DK_I || k == DK_FLAT || w.upd[(size_t)f * w.g.nb + b]) last = f;
         w.fill_src[(size_t)f * w.g.nb + b] = (int16_t)last;
     }
+    keep[b] = (int16_t)last;
 }
 
 // gather every block a frame did not write itself from the frame that holds it (or paint flat
@@ -1480,9 +1497,10 @@ __global__ void __launch_bounds__(256) k_dec_fill(DecWork w) {
     const int strips_x = (g.nbx + 7) >> 3;
     const int strips_per_frame = strips_x * g.nby;
     const long strip = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (strip >= (long)w.n * strips_per_frame) return;
-    const int f = (int)(strip / strips_per_frame);
-    const int s = (int)(strip - (long)f * strips_per_frame);
+    if (strip >= (long)(w.f_end - w.f_begin) * strips_per_frame) return;
+    const int fr = (int)(strip / strips_per_frame);
+    const int f = w.f_begin + fr;
+    const int s = (int)(strip - (long)fr * strips_per_frame);
     const int by = s / strips_x, sx = s - by * strips_x;
     const int bx = sx * 8 + (lane >> 2);
     if (bx >= g.nbx) return;
@@ -1547,7 +1565,7 @@ static int ensure_dec_states(scpr_codec* c, int n) {
 
 // n frames, bitstreams on the host, decoded frames to device memory `d_out` (pitch bytes per row)
 static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
-                        int pitch) {
+                        int pitch, uint8_t* h_out = nullptr) {
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->st;
     if (n <= 0) return 1;
@@ -1625,7 +1643,8 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
         return SCPR_E_PARAM;
     }
     const size_t map_bytes = map_shared ? 0 : (size_t)n_chains * g.nb * 4;
-    TRY(c->dec_ws.ensure(map_bytes + (size_t)n * g.nb * 3 + 64));
+    const size_t upd_bytes = ((size_t)n * g.nb + 15) & ~(size_t)15, fsrc_bytes = ((size_t)n * g.nb * 2 + 15) & ~(size_t)15;
+    TRY(c->dec_ws.ensure(map_bytes + upd_bytes + fsrc_bytes + (size_t)n_chains * g.nb * 2 + 64));
     if (c->dec_prev_pitch != pitch) {  // previous frame is kept in output format
         TRY(c->dec_prev.ensure(g.frame_bytes));
         if (c->dec_prev_pitch == 0) CK(cudaMemsetAsync(c->dec_prev.p, 0, g.frame_bytes, st));
@@ -1653,10 +1672,28 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     uint8_t* ws = (uint8_t*)c->dec_ws.p;
     w.gmap = (uint32_t*)ws;
     w.upd = ws + map_bytes;
-    w.fill_src = (int16_t*)(ws + map_bytes + (((size_t)n * g.nb + 15) & ~(size_t)15));
+    w.fill_src = (int16_t*)(ws + map_bytes + upd_bytes);
+    w.fill_last = (int16_t*)(ws + map_bytes + upd_bytes + fsrc_bytes);
     w.n = n;
     w.msr_x = (int)c->p.high_range_x;
     w.msr_y = (int)c->p.high_range_y;
+    w.progress = nullptr;
+    if (h_out && n >= 64) {  // worth overlapping: progress words in mapped host memory, a second stream for the tail work
+        if (!c->copy_st) CK(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+        if (c->dec_progress_cap < n_chains) {
+            if (c->dec_progress) cudaFreeHost((void*)c->dec_progress);
+            c->dec_progress = nullptr;
+            c->dec_progress_cap = 0;
+            void* hp = nullptr;
+            CK(cudaHostAlloc(&hp, (size_t)(n_chains + 16) * sizeof(int), cudaHostAllocMapped));
+            c->dec_progress = (volatile int*)hp;
+            c->dec_progress_cap = n_chains + 16;
+        }
+        for (int k = 0; k < n_chains; k++) c->dec_progress[k] = chains[k].first;
+        void* dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, (void*)c->dec_progress, 0));
+        w.progress = (volatile int*)dp;
+    }
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
     StageTimer tm(st);
     const bool v2 = c->dec_version == 2;
@@ -1671,12 +1708,53 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     else LAUNCH_CHAIN(false, true);
 #undef LAUNCH_CHAIN
     tm.mark("chain");
-    k_dec_sources<<<(g.nb + 127) / 128, 128, 0, st>>>(w);
-    const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
-    k_dec_fill<<<(unsigned)((strips + 7) / 8), 256, 0, st>>>(w);
-    c->launches += 3;
+    // ---- untouched blocks + (host output) download, range by range -----------------------------------------------
+    auto finish_range = [&](int k, int a, int b, cudaStream_t s2) {
+        DecWork r = w;
+        r.chain = k; r.f_begin = a; r.f_end = b;
+        k_dec_sources<<<(g.nb + 127) / 128, 128, 0, s2>>>(r);
+        const long strips = (long)(b - a) * g.nby * ((g.nbx + 7) >> 3);
+        k_dec_fill<<<(unsigned)((strips + 7) / 8), 256, 0, s2>>>(r);
+        c->launches += 2;
+        if (h_out)
+            cudaMemcpyAsync(h_out + (size_t)a * g.frame_bytes, d_out + (size_t)a * g.frame_bytes, (size_t)(b - a) * g.frame_bytes,
+                            cudaMemcpyDeviceToHost, s2);
+    };
+    if (w.progress) {
+        // the chain kernel reports finished frames; finished ranges are completed and sent home while it keeps going
+        const int step = 24;
+        std::vector<int> next(n_chains);
+        for (int k = 0; k < n_chains; k++) next[k] = chains[k].first;
+        bool idle = false;  // the chain kernel has left the stream: whatever it reported last is final
+        for (bool busy = true; busy;) {
+            busy = false;
+            for (int k = 0; k < n_chains; k++) {
+                const int end = chains[k].first + chains[k].count;
+                const int done = idle ? end : c->dec_progress[k];
+                while (next[k] < end && (next[k] + step <= done || done >= end)) {
+                    const int b = done >= end ? (next[k] + 4 * step < end ? next[k] + 4 * step : end) : next[k] + step;
+                    finish_range(k, next[k], b, c->copy_st);
+                    next[k] = b;
+                }
+                if (next[k] < end) busy = true;
+            }
+            if (busy) {
+                if (cudaStreamQuery(st) != cudaErrorNotReady) idle = true;  // finished (or failed: reported by the sync below)
+                else {
+                    struct timespec ts = {0, 100000};
+                    nanosleep(&ts, nullptr);
+                }
+            }
+        }
+        CK(cudaStreamSynchronize(c->copy_st));
+    } else {
+        CK(cudaStreamSynchronize(st));  // chains may have finished in any order; ranges of one chain go in frame order
+        for (int k = 0; k < n_chains; k++) finish_range(k, chains[k].first, chains[k].first + chains[k].count, st);
+    }
+    c->launches += 1;
     tm.mark("sources+fill");
     tm.report("decode_batch");
+    CK(cudaStreamSynchronize(st));
     CK(cudaMemcpyAsync(c->dec_prev.p, d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -1685,7 +1763,7 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
 
 // any number of frames: launches of at most DEC_MAX_FRAMES frames (the open chain carries over, as between calls)
 static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
-                        int pitch) {
+                        int pitch, uint8_t* h_out = nullptr) {
     if (c->rgb16) {  // decode to RGB24 on the device, then put the 16-bit words together (screencap.cpp:1726-1734)
         if (pitch < c->g.X * 2) return SCPR_E_PARAM;
         CK(cudaSetDevice(c->device));
@@ -1704,7 +1782,8 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     const size_t frame_bytes = (size_t)pitch * c->g.Y;
     for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
         const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
-        const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, d_out + (size_t)f0 * frame_bytes, pitch);
+        const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, d_out + (size_t)f0 * frame_bytes, pitch,
+                                   h_out ? h_out + (size_t)f0 * frame_bytes : nullptr);
         if (r != 1) return r;
         for (int f = f0; f < f0 + m; f++) stream += sizes[f];
     }
@@ -1728,10 +1807,14 @@ int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* s
     TRY(c->dec_frames.ensure(bytes));
     // row padding of the caller's buffer is not produced by the kernels: start from zeros
     if (pitch != c->g.X * (c->rgb16 ? 2 : c->g.bpp)) CK(cudaMemsetAsync(c->dec_frames.p, 0, bytes, c->st));
-    const int r = decode_batch(c, stream, sizes, ftypes, n, (uint8_t*)c->dec_frames.p, pitch);
+    // the download is part of decode_batch: finished frame ranges travel while the chains are still decoding
+    const bool direct = !c->rgb16;
+    const int r = decode_batch(c, stream, sizes, ftypes, n, (uint8_t*)c->dec_frames.p, pitch, direct ? frames : nullptr);
     if (r != 1) return r;
-    CK(cudaMemcpyAsync(frames, c->dec_frames.p, bytes, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    if (!direct) {
+        CK(cudaMemcpyAsync(frames, c->dec_frames.p, bytes, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
     return 1;
 }
 
