@@ -1200,15 +1200,16 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             const PixSrc sT = resolve_src(w, by > 0 ? src_now(map.get(bT)) : SRC_PREV0);
             const PixSrc sL = resolve_src(w, bx > 0 ? src_now(map.get(bL)) : SRC_PREV0);
             const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
+            // block rows 2u + (lane >> 4), column lane & 15; then the row above (17 pixels with the corner) and the column to
+            // the left: ten loads per lane with additive addressing (a lone warp pays for every instruction)
+            const int cxl = lane & 15, ryl = lane >> 4;
 #pragma unroll
-            for (int u = 0; u < 10; u++) {
-                const int p = lane + 32 * u;
-                const int ty = p / 17, tx = p - ty * 17;
-                const int x = bx0 + tx - 1, y = by0 + ty - 1;
-                uint32_t v = 0;
-                if (p < 17 * 17 && x >= 0 && y >= 0 && x < g.X && y < g.Y) v = src_px(ty == 0 ? (tx == 0 ? sA : sT) : tx == 0 ? sL : sP, g, x, y);
-                tv[u] = v;
+            for (int u = 0; u < 8; u++) {
+                const int yy = 2 * u + ryl;
+                tv[u] = (cxl < bw && yy < bh) ? src_px(sP, g, bx0 + cxl, by0 + yy) : 0u;
             }
+            tv[8] = (lane < 17 && by > 0 && (lane > 0 ? lane - 1 < bw : bx > 0)) ? src_px(lane == 0 ? sA : sT, g, bx0 + lane - 1, by0 - 1) : 0u;
+            tv[9] = (lane < 16 && bx > 0 && lane < bh) ? src_px(sL, g, bx0 - 1, by0 + lane) : 0u;
           PROF_ADD(c_tile) }
         if ((bt - 1) & 1) {
             x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
@@ -1221,10 +1222,12 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             if (y1 >= y2) y1 = y2 - 1;
         }
         { PROF_T0
+            {
+                const uint32_t a0 = tb + (uint32_t)((1 + (lane >> 4)) * 17 + 1 + (lane & 15)) * 4u;
 #pragma unroll
-            for (int u = 0; u < 10; u++) {
-                const int p = lane + 32 * u;
-                if (p < 17 * 17) sts32(tb + (uint32_t)p * 4u, tv[u]);
+                for (int u = 0; u < 8; u++) sts32(a0 + (uint32_t)u * 136u, tv[u]);
+                if (lane < 17) sts32(tb + (uint32_t)lane * 4u, tv[8]);
+                if (lane < 16) sts32(tb + (uint32_t)(1 + lane) * 68u, tv[9]);
             }
             __syncwarp();
           PROF_ADD(c_tile) }
@@ -1444,10 +1447,10 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
 #ifdef SCPR_PROF
     if (lane == 0)
         printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc; %lld serial, %lld rescales) | "
-               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f\n",
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f | cache misses %lld\n",
                (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
-               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6);
+               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6, e.n_miss);
 #endif
     // leave the cached contexts, the fixed tables and the kinds behind for the next call (v2 tables are already in place)
     __syncwarp();
