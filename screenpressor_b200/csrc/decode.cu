@@ -525,6 +525,8 @@ __device__ __forceinline__ void color_refresh(ModelState* m, uint32_t sb, int la
     __syncwarp();
 }
 
+__device__ void color_new_small(ModelState* m, uint32_t sb, int lane, int id, int c);  // defined with the other promotions below
+
 // SmallContext decode (ans_contexts.h:238-283) from cache entry h; `ent` = this lane's entry, `hd` = the header
 __device__ __forceinline__ int dec_color_small(Ent& e, int id, uint32_t h, uint32_t ent, uint2 hd) {
     const int k = e.lane & 15;
@@ -577,8 +579,7 @@ __device__ __forceinline__ int dec_color_small(Ent& e, int id, uint32_t h, uint3
         c = (lastSymb + v - cumFr) & 255;
         rdec_advance(e, v0 - (uint32_t)(v << shift), (uint32_t)(1 << shift));
         cache_writeback(e.m, e.sb, e.lane, h);  // insert / promote on the canonical state: the general path
-        if (e.lane == 0) cc_encode_counted(e.m->color[id], c);
-        color_refresh(e.m, e.sb, e.lane, id);
+        color_new_small(e.m, e.sb, e.lane, id, c);
         PROF_CNT(n_gen)
     }
     return c;
@@ -639,10 +640,235 @@ __device__ __noinline__ void flat_rescale(uint8_t* xs, int kind, int lane) {  //
     }
     __syncwarp();
 }
+
+// ---- promotions and first occurrences, by the whole warp --------------------------------------------------------------
+// Photo / noise content walks every colour context through the reference's chain of representations (Cx1 -> Cx2 -> Cx3
+// sets, SmallContext, Cx6, Cx7; ans_contexts.cpp:3-50) and meets a new symbol in a context hundreds of thousands of
+// times per frame.  The transitions that touch all 256 symbols are done here with 8 symbols per lane and warp scans; only
+// the edits of the <= 16-entry lists stay on one lane (cc_encode_counted / cc_update_raw of models.cuh, which remain the
+// single-lane statement of the same rules and are what the encoder's replay uses).
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ void store_row8(uint8_t* row, const uint32_t* v) {  // eight u16 as one 128-bit store
+    *reinterpret_cast<uint4*>(row) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+// Cx6 tables from a set of met symbols with start frequencies (c6_build + c6_calcsum of models.cuh; ans_contexts.h:454-533,
+// 549-555).  met = this lane's 8-bit membership mask, frs[j] = start frequency of symbol 8*lane + j (met symbols only);
+// extra_c >= 0: that symbol additionally gets the count of a first occurrence and joins the set (Cx6::create(Cx5&, c)).
+__device__ __noinline__ void c6_build_w(uint8_t* xs, uint32_t met, const uint32_t* frs, int d, int totFr, int extra_c, int lane) {
+    int shift = 0, tot = totFr;
+    while (tot <= PROB_SCALE / 2) {
+        tot <<= 1;
+        shift++;
+    }
+    uint32_t fr[8], cn[8], cu[8], sum = 0, csum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const bool m = (met >> j) & 1u;
+        fr[j] = m ? (frs[j] << shift) : (1u << shift);
+        cn[j] = m ? (fr[j] - (fr[j] >> 1)) & 0xFFFFu : 0u;
+        fr[j] &= 0xFFFFu;
+        sum += fr[j];
+    }
+    if (extra_c >= 0 && (extra_c >> 3) == lane) {
+        const uint32_t f1 = 1u << shift;
+        cn[extra_c & 7] = (f1 - (f1 >> 1) + (25u << shift)) & 0xFFFFu;
+        d++;
+    }
+    d = __shfl_sync(0xFFFFFFFFu, d, extra_c >= 0 ? (extra_c >> 3) : 0);
+    uint32_t total;
+    uint32_t cf = warp_excl_scan(sum, lane, total);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cu[j] = cf & 0xFFFFu;
+        cf += fr[j];
+        csum += cn[j];
+    }
+    store_row8(xs + CS_FREQ + lane * 16, fr);
+    store_row8(xs + CS_CUM + lane * 16, cu);
+    store_row8(xs + CS_CNT + lane * 16, cn);
+    csum = __reduce_add_sync(0xFFFFFFFFu, csum);
+    if (lane == 0) {
+        const int shft = shift > 0 ? shift - 1 : 0;
+        xs[0] = 6;                                             // kind
+        xs[1] = (uint8_t)shift;                                // fshift
+        *reinterpret_cast<uint16_t*>(xs + 4) = (uint16_t)d;    // d
+        *reinterpret_cast<int*>(xs + 8) = (int)((((256 - d) << shft) + csum) & 0xFFFFu);  // cntsum = c6_calcsum
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t seen_byte(const ColorState& x, int lane) { return (x.seen[lane >> 2] >> ((lane & 3) * 8)) & 0xFFu; }
+// Cx2 -> Cx6 (create23, ans_contexts.h:491-533): every met symbol starts with f0, the repeated one with 2 * f0
+__device__ __forceinline__ void c6_from_set_w(ColorState& x, int c, int f0, int lane) {
+    const uint32_t met = seen_byte(x, lane);
+    const int d = x.d;
+    uint32_t frs[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) frs[j] = (lane * 8 + j == c) ? 2u * (uint32_t)f0 : (uint32_t)f0;
+    __syncwarp();
+    c6_build_w(reinterpret_cast<uint8_t*>(&x), met, frs, d, 256 - d + d * f0 + f0, -1, lane);
+}
+// Cx5 -> Cx6 (Cx6::create(Cx5&, c), ans_contexts.h:454-489): the sixteen listed symbols keep their frequencies, c joins
+__device__ __forceinline__ void c6_from_small_w(ColorState& x, int c, int lane) {
+    const int d = x.d;  // 16
+    const uint32_t ks = lane < d ? x.ssym[lane & 15] : 0x100u, kf = lane < d ? x.sfreq[lane & 15] : 0u;
+    uint32_t tot;
+    warp_excl_scan(kf, lane, tot);
+    uint32_t met = 0, frs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < d; k++) {
+        const uint32_t sk = __shfl_sync(0xFFFFFFFFu, ks, k), fk = __shfl_sync(0xFFFFFFFFu, kf, k);
+        if ((int)(sk >> 3) == lane) {
+            met |= 1u << (sk & 7);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((int)(sk & 7) == j) frs[j] = fk;
+        }
+    }
+    __syncwarp();
+    c6_build_w(reinterpret_cast<uint8_t*>(&x), met, frs, d, (int)(256 - d + tot), c, lane);
+}
+// Cx6 -> Cx7 (c7_from_c6, ans_contexts.h:868-915): symbols not met yet get the count of a fresh slot; c itself is not counted
+__device__ __forceinline__ void c7_from_c6_w(ColorState& x, int lane) {
+    uint8_t* xs = reinterpret_cast<uint8_t*>(&x);
+    const uint32_t funmet = 1u << x.fshift, cu = funmet - (funmet >> 1);
+    const uint4 r = *reinterpret_cast<const uint4*>(xs + CS_CNT + lane * 16);
+    uint32_t v[8] = {r.x & 0xFFFFu, r.x >> 16, r.y & 0xFFFFu, r.y >> 16, r.z & 0xFFFFu, r.z >> 16, r.w & 0xFFFFu, r.w >> 16};
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (!v[j]) v[j] = cu & 0xFFFFu;
+    __syncwarp();
+    store_row8(xs + CS_CNT + lane * 16, v);
+    if (lane == 0) xs[0] = 7;
+    __syncwarp();
+}
+// Cx3 -> Cx7 (c7_from_set, ans_contexts.h:917-951)
+__device__ __forceinline__ void c7_from_set_w(ColorState& x, int c, int lane) {
+    uint8_t* xs = reinterpret_cast<uint8_t*>(&x);
+    const uint32_t met = seen_byte(x, lane);
+    const int d = x.d;
+    const uint32_t f0 = (uint32_t)((PROB_SCALE - (256 - d)) / (d + 1)), c0 = f0 - (f0 >> 1);
+    uint32_t fr[8], cn[8], cu[8], sum = 0, csum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const bool m = (met >> j) & 1u;
+        fr[j] = m ? f0 : 1u;
+        cn[j] = m ? c0 : 1u;
+        if (lane * 8 + j == c) {
+            fr[j] += f0;
+            cn[j] += 16u;
+        }
+        fr[j] &= 0xFFFFu;
+        cn[j] &= 0xFFFFu;
+        sum += fr[j];
+        csum += cn[j];
+    }
+    uint32_t total;
+    uint32_t cf = warp_excl_scan(sum, lane, total);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        cu[j] = cf & 0xFFFFu;
+        cf += fr[j];
+    }
+    __syncwarp();
+    store_row8(xs + CS_FREQ + lane * 16, fr);
+    store_row8(xs + CS_CUM + lane * 16, cu);
+    store_row8(xs + CS_CNT + lane * 16, cn);
+    csum = __reduce_add_sync(0xFFFFFFFFu, csum);
+    if (lane == 0) {
+        *reinterpret_cast<int*>(xs + 8) = (int)csum;
+        xs[0] = 7;
+    }
+    __syncwarp();
+}
+// Cx1 -> SmallContext (small_from_set, ans_contexts.h:161-172): the <= 14 met symbols in order, 50 each, 100 for the repeated one
+__device__ __forceinline__ void small_from_set_w(ColorState& x, int c, int lane) {
+    uint32_t wbits = lane < 8 ? x.seen[lane & 7] : 0u;
+    const int d = x.d;
+    uint32_t total;
+    uint32_t pos = warp_excl_scan((uint32_t)__popc(wbits), lane, total);
+    __syncwarp();
+    while (wbits) {
+        const int sidx = lane * 32 + __ffs(wbits) - 1;
+        wbits &= wbits - 1;
+        if (pos < 16) {
+            x.ssym[pos] = (uint8_t)sidx;
+            x.sfreq[pos] = (uint16_t)(sidx == c ? 100 : 50);
+            if (sidx == c) x.maxpos = (uint8_t)pos;
+        }
+        pos++;
+    }
+    if (lane >= d && lane < 16) x.sfreq[lane] = 0;
+    __syncwarp();
+}
+// Context::update for a context without statistics (kinds 0..3: the byte was stored raw); cc_update_raw of models.cuh
+__device__ __noinline__ void color_raw_w(ColorState& x, int c, int f0, int lane) {
+    const int kind = x.kind, d = x.d;
+    const bool have = kind != 0 && seen_has(x, c);
+    __syncwarp();
+    if (kind == 0 || !have) {  // start the set, or one more distinct symbol: a few scalar stores
+        if (lane == 0) cc_update_raw(x, c, f0);
+    } else if (kind == 1) {
+        small_from_set_w(x, c, lane);
+        if (lane == 0) {
+            if (d <= 4)
+                x.kind = 4;
+            else {
+                x.kind = 5;
+                x.cntsum = small_calcsum(x);
+            }
+        }
+    } else if (kind == 2) {
+        c6_from_set_w(x, c, f0, lane);
+    } else {
+        c7_from_set_w(x, c, lane);
+    }
+    __syncwarp();
+}
+// a symbol its context (kinds 4..6) has not met before: insert / place it, or promote the context (cc_encode_counted)
+__device__ __noinline__ void color_new_w(ColorState& x, int c, int lane) {
+    uint8_t* xs = reinterpret_cast<uint8_t*>(&x);
+    const int kind = x.kind, d = x.d;
+    __syncwarp();
+    if (kind == 5 && d == 16) {
+        c6_from_small_w(x, c, lane);
+    } else if (kind == 6) {
+        if (d >= 40) {  // MaxD6 (ans_contexts.h:631)
+            c7_from_c6_w(x, lane);
+        } else {        // placeSymbol + incrCnt (ans_contexts.h:621-638, 686-691)
+            const int fshift = x.fshift, cs = x.cntsum;
+            const int step = 25 << fshift;
+            __syncwarp();
+            if (lane == 0) {
+                const int fr = 1 << fshift;
+                x.cnt[c] = (uint16_t)(fr - (fr >> 1) + step);
+                x.d = (uint16_t)(d + 1);
+                x.cntsum = (cs + step) & 0xFFFF;
+            }
+            if (((cs + step) & 0xFFFF) + step > PROB_SCALE) flat_rescale(xs, 6, lane);
+        }
+    } else {
+        if (lane == 0) cc_encode_counted(x, c);
+    }
+    __syncwarp();
+}
+__device__ __noinline__ void color_new_small(ModelState* m, uint32_t sb, int lane, int id, int c) {
+    color_new_w(m->color[id], c, lane);
+    color_refresh(m, sb, lane, id);
+}
+
 __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int kind) {
     const uint4 hd = *reinterpret_cast<const uint4*>(xs);
     const uint4 cr = *reinterpret_cast<const uint4*>(xs + CS_CUM + e.lane * 16);
     const uint4 fq = *reinterpret_cast<const uint4*>(xs + CS_FREQ + e.lane * 16);
+    const uint4 cq = *reinterpret_cast<const uint4*>(xs + CS_CNT + e.lane * 16);  // fetched with the rest: no second round trip for cnt[c]
     const uint32_t v = e.x & (PROB_SCALE - 1);
     // number of this lane's cumulative frequencies <= v, two halfwords at a time (values < 2^15: no borrow between halves)
     const uint32_t vv = (v * 0x10001u) | 0x80008000u;
@@ -657,7 +883,7 @@ __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int k
     const int c = L * 8 + __shfl_sync(0xFFFFFFFFu, idx, L);
     // count the symbol
     uint16_t* cnt = reinterpret_cast<uint16_t*>(xs + CS_CNT);
-    const int cn = cnt[c], cs = (int)hd.z;
+    const int cn = (int)__shfl_sync(0xFFFFFFFFu, half_at(cq, idx & 7), L), cs = (int)hd.z;
     const int step = kind == 7 ? 16 : (25 << ((hd.x >> 8) & 255));
     if (cn != 0 || kind == 7) {  // met before: count (+ rescale), ans_contexts.h:686-691, 959-981
         if (e.lane == 0) {
@@ -669,7 +895,7 @@ __device__ __forceinline__ int dec_color_flat(Ent& e, uint8_t* xs, int id, int k
             PROF_CNT(n_resc)
         }
     } else {  // first occurrence in a Cx6: placeSymbol or the promotion to Cx7
-        if (e.lane == 0) cc_encode_counted(e.m->color[id], c);
+        color_new_w(e.m->color[id], c, e.lane);
         color_refresh(e.m, e.sb, e.lane, id);
         PROF_CNT(n_gen)
     }
@@ -694,7 +920,7 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
         if (kind < 4) {  // no statistics yet: the byte is stored raw (screencap.h:324-325)
             c = (int)(rd_peek(e) & 0xFFu);
             rd_skip(e, 8);
-            if (e.lane == 0) cc_update_raw(e.m->color[id], c, e.f0);
+            color_raw_w(e.m->color[id], c, e.f0, e.lane);
             color_refresh(e.m, e.sb, e.lane, id);
             rdec_count<CNT>(e);
             PROF_ADD(c_raw) PROF_CNT(n_raw) PROF_ADD(c_color) PROF_CNT(n_color)
@@ -1029,8 +1255,12 @@ __device__ void mv_copy(const DecWork& w, const BlockMap<SM>& map, int f, int bi
     const int by = bi / g.nbx, bx = bi - by * g.nbx;
     const int bx0 = bx * 16, by0 = by * 16;
     const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
-    const int x1 = bx0 + (int)(rect & 15u), y1 = by0 + (int)((rect >> 4) & 15u);
-    const int x2 = bx0 + (int)((rect >> 8) & 15u) + 1, y2 = by0 + (int)((rect >> 12) & 15u) + 1;
+    int x1 = bx0 + (int)(rect & 15u), y1 = by0 + (int)((rect >> 4) & 15u);
+    int x2 = bx0 + (int)((rect >> 8) & 15u) + 1, y2 = by0 + (int)((rect >> 12) & 15u) + 1;
+    if (x2 > bx0 + bw) x2 = bx0 + bw;  // blocks cut by the frame edge, and corrupt input
+    if (y2 > by0 + bh) y2 = by0 + bh;
+    if (x1 >= x2) x1 = x2 - 1;
+    if (y1 >= y2) y1 = y2 - 1;
     uint8_t* frame = w.out + (size_t)f * g.frame_bytes;
     const int gx = min(max(x1 + mx, 0), g.X - 1), gy = min(max(y1 + my, 0), g.Y - 1);  // corrupt input guard
     const int cbx = gx >> 4, cby = gy >> 4;
@@ -1061,7 +1291,13 @@ __device__ void mv_copy(const DecWork& w, const BlockMap<SM>& map, int f, int bi
         const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
         if (xx < bw && yy < bh) store_px(frame, g, bx0 + xx, by0 + yy, px[u]);
     }
-    if (lane == 0) w.upd[(size_t)f * g.nb + bi] = 1;
+    __syncwarp();
+    if (lane == 0) {
+        // the block now belongs to frame f.  Readers that still see the old word get the same answer: they ask for the
+        // source as of frame f - 1 (other copies of this frame) or come after the chain warp's drain (tile loads, frame f + 1)
+        map.write(bi, (uint32_t)f);
+        w.upd[(size_t)f * g.nb + bi] = 1;
+    }
 }
 
 template <bool SM>
@@ -1153,23 +1389,17 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
         const int bi = b0 + __ffs(chm) - 1;
         chm &= chm - 1;
         const int bt = (int)lds8(btsb + bi);
-        const int by = bi / g.nbx, bx = bi - by * g.nbx;
-        const int bx0 = bx * 16, by0 = by * 16;
-        const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
-        int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
         PROF_CNT(n_blocks)
         if ((bt - 1) & 2) {
-            // ---- motion-vector block: decode its symbols, post the copy (screencap.cpp:1333-1368)
+            // ---- motion-vector block: decode its symbols, post the copy (screencap.cpp:1333-1368).  The helper that
+            // executes it clips the rectangle to the block and records the block's new owner in the map.
             PROF_T0
+            uint32_t rect = 0xFF00u;  // the whole block
             if ((bt - 1) & 1) {
-                x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
-                y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
-                x2 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) + 1;
-                y2 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) + 1;
-                if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
-                if (y2 > by0 + bh) y2 = by0 + bh;
-                if (x1 >= x2) x1 = x2 - 1;
-                if (y1 >= y2) y1 = y2 - 1;
+                rect = (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
+                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e) << 4;
+                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) << 8;
+                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) << 12;
             }
             int mx = lastmx, my = lastmy;
             if (V2) {  // no repeat flag before v3, vectors offset by the stream's own motion range (screencap.cpp:1358-1361)
@@ -1180,13 +1410,14 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
                 my = dec_fxc<512, CX_MV - CX_NTAB + 1>(e) - 256;
             }
             lastmx = mx; lastmy = my;
-            map.write(bi, (uint32_t)f);
-            cmd_push(e, (uint32_t)bi | ((uint32_t)f << 16),
-                     (uint32_t)(x1 - bx0) | ((uint32_t)(y1 - by0) << 4) | ((uint32_t)(x2 - 1 - bx0) << 8) | ((uint32_t)(y2 - 1 - by0) << 12),
-                     ((uint32_t)mx & 0xFFFFu) | ((uint32_t)my << 16));
+            cmd_push(e, (uint32_t)bi | ((uint32_t)f << 16), rect, ((uint32_t)mx & 0xFFFFu) | ((uint32_t)my << 16));
             PROF_ADD(c_mv)
             continue;
         }
+        const int by = bi / g.nbx, bx = bi - by * g.nbx;
+        const int bx0 = bx * 16, by0 = by * 16;
+        const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
+        int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
         // ---- pixel-coded block, decoded in a shared-memory tile ----
         // tile[1+yy][1+xx] = block pixel, initially the previous frame's block (so pixels of type 3, and the part
         // of a partial block outside the sub-rect, are already in place); row 0 / column 0 = the neighbours
