@@ -59,6 +59,7 @@ struct DecWork {
     volatile int* progress;  // per chain (mapped host memory, may be null): every frame below this index is complete
     int16_t* fill_last; // per chain x nb: source of every block after the last range k_dec_sources processed
     int f_begin, f_end, chain;  // range arguments of k_dec_sources / k_dec_fill
+    uint32_t irows;     // offset of the two I-frame row buffers in shared memory, 0 = none (decode_i_rows)
 };
 
 // ---- block-source map ------------------------------------------------------------------------------
@@ -1195,31 +1196,142 @@ __device__ void decode_i(const DecWork& w, Ent& e, uint8_t* frame, int lane) {
             p = ipos_add(p, n, X);
             lastv = c;
         } else {
+            // the run's last pixel is the next literal's context: it is taken from the lane that produced it, not read back
+            uint32_t myv = 0;
             if (n < X && (ptype == 2 || ptype == 5)) {  // sources lie strictly before the run
                 for (int i = lane; i < n; i += 32) {
                     const IPos q = ipos_add(p, i, X);
-                    if (q.y < Y) store_px(frame, g, q.x, q.y, ptype == 2 ? load_px(frame, g, q.x, q.y - 1) : tl_at(frame, g, q, padded));
+                    if (q.y < Y) {
+                        myv = ptype == 2 ? load_px(frame, g, q.x, q.y - 1) : tl_at(frame, g, q, padded);
+                        store_px(frame, g, q.x, q.y, myv);
+                    }
                 }
+                lastv = __shfl_sync(0xFFFFFFFFu, myv, (n - 1) & 31);
             } else {  // gradient chains through the left pixel; tiny frames may read their own run
                 if (lane == 0) {
                     IPos q = p;
+                    uint32_t left = lastv, ptop = 0;  // the pixel before q in raster order; the pixel above it
+                    bool have_ptop = false;
                     for (int i = 0; i < n && q.y < Y; i++) {
-                        uint32_t v;
-                        if (ptype == 2) v = load_px(frame, g, q.x, q.y - 1);
-                        else if (ptype == 5) v = tl_at(frame, g, q, padded);
+                        if (ptype == 2) myv = load_px(frame, g, q.x, q.y - 1);
+                        else if (ptype == 5) myv = tl_at(frame, g, q, padded);
                         else {
-                            const IPos l = ipos_prev(q, X);
-                            v = grad_px(load_px(frame, g, l.x, l.y), load_px(frame, g, q.x, q.y - 1), tl_at(frame, g, q, padded));
+                            const uint32_t top = load_px(frame, g, q.x, q.y - 1);
+                            const uint32_t tlv = (have_ptop && q.x > 0) ? ptop : tl_at(frame, g, q, padded);
+                            myv = grad_px(left, top, tlv);
+                            ptop = top;
+                            have_ptop = true;
                         }
-                        store_px(frame, g, q.x, q.y, v);
+                        store_px(frame, g, q.x, q.y, myv);
+                        left = myv;
                         q = ipos_add(q, 1, X);
                     }
                 }
+                lastv = __shfl_sync(0xFFFFFFFFu, myv, 0);
             }
             __syncwarp();
             p = ipos_add(p, n, X);
-            const IPos l = ipos_prev(p, X);
-            lastv = l.y < Y ? load_px(frame, g, l.x, l.y) : 0u;
+        }
+        e.lastpx = lastv;
+        PROF_ADD(c_ifill)
+    }
+}
+
+
+// ---- I frame through two row buffers in shared memory -------------------------------------------------------------------
+// Every predictor of an I frame reaches at most one row up (the corner pixel at x == 0 reaches the tail of row y - 2, which
+// still sits in the buffer row y is about to reuse), so the current and the previous row are kept in shared memory: run
+// fills read and write shared memory only, and a row goes to the frame in one coalesced pass when the raster leaves it.
+// Needs X >= 256 (a run is at most 255 pixels: it touches at most two rows) and 8 * X bytes of shared memory; other
+// frames take decode_i above.
+__device__ __forceinline__ void irow_flush(const Geo& g, uint8_t* frame, uint32_t row, int y, int lane) {
+    if (g.bpp == 4 && (g.X & 3) == 0 && (g.pitch & 15) == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(frame + (size_t)y * g.pitch);
+        for (int i = lane; i < g.X / 4; i += 32) {
+            uint4 v = lds128(row + 16u * (uint32_t)i);
+            v.x |= 0xFF000000u; v.y |= 0xFF000000u; v.z |= 0xFF000000u; v.w |= 0xFF000000u;
+            dst[i] = v;
+        }
+    } else {
+        for (int x = lane; x < g.X; x += 32) store_px(frame, g, x, y, lds32(row + 4u * (uint32_t)x));
+    }
+}
+template <bool V2>
+__device__ void decode_i_rows(const DecWork& w, Ent& e, uint8_t* frame, int lane, uint32_t rb) {
+    const Geo& g = w.g;
+    const int X = g.X, Y = g.Y;
+    const bool padded = ((X * 3 + 3) & ~3) != X * 3;
+    const uint32_t rowbytes = (uint32_t)X * 4u;
+    int x = 0, y = 0;    // the next pixel
+    int ptype = 0;
+    int hdr = X + 1;
+    uint32_t lastv = 0;  // the pixel before it in raster order
+    bool header = true;
+    while (y < Y) {
+        uint32_t c = lastv;  // type 1: the previous pixel in raster order, whatever the row
+        int n;
+        if (header) {  // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
+            c = V2 ? rc_rgb(e) : dec_rgb(e);
+            n = V2 ? rc_n(e, 0) : dec_n(e, 0);
+            ptype = 0;
+            hdr -= n;
+            if (hdr <= 0) header = false;
+        } else
+            n = dec_run<V2>(e, ptype, c);
+        if (n <= 0) break;
+        PROF_T0
+        const uint32_t r0 = rb + (uint32_t)(y & 1) * rowbytes, r1 = rb + (uint32_t)((y + 1) & 1) * rowbytes;  // rows y (and y - 2) / y + 1 (and y - 1)
+        if (ptype == 0 || ptype == 1) {
+            for (int i = lane; i < n; i += 32) {
+                const int xi = x + i;
+                if (xi < X) sts32(r0 + 4u * (uint32_t)xi, c);
+                else if (y + 1 < Y) sts32(r1 + 4u * (uint32_t)(xi - X), c);
+            }
+            lastv = c;
+        } else if (ptype == 2 || ptype == 5) {  // sources lie strictly before the run: the lanes work independently
+            uint32_t myv = 0;
+            for (int i = lane; i < n; i += 32) {
+                int xi = x + i, yi = y;
+                uint32_t cur = r0, up = r1;
+                if (xi >= X) {
+                    xi -= X; yi++;
+                    cur = r1; up = r0;
+                }
+                if (yi < Y) {
+                    if (ptype == 2) myv = lds32(up + 4u * (uint32_t)xi);
+                    else if (xi > 0) myv = lds32(up + 4u * (uint32_t)(xi - 1));
+                    else myv = padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1));  // tail of row yi - 2
+                    sts32(cur + 4u * (uint32_t)xi, myv);
+                }
+            }
+            lastv = __shfl_sync(0xFFFFFFFFu, myv, (n - 1) & 31);
+        } else {  // gradient chains through the left pixel: one lane
+            uint32_t myv = 0;
+            if (lane == 0) {
+                int xi = x, yi = y;
+                uint32_t cur = r0, up = r1, left = lastv;
+                for (int i = 0; i < n && yi < Y; i++) {
+                    const uint32_t top = lds32(up + 4u * (uint32_t)xi);
+                    const uint32_t tlv = xi > 0 ? lds32(up + 4u * (uint32_t)(xi - 1))
+                                                : (padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1)));
+                    myv = grad_px(left, top, tlv);
+                    sts32(cur + 4u * (uint32_t)xi, myv);
+                    left = myv;
+                    if (++xi == X) {
+                        xi = 0; yi++;
+                        const uint32_t t = cur; cur = up; up = t;
+                    }
+                }
+            }
+            lastv = __shfl_sync(0xFFFFFFFFu, myv, 0);
+        }
+        __syncwarp();
+        x += n;
+        if (x >= X) {  // the raster left row y: it is complete
+            irow_flush(g, frame, r0, y, lane);
+            __syncwarp();
+            x -= X;
+            y++;
         }
         e.lastpx = lastv;
         PROF_ADD(c_ifill)
@@ -1657,7 +1769,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
                     e.nleft = RANS_BLOCK;
                     rdec_init(e);
                 }
-                decode_i<V2>(w, e, frame, lane);
+                if (w.irows) decode_i_rows<V2>(w, e, frame, lane, sb + w.irows);
+                else decode_i<V2>(w, e, frame, lane);
             }
             continue;
         }
@@ -1869,9 +1982,16 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     TRY(c->dec_stream.ensure((size_t)off + 64));
     TRY(c->dec_desc.ensure((size_t)n * sizeof(DecFrame) + (size_t)n_chains * sizeof(DecChain)));
     // the block-source map sits in shared memory when it fits next to the tables, else in global memory
-    const size_t smem_sm = (size_t)s_map_off(g.nb) + (size_t)g.nb * 4 + 16, smem_gm = (size_t)s_map_off(g.nb) + 16;
-    const bool map_shared = smem_sm <= 227 * 1024;
-    const size_t smem = map_shared ? smem_sm : smem_gm;
+    // shared memory beyond the tables: block types (nb bytes), the block-source map when it fits (4 nb), two I-frame rows
+    // when they fit (8 X; rows first -- I frames are where the time goes on big frames)
+    const size_t smem_lim = 227 * 1024;
+    const size_t smem_sm = ((size_t)s_map_off(g.nb) + (size_t)g.nb * 4 + 31) & ~(size_t)15, smem_gm = (size_t)s_map_off(g.nb) + 16;
+    const size_t rows_bytes = g.X >= 256 ? (size_t)g.X * 8 : 0;
+    bool map_shared = smem_sm + rows_bytes <= smem_lim;
+    const bool rows = rows_bytes && (map_shared || smem_gm + rows_bytes <= smem_lim);
+    if (!rows) map_shared = smem_sm <= smem_lim;
+    const uint32_t irows_off = rows ? (uint32_t)(map_shared ? smem_sm : smem_gm) : 0u;
+    const size_t smem = (map_shared ? smem_sm : smem_gm) + (rows ? rows_bytes : 0);
     if (smem > 227 * 1024) {
         set_error("frame has too many blocks for the decoder's shared-memory block map");
         return SCPR_E_PARAM;
@@ -1911,6 +2031,7 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.n = n;
     w.msr_x = (int)c->p.high_range_x;
     w.msr_y = (int)c->p.high_range_y;
+    w.irows = irows_off;
     w.progress = nullptr;
     if (h_out && n >= 64) {  // worth overlapping: progress words in mapped host memory, a second stream for the tail work
         if (!c->copy_st) CK(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
