@@ -189,9 +189,12 @@ constexpr uint32_t S_CENT = S_CHDR + NCACHE * 8;         // u32[NCACHE][16]: ent
 constexpr int RING = 256;                                // MV-copy commands in flight (see "helper warps" below)
 constexpr uint32_t S_RING = S_CENT + NCACHE * 64;        // uint4[RING]
 constexpr uint32_t S_SYNC = S_RING + RING * 16;          // u32: head, next, done, quit
-constexpr uint32_t S_BTS = S_SYNC + 16;                  // u8[nb], padded to 16; then (SM maps) u32[nb]
+constexpr int RQ = 256;                                  // pixel-block commands in flight (see "reconstruction warp" below)
+constexpr uint32_t S_RQ = S_SYNC + 16;                   // uint4[RQ]
+constexpr uint32_t S_RSYNC = S_RQ + RQ * 16;             // u32: -, done, {commands up to the last run, its last pixel}
+constexpr uint32_t S_BTS = S_RSYNC + 16;                 // u8[nb], padded to 16; then (SM maps) u32[nb]
 static_assert(S_HEADS % 16 == 0 && S_LUT32 % 16 == 0 && S_TILE % 16 == 0 && S_CTAG % 16 == 0 && S_RING % 16 == 0, "shared layout alignment");
-constexpr int DEC_WARPS = 8;                             // warp 0 = the chain, warp 4 (same scheduler as warp 0) idles, the rest copy
+constexpr int DEC_WARPS = 8;                             // warp 0 = the chain, warp 1 = reconstruction, warp 4 (warp 0's scheduler) idles, the rest copy
 __host__ __device__ constexpr uint32_t s_map_off(int nb) { return S_BTS + (((uint32_t)nb + 15u) & ~15u); }
 __host__ __device__ constexpr int fx_off(int t) {
     return t < 8 ? t * 256 : t == 8 ? 2048 : t < 13 ? 2056 + (t - 9) * 16 : t < 15 ? 2120 + (t - 13) * 512 : 3144 + (t - 15) * 8;
@@ -223,6 +226,8 @@ struct Ent {
     int nleft;                // symbols until the next RansDecInit
     uint32_t lastpx;          // the pixel before the next run: the colour contexts are functions of it (screencap.cpp:371-372, 616-624)
     uint32_t sb;              // shared-memory base address
+    uint32_t rposted;         // pixel-block commands posted to the reconstruction warp so far
+    uint32_t lp_wait;         // 0: lastpx is current; else lastpx is what the reconstruction warp leaves after this many commands
     uint32_t head;            // motion-vector copies posted so far
     // v2 streams: range coder state (RangeCoderSub, sub.h:21-45) and the count tables
     uint32_t rc_code, rc_range;
@@ -937,10 +942,31 @@ __device__ __forceinline__ int dec_color(Ent& e, int id) {  // decodeC, screenca
     PROF_ADD(c_small) PROF_CNT(n_small) PROF_ADD(c_color) PROF_CNT(n_color)
     return c;
 }
+__device__ __forceinline__ uint32_t ldv_shared(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stv_shared(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// The pixel before a literal is the literal's context.  In P frames pixels are produced by the reconstruction warp: when
+// the run before the literal was a predicted one, the chain warp waits here until that run has been filled (it has had the
+// time of one symbol decode to do so) and takes the run's last pixel from it.
+__device__ __forceinline__ void fetch_lastpx(Ent& e) {
+    if (e.lp_wait) {
+        // {commands executed up to and including the last run, that run's last pixel}: one 64-bit word, written at once
+        uint2 lp;
+        do {
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lp.x), "=r"(lp.y) : "r"(e.sb + S_RSYNC + 8u) : "memory");
+        } while ((int)(lp.x - e.lp_wait) < 0);
+        e.lastpx = lp.y;
+        e.lp_wait = 0;
+    }
+}
 // The context of a colour byte is made of the two bytes coded before it, quantised to 6 bits: for byte 0 those
 // are bytes 2 and 1 of the pixel before the run (MAKECX1, screencap.h:36; :371-372, 488-493, 1417-1419).
 template <bool CNT = true>
 __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.cpp:662-679
+    fetch_lastpx(e);
     uint32_t px = 0;
     uint32_t cx = (e.lastpx >> 18) & 63u, cx1 = (e.lastpx >> 4) & 0xFC0u;
 #pragma unroll 1
@@ -1051,6 +1077,7 @@ __device__ __forceinline__ int rc_fx(Ent& e) {
 }
 __device__ __forceinline__ int rc_n(Ent& e, int ptype) { return rc_val<256>(e, e.v2 + V2_N + ptype * 257, 256, 400); }
 __device__ __forceinline__ uint32_t rc_rgb(Ent& e) {  // DecodeRGB with decodeC = DecodeValUni(cntab, step SC_STEP)
+    fetch_lastpx(e);
     uint32_t px = 0;
     uint32_t cx = (e.lastpx >> 18) & 63u, cx1 = (e.lastpx >> 4) & 0xFC0u;
 #pragma unroll 1
@@ -1349,12 +1376,6 @@ __device__ void decode_i_rows(const DecWork& w, Ent& e, uint8_t* frame, int lane
 //     newest) and (b) before it reads pixels itself (tile loads of pixel-coded blocks).
 // Command (uint4): x = bi | frame << 16;  y = sub-rect inside the block, x1 | y1 << 4 | (x2-1) << 8 | (y2-1) << 12;
 // z = (mx & 0xFFFF) | my << 16.  S_SYNC: head (commands published), next (commands taken), done, quit.
-__device__ __forceinline__ uint32_t ldv_shared(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stv_shared(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t a, uint32_t v) {
     uint32_t r;
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory");
@@ -1461,13 +1482,34 @@ __device__ __forceinline__ void cmd_drain(Ent& e) {
     __threadfence_block();
 }
 
+// commands to the reconstruction warp (uint4): x = op | ..., see recon_loop
+constexpr uint32_t RQ_BEGIN = 1u, RQ_RUN = 2u, RQ_END = 3u;
+__device__ __forceinline__ void rq_post(Ent& e, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t rs = e.sb + S_RSYNC;
+    if ((e.rposted & 63u) == 0u)  // ring space, checked once per 64 commands
+        while (e.rposted - ldv_shared(rs + 4) > (uint32_t)(RQ - 64)) {
+        }
+    // the slot carries its own sequence number: the reconstruction warp polls the slot itself.  Arguments first, then the
+    // 64-bit {command, sequence number} word it polls (volatile stores of one thread, in program order)
+    const uint32_t slot = e.sb + S_RQ + 16u * (e.rposted % RQ);
+    e.rposted++;
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot + 8u), "r"(y), "r"(z) : "memory");
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(x), "r"(e.rposted) : "memory");
+}
+// everything posted to the reconstruction warp has been executed (its frame writes and map updates are in place)
+__device__ __forceinline__ void rq_drain(Ent& e) {
+    const uint32_t rs = e.sb + S_RSYNC;
+    while (ldv_shared(rs + 4) != e.rposted) __nanosleep(50);
+    __threadfence_block();
+}
+
 // ---- P frame (DecompressP, screencap.cpp:1275-1432) ------------------------------------------------
 __device__ __forceinline__ uint32_t tile_at(uint32_t tb, int ty, int tx) { return lds32(tb + (uint32_t)(ty * 17 + tx) * 4u); }
 
 template <bool SM, bool V2>
 __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint8_t* frame, int f, int lane) {
     const Geo& g = w.g;
-    const uint32_t tb = e.sb + S_TILE, btsb = e.sb + S_BTS;
+    const uint32_t btsb = e.sb + S_BTS;
 #ifdef SCPR_PROF
     const long long thdr__ = clock64();
 #endif
@@ -1488,11 +1530,12 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
 #ifdef SCPR_PROF
     e.c_hdr += clock64() - thdr__;
 #endif
-    cmd_drain(e);  // the copies of the previous frame are complete before this frame touches the map
+    rq_drain(e);   // the blocks and ...
+    cmd_drain(e);  // ... the copies of the previous frame are complete before this frame touches the map
     publish_progress(w, f, lane);
     e.lastpx = 0;  // cx = cx1 = 0, screencap.cpp:1319
+    e.lp_wait = 0;
     int lastmx = 0, lastmy = 0;
-    uint8_t* upd = w.upd + (size_t)f * g.nb;
     // visit changed blocks only: 32 block types per step, ballot, iterate the set bits
     for (int b0 = xx1 & ~31; b0 <= xx2; b0 += 32) {
       const int myb = b0 + lane;
@@ -1530,30 +1573,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
         const int bx0 = bx * 16, by0 = by * 16;
         const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
         int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
-        // ---- pixel-coded block, decoded in a shared-memory tile ----
-        // tile[1+yy][1+xx] = block pixel, initially the previous frame's block (so pixels of type 3, and the part
-        // of a partial block outside the sub-rect, are already in place); row 0 / column 0 = the neighbours
-        // above / left in the current frame.  The loads are issued first, the sub-rect symbols are decoded while
-        // they are in flight.
-        uint32_t tv[10];
-        { PROF_T0
-            cmd_drain(e);  // neighbours may be motion-vector blocks of this frame
-            const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
-            const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? src_now(map.get(bA)) : SRC_PREV0);
-            const PixSrc sT = resolve_src(w, by > 0 ? src_now(map.get(bT)) : SRC_PREV0);
-            const PixSrc sL = resolve_src(w, bx > 0 ? src_now(map.get(bL)) : SRC_PREV0);
-            const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
-            // block rows 2u + (lane >> 4), column lane & 15; then the row above (17 pixels with the corner) and the column to
-            // the left: ten loads per lane with additive addressing (a lone warp pays for every instruction)
-            const int cxl = lane & 15, ryl = lane >> 4;
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int yy = 2 * u + ryl;
-                tv[u] = (cxl < bw && yy < bh) ? src_px(sP, g, bx0 + cxl, by0 + yy) : 0u;
-            }
-            tv[8] = (lane < 17 && by > 0 && (lane > 0 ? lane - 1 < bw : bx > 0)) ? src_px(lane == 0 ? sA : sT, g, bx0 + lane - 1, by0 - 1) : 0u;
-            tv[9] = (lane < 16 && bx > 0 && lane < bh) ? src_px(sL, g, bx0 - 1, by0 + lane) : 0u;
-          PROF_ADD(c_tile) }
+        // ---- pixel-coded block: the chain warp decodes its symbols, the reconstruction warp builds its pixels ----
         if ((bt - 1) & 1) {
             x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
             y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
@@ -1564,117 +1584,187 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             if (x1 >= x2) x1 = x2 - 1;
             if (y1 >= y2) y1 = y2 - 1;
         }
-        { PROF_T0
-            {
-                const uint32_t a0 = tb + (uint32_t)((1 + (lane >> 4)) * 17 + 1 + (lane & 15)) * 4u;
-#pragma unroll
-                for (int u = 0; u < 8; u++) sts32(a0 + (uint32_t)u * 136u, tv[u]);
-                if (lane < 17) sts32(tb + (uint32_t)lane * 4u, tv[8]);
-                if (lane < 16) sts32(tb + (uint32_t)(1 + lane) * 68u, tv[9]);
-            }
-            __syncwarp();
-          PROF_ADD(c_tile) }
-        const int sw = x2 - x1, sh = y2 - y1;
-        const uint32_t swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;   // idx / sw == (idx * swinv) >> 16 for idx < 256
-        const uint32_t sw1inv = (65536u + (uint32_t)sw) / (uint32_t)(sw + 1);  // same for sw + 1
-        {  // pixel runs over the sub-rect in its own raster order.  The sources of every predicted pixel lie
-           // outside the run (closed forms below), so the lanes fill a run independently of each other.
+        rq_post(e, RQ_BEGIN | ((uint32_t)bi << 8), (uint32_t)f,
+                (uint32_t)(x1 - bx0) | ((uint32_t)(y1 - by0) << 4) | ((uint32_t)(x2 - 1 - bx0) << 8) | ((uint32_t)(y2 - 1 - by0) << 12));
+        {
             PROF_T0
             int pos = 0, ptype = 0;
-            const int npx = sw * sh;
-            const int ox = 1 + x1 - bx0, oy = 1 + y1 - by0;
-            int xx0 = 0, yy0 = 0;                                   // the run's first pixel in the sub-rect ...
-            uint32_t ca = tb + (uint32_t)(oy * 17 + ox) * 4u;       // ... and its tile address
+            const int npx = (x2 - x1) * (y2 - y1);
             while (pos < npx) {
                 uint32_t c = 0;
                 int n = dec_run<V2>(e, ptype, c);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
-                const int xe = xx0 + n;
-                uint32_t vlast;
-                if (xe <= sw && ptype != 4) {
-                    // the run stays in its row (the common case; at most 16 pixels): every source is one fixed step
-                    // away -- left: the pixel before the run; top: one tile row up; top-left: one row up, one left;
-                    // type 3 keeps the previous frame's pixel that is already in the tile
-                    const uint32_t al = ca + 4u * (uint32_t)(n - 1);
-                    const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
-                    uint32_t v = c;
-                    vlast = c;
-                    if (ptype == 1) {
-                        v = vlast = lds32(ca - 4u);
-                    } else if (ptype == 2) {
-                        v = lds32(a - 68u);
-                        vlast = lds32(al - 68u);
-                    } else if (ptype == 5) {
-                        v = lds32(a - 72u);
-                        vlast = lds32(al - 72u);
-                    } else if (ptype == 3) {
-                        vlast = lds32(al);
-                    }
-                    if (ptype != 3 && lane < n) sts32(a, v);
-                    __syncwarp();
-                } else {
-                    if (ptype == 4) {  // gradient chains through the left pixel: serial
-                        if (lane == 0) {
-                            int xx = xx0, yy = yy0;
-                            for (int i = 0; i < n; i++) {
-                                const uint32_t a = tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u;
-                                sts32(a, grad_px(lds32(a - 4), lds32(a - 68), lds32(a - 72)));
-                                if (++xx == sw) {
-                                    xx = 0;
-                                    yy++;
-                                }
-                            }
-                        }
-                    } else if (ptype != 3) {
-                        for (int i = lane; i < n; i += 32) {
-                            const int idx = pos + i;
-                            const int yy = (int)(((uint32_t)idx * swinv) >> 16), xx = idx - yy * sw;
-                            uint32_t v = c;
-                            if (ptype == 1) {  // left: the pixel before the row segment the pixel lies in
-                                v = yy == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + yy, ox - 1);
-                            } else if (ptype == 2) {  // top: the pixel above the run's first row in this column
-                                v = tile_at(tb, oy + (xx >= xx0 ? yy0 : yy0 + 1) - 1, ox + xx);
-                            } else if (ptype == 5) {  // top-left: walk the diagonal until it leaves the run or the sub-rect
-                                const int k = min((int)(((uint32_t)i * sw1inv) >> 16) + 1, xx + 1);
-                                v = tile_at(tb, oy + yy - k, ox + xx - k);
-                            }
-                            sts32(tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u, v);
-                        }
-                    }
-                    __syncwarp();
-                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
-                    vlast = tile_at(tb, oy + ly, ox + li - ly * sw);
-                }
-                e.lastpx = vlast;
+                rq_post(e, RQ_RUN | ((uint32_t)ptype << 8) | ((uint32_t)n << 16), c, 0u);
+                if (ptype) e.lp_wait = e.rposted;  // a predicted run: its last pixel is known once this command is done
                 pos += n;
-                xx0 = xe;
-                ca += 4u * (uint32_t)n;
-                if (xx0 >= sw) {  // next row(s)
-                    const int q = (int)(((uint32_t)xx0 * swinv) >> 16);
-                    xx0 -= q * sw;
-                    yy0 += q;
-                    ca = tb + (uint32_t)((oy + yy0) * 17 + ox + xx0) * 4u;
-                }
             }
             PROF_ADD(c_runs)
         }
-        __syncwarp();
-        // write the whole block and hand its ownership to this frame
-        { PROF_T0
-        if (bw == 16) {
-            for (int p = lane; p < 16 * bh; p += 32) store_px(frame, g, bx0 + (p & 15), by0 + (p >> 4), tile_at(tb, 1 + (p >> 4), 1 + (p & 15)));
-        } else {
-            for (int p = lane; p < bw * bh; p += 32) {
-                const int xx = p % bw, yy = p / bw;
-                store_px(frame, g, bx0 + xx, by0 + yy, tile_at(tb, 1 + yy, 1 + xx));
+        rq_post(e, RQ_END, 0u, 0u);
+      }
+    }
+}
+
+// ---- reconstruction warp ---------------------------------------------------------------------------------------------------
+// Builds the pixels of pixel-coded P blocks from the commands of the chain warp: BEGIN (block, frame, sub-rect) loads the
+// 17 x 17 tile -- tile[1+yy][1+xx] = block pixel, initially the previous frame's block (so pixels of type 3, and the part
+// of a partial block outside the sub-rect, are already in place); row 0 / column 0 = the neighbours above / left in the
+// current frame --, RUN (type, length, colour) fills a run, END writes the block to the frame and records its owner.
+// After every command it publishes the command count and, after a run, the run's last pixel (the context of a following
+// literal, fetch_lastpx).  Commands are executed in order, so the map and the frame see the blocks in bitstream order;
+// before a tile is loaded the motion-vector copies posted so far must have landed (neighbours may be such blocks).
+template <bool SM>
+__device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t sb, int lane) {
+    const Geo& g = w.g;
+    const uint32_t tb = sb + S_TILE, rs = sb + S_RSYNC, sy = sb + S_SYNC;
+    // block state
+    int bi = 0, f = 0, bx0 = 0, by0 = 0, bw = 16, bh = 16, sw = 1, pos = 0, xx0 = 0, yy0 = 0, ox = 1, oy = 1;
+    uint32_t swinv = 65536u, sw1inv = 32768u, ca = tb;
+    uint8_t* frame = w.out;
+    for (uint32_t ridx = 0;; ridx++) {
+        uint4 cmd;
+        const uint32_t slot = sb + S_RQ + 16u * (ridx % RQ);
+        for (uint32_t spins = 0;; spins++) {
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.x), "=r"(cmd.w) : "r"(slot) : "memory");
+            if (cmd.w == ridx + 1u) {
+                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.y), "=r"(cmd.z) : "r"(slot + 8u) : "memory");
+                break;
+            }
+            if ((spins & 31u) == 31u) {
+                if (ldv_shared(sy + 12)) return;
+                if (spins > 2048) __nanosleep(spins > 65536 ? 400 : 50);
             }
         }
-        map.write(bi, (uint32_t)f);
-        if (lane == 0) upd[bi] = 1;
-        __syncwarp();
-        PROF_ADD(c_blkwr) }
-      }
+        const uint32_t op = cmd.x & 0xFFu;
+        if (op == RQ_RUN) {
+            const int ptype = (int)((cmd.x >> 8) & 0xFFu), n = (int)(cmd.x >> 16);
+            const uint32_t c = cmd.y;
+            const int xe = xx0 + n;
+            uint32_t vlast;
+            if (xe <= sw && ptype != 4) {
+                // the run stays in its row (the common case; at most 16 pixels): every source is one fixed step
+                // away -- left: the pixel before the run; top: one tile row up; top-left: one row up, one left;
+                // type 3 keeps the previous frame's pixel that is already in the tile
+                const uint32_t al = ca + 4u * (uint32_t)(n - 1);
+                const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
+                uint32_t v = c;
+                vlast = c;
+                if (ptype == 1) {
+                    v = vlast = lds32(ca - 4u);
+                } else if (ptype == 2) {
+                    v = lds32(a - 68u);
+                    vlast = lds32(al - 68u);
+                } else if (ptype == 5) {
+                    v = lds32(a - 72u);
+                    vlast = lds32(al - 72u);
+                } else if (ptype == 3) {
+                    vlast = lds32(al);
+                }
+                // the chain warp may be waiting for this pixel: out it goes before the fill
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+                if (ptype != 3 && lane < n) sts32(a, v);
+                __syncwarp();
+            } else {
+                if (ptype == 4) {  // gradient chains through the left pixel: serial
+                    if (lane == 0) {
+                        int xx = xx0, yy = yy0;
+                        for (int i = 0; i < n; i++) {
+                            const uint32_t a = tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u;
+                            sts32(a, grad_px(lds32(a - 4), lds32(a - 68), lds32(a - 72)));
+                            if (++xx == sw) {
+                                xx = 0;
+                                yy++;
+                            }
+                        }
+                    }
+                } else if (ptype != 3) {
+                    for (int i = lane; i < n; i += 32) {
+                        const int idx = pos + i;
+                        const int yy = (int)(((uint32_t)idx * swinv) >> 16), xx = idx - yy * sw;
+                        uint32_t v = c;
+                        if (ptype == 1) {  // left: the pixel before the row segment the pixel lies in
+                            v = yy == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + yy, ox - 1);
+                        } else if (ptype == 2) {  // top: the pixel above the run's first row in this column
+                            v = tile_at(tb, oy + (xx >= xx0 ? yy0 : yy0 + 1) - 1, ox + xx);
+                        } else if (ptype == 5) {  // top-left: walk the diagonal until it leaves the run or the sub-rect
+                            const int k = min((int)(((uint32_t)i * sw1inv) >> 16) + 1, xx + 1);
+                            v = tile_at(tb, oy + yy - k, ox + xx - k);
+                        }
+                        sts32(tb + (uint32_t)((oy + yy) * 17 + ox + xx) * 4u, v);
+                    }
+                }
+                __syncwarp();
+                const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                vlast = tile_at(tb, oy + ly, ox + li - ly * sw);
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+            }
+            pos += n;
+            xx0 = xe;
+            ca += 4u * (uint32_t)n;
+            if (xx0 >= sw) {  // next row(s)
+                const int q = (int)(((uint32_t)xx0 * swinv) >> 16);
+                xx0 -= q * sw;
+                yy0 += q;
+                ca = tb + (uint32_t)((oy + yy0) * 17 + ox + xx0) * 4u;
+            }
+        } else if (op == RQ_BEGIN) {
+            bi = (int)(cmd.x >> 8);
+            f = (int)cmd.y;
+            frame = w.out + (size_t)f * g.frame_bytes;
+            const int by = bi / g.nbx, bx = bi - by * g.nbx;
+            bx0 = bx * 16; by0 = by * 16;
+            bw = min(16, g.X - bx0); bh = min(16, g.Y - by0);
+            const int x1 = (int)(cmd.z & 15u), y1 = (int)((cmd.z >> 4) & 15u), x2 = (int)((cmd.z >> 8) & 15u) + 1;
+            sw = x2 - x1;
+            swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;    // idx / sw == (idx * swinv) >> 16 for idx < 272
+            sw1inv = (65536u + (uint32_t)sw) / (uint32_t)(sw + 1);  // same for sw + 1
+            ox = 1 + x1; oy = 1 + y1;
+            pos = 0; xx0 = 0; yy0 = 0;
+            ca = tb + (uint32_t)(oy * 17 + ox) * 4u;
+            // neighbours may be motion-vector blocks of this frame: every copy posted so far must have landed
+            while (ldv_shared(sy + 8) != ldv_shared(sy)) __nanosleep(50);
+            __threadfence_block();
+            const int bA = bi - g.nbx - 1, bT = bi - g.nbx, bL = bi - 1;
+            const PixSrc sA = resolve_src(w, (bx > 0 && by > 0) ? src_now(map.get(bA)) : SRC_PREV0);
+            const PixSrc sT = resolve_src(w, by > 0 ? src_now(map.get(bT)) : SRC_PREV0);
+            const PixSrc sL = resolve_src(w, bx > 0 ? src_now(map.get(bL)) : SRC_PREV0);
+            const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
+            // block rows 2u + (lane >> 4), column lane & 15; then the row above (17 pixels with the corner) and the column to
+            // the left: ten loads per lane with additive addressing
+            uint32_t tv[10];
+            const int cxl = lane & 15, ryl = lane >> 4;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int yy = 2 * u + ryl;
+                tv[u] = (cxl < bw && yy < bh) ? src_px(sP, g, bx0 + cxl, by0 + yy) : 0u;
+            }
+            tv[8] = (lane < 17 && by > 0 && (lane > 0 ? lane - 1 < bw : bx > 0)) ? src_px(lane == 0 ? sA : sT, g, bx0 + lane - 1, by0 - 1) : 0u;
+            tv[9] = (lane < 16 && bx > 0 && lane < bh) ? src_px(sL, g, bx0 - 1, by0 + lane) : 0u;
+            const uint32_t a0 = tb + (uint32_t)((1 + (lane >> 4)) * 17 + 1 + (lane & 15)) * 4u;
+#pragma unroll
+            for (int u = 0; u < 8; u++) sts32(a0 + (uint32_t)u * 136u, tv[u]);
+            if (lane < 17) sts32(tb + (uint32_t)lane * 4u, tv[8]);
+            if (lane < 16) sts32(tb + (uint32_t)(1 + lane) * 68u, tv[9]);
+            __syncwarp();
+        } else {  // RQ_END: write the whole block and hand its ownership to this frame
+            if (bw == 16) {
+                for (int p = lane; p < 16 * bh; p += 32) store_px(frame, g, bx0 + (p & 15), by0 + (p >> 4), tile_at(tb, 1 + (p >> 4), 1 + (p & 15)));
+            } else {
+                for (int p = lane; p < bw * bh; p += 32) {
+                    const int xx = p % bw, yy = p / bw;
+                    store_px(frame, g, bx0 + xx, by0 + yy, tile_at(tb, 1 + yy, 1 + xx));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                map.write(bi, (uint32_t)f);
+                w.upd[(size_t)f * g.nb + bi] = 1;
+            }
+            __syncwarp();
+        }
+        __threadfence_block();
+        stv_shared(rs + 4, ridx + 1);
     }
 }
 
@@ -1691,12 +1781,17 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     BlockMap<SM> map;
     map.sbase = sb + s_map_off(g.nb);
     map.g = SM ? nullptr : w.gmap + (size_t)blockIdx.x * g.nb;
-    if (threadIdx.x < 4) sts32(sb + S_SYNC + 4u * threadIdx.x, 0u);
+    if (threadIdx.x < 4) {
+        sts32(sb + S_SYNC + 4u * threadIdx.x, 0u);
+        sts32(sb + S_RSYNC + 4u * threadIdx.x, 0u);
+    }
+    for (int i = threadIdx.x; i < RQ; i += 32 * DEC_WARPS) sts128(sb + S_RQ + 16u * i, 0u, 0u, 0u, 0u);  // no slot carries a sequence number yet
     for (int i = threadIdx.x; i < g.nb; i += 32 * DEC_WARPS) map.set(i, 0xFFFFFFFFu);  // everything lives in prev0
     __threadfence_block();
     __syncthreads();
     if (warp != 0) {
-        if (warp != 4) helper_loop<SM>(w, map, sb, lane);
+        if (warp == 1) recon_loop<SM>(w, map, sb, lane);
+        else if (warp != 4) helper_loop<SM>(w, map, sb, lane);
         return;
     }
     Ent e;
@@ -1704,6 +1799,8 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     e.f0 = w.f0;
     e.lastpx = 0;
     e.head = 0;
+    e.rposted = 0;
+    e.lp_wait = 0;
     e.nleft = RANS_BLOCK;
     e.x = 0;
     e.w0 = e.w1 = e.k8 = 0;
@@ -1755,8 +1852,10 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
                 __syncwarp();
                 for (int t = 0; t < NUM_FIXED_CX; t++) fixed_rebuild(sb, t, lane, false);
             }
+            rq_drain(e);
             cmd_drain(e);
             publish_progress(w, f, lane);
+            e.lp_wait = 0;
             const uint32_t code = (uint32_t)f | (df.kind == DK_FLAT ? SRC_FLAT : 0u);
             for (int i = lane; i < g.nb; i += 32) map.write(i, code);  // the whole frame is new
             __syncwarp();
@@ -1784,6 +1883,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
         decode_p<SM, V2>(w, map, e, frame, f, lane);
         __threadfence_block();
     }
+    rq_drain(e);
     cmd_drain(e);
     __threadfence();
     publish_progress(w, ch.first + ch.count, lane);
