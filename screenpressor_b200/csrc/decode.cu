@@ -218,7 +218,7 @@ struct Ent {
 #ifdef SCPR_PROF
     long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
               c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0,
-              c_raw = 0, n_raw = 0, n_miss = 0, c_drain = 0;
+              c_raw = 0, n_raw = 0, n_miss = 0, c_drain = 0, c_lpwait = 0, n_lpwait = 0;
 #endif
     uint32_t x;
     uint32_t w0, w1, k8;      // window: stream bytes from bit k8 of w0 on
@@ -954,12 +954,14 @@ __device__ __forceinline__ void stv_shared(uint32_t a, uint32_t v) { asm volatil
 __device__ __forceinline__ void fetch_lastpx(Ent& e) {
     if (e.lp_wait) {
         // {commands executed up to and including the last run, that run's last pixel}: one 64-bit word, written at once
+        PROF_T0
         uint2 lp;
         do {
             asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lp.x), "=r"(lp.y) : "r"(e.sb + S_RSYNC + 8u) : "memory");
         } while ((int)(lp.x - e.lp_wait) < 0);
         e.lastpx = lp.y;
         e.lp_wait = 0;
+        PROF_ADD(c_lpwait) PROF_CNT(n_lpwait)
     }
 }
 // The context of a colour byte is made of the two bytes coded before it, quantised to 6 bits: for byte 0 those
@@ -1404,20 +1406,18 @@ __device__ void mv_copy(const DecWork& w, const BlockMap<SM>& map, int f, int bi
         sq[q] = resolve_src(w, src_before(map.get(qy * g.nbx + qx), f));
     }
     const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
+    // eight unconditional loads from clamped coordinates (all in flight together), flat colours patched in afterwards
     uint32_t px[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
         const int p = lane + 32 * u, xx = p & 15, yy = p >> 4;
-        const int x = bx0 + xx, y = by0 + yy;
-        px[u] = 0;
-        if (xx < bw && yy < bh) {
-            if (x >= x1 && x < x2 && y >= y1 && y < y2) {
-                const int sx = min(max(x + mx, 0), g.X - 1), sy = min(max(y + my, 0), g.Y - 1);
-                const int q = ((sx >> 4) > cbx ? 1 : 0) + ((sy >> 4) > cby ? 2 : 0);
-                px[u] = src_px(q == 0 ? sq[0] : q == 1 ? sq[1] : q == 2 ? sq[2] : sq[3], g, sx, sy);
-            } else
-                px[u] = src_px(sP, g, x, y);  // the rest of a partial block: the previous frame, same place
-        }
+        const int x = min(bx0 + xx, g.X - 1), y = min(by0 + yy, g.Y - 1);
+        const bool in = x >= x1 && x < x2 && y >= y1 && y < y2;
+        const int sx = in ? min(max(x + mx, 0), g.X - 1) : x, sy = in ? min(max(y + my, 0), g.Y - 1) : y;
+        const int q = ((sx >> 4) > cbx ? 1 : 0) + ((sy >> 4) > cby ? 2 : 0);
+        const PixSrc& sS = !in ? sP : q == 0 ? sq[0] : q == 1 ? sq[1] : q == 2 ? sq[2] : sq[3];  // outside the sub-rect: the previous frame, same place
+        const uint32_t v = load_px(sS.base, g, sx, sy);
+        px[u] = sS.flat ? sS.clr : v;
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -1483,7 +1483,7 @@ __device__ __forceinline__ void cmd_drain(Ent& e) {
 }
 
 // commands to the reconstruction warp (uint4): x = op | ..., see recon_loop
-constexpr uint32_t RQ_BEGIN = 1u, RQ_RUN = 2u, RQ_END = 3u;
+constexpr uint32_t RQ_BEGIN = 1u, RQ_RUN = 2u, RQ_END = 3u, RQ_LOAD = 4u;
 __device__ __forceinline__ void rq_post(Ent& e, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t rs = e.sb + S_RSYNC;
     if ((e.rposted & 63u) == 0u)  // ring space, checked once per 64 commands
@@ -1574,6 +1574,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
         const int bw = min(16, g.X - bx0), bh = min(16, g.Y - by0);
         int x1 = bx0, y1 = by0, x2 = bx0 + bw, y2 = by0 + bh;
         // ---- pixel-coded block: the chain warp decodes its symbols, the reconstruction warp builds its pixels ----
+        rq_post(e, RQ_LOAD | ((uint32_t)bi << 8), (uint32_t)f, 0u);  // the tile load starts while the sub-rect is still being decoded
         if ((bt - 1) & 1) {
             x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
             y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
@@ -1584,8 +1585,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             if (x1 >= x2) x1 = x2 - 1;
             if (y1 >= y2) y1 = y2 - 1;
         }
-        rq_post(e, RQ_BEGIN | ((uint32_t)bi << 8), (uint32_t)f,
-                (uint32_t)(x1 - bx0) | ((uint32_t)(y1 - by0) << 4) | ((uint32_t)(x2 - 1 - bx0) << 8) | ((uint32_t)(y2 - 1 - by0) << 12));
+        rq_post(e, RQ_BEGIN, 0u, (uint32_t)(x1 - bx0) | ((uint32_t)(y1 - by0) << 4) | ((uint32_t)(x2 - 1 - bx0) << 8) | ((uint32_t)(y2 - 1 - by0) << 12));
         {
             PROF_T0
             int pos = 0, ptype = 0;
@@ -1607,10 +1607,10 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
 }
 
 // ---- reconstruction warp ---------------------------------------------------------------------------------------------------
-// Builds the pixels of pixel-coded P blocks from the commands of the chain warp: BEGIN (block, frame, sub-rect) loads the
+// Builds the pixels of pixel-coded P blocks from the commands of the chain warp: LOAD (block, frame) loads the
 // 17 x 17 tile -- tile[1+yy][1+xx] = block pixel, initially the previous frame's block (so pixels of type 3, and the part
 // of a partial block outside the sub-rect, are already in place); row 0 / column 0 = the neighbours above / left in the
-// current frame --, RUN (type, length, colour) fills a run, END writes the block to the frame and records its owner.
+// current frame --, BEGIN (sub-rect) sets the cursor, RUN (type, length, colour) fills a run, END writes the block to the frame and records its owner.
 // After every command it publishes the command count and, after a run, the run's last pixel (the context of a following
 // literal, fetch_lastpx).  Commands are executed in order, so the map and the frame see the blocks in bitstream order;
 // before a tile is loaded the motion-vector copies posted so far must have landed (neighbours may be such blocks).
@@ -1622,7 +1622,13 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
     int bi = 0, f = 0, bx0 = 0, by0 = 0, bw = 16, bh = 16, sw = 1, pos = 0, xx0 = 0, yy0 = 0, ox = 1, oy = 1;
     uint32_t swinv = 65536u, sw1inv = 32768u, ca = tb;
     uint8_t* frame = w.out;
+#ifdef SCPR_PROF
+    long long r_pub = 0, r_run = 0, r_nrun = 0, r_load = 0, r_nload = 0, r_end = 0, r_idle = 0;
+#endif
     for (uint32_t ridx = 0;; ridx++) {
+#ifdef SCPR_PROF
+        const long long ti__ = clock64();
+#endif
         uint4 cmd;
         const uint32_t slot = sb + S_RQ + 16u * (ridx % RQ);
         for (uint32_t spins = 0;; spins++) {
@@ -1632,38 +1638,54 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
                 break;
             }
             if ((spins & 31u) == 31u) {
+#ifdef SCPR_PROF
+                if (ldv_shared(sy + 12) && lane == 0)
+                    printf("[rec prof] runs %lld: detect->publish %.0f cyc, whole run %.0f cyc | loads %lld: %.0f cyc | ends %.0f cyc | idle %.1f Mcyc\n", r_nrun,
+                           (double)r_pub / (double)max(1LL, r_nrun), (double)r_run / (double)max(1LL, r_nrun), r_nload, (double)r_load / (double)max(1LL, r_nload),
+                           (double)r_end / (double)max(1LL, r_nload), r_idle * 1e-6);
+#endif
                 if (ldv_shared(sy + 12)) return;
                 if (spins > 2048) __nanosleep(spins > 65536 ? 400 : 50);
             }
         }
         const uint32_t op = cmd.x & 0xFFu;
+#ifdef SCPR_PROF
+        const long long td__ = clock64();
+        r_idle += td__ - ti__;
+#endif
         if (op == RQ_RUN) {
             const int ptype = (int)((cmd.x >> 8) & 0xFFu), n = (int)(cmd.x >> 16);
             const uint32_t c = cmd.y;
             const int xe = xx0 + n;
-            uint32_t vlast;
+            // The chain warp may be waiting for the run's last pixel (the context of a literal that follows): every source
+            // of a predicted pixel lies outside its run, so that pixel is computed and published first, the fill follows.
+            if (ptype != 4) {
+                const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16), lx = li - ly * sw;
+                uint32_t vlast = c;
+                if (ptype == 1) vlast = ly == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + ly, ox - 1);
+                else if (ptype == 2) vlast = tile_at(tb, oy + (lx >= xx0 ? yy0 : yy0 + 1) - 1, ox + lx);
+                else if (ptype == 3) vlast = tile_at(tb, oy + ly, ox + lx);
+                else if (ptype == 5) {
+                    const int k = min((int)(((uint32_t)(n - 1) * sw1inv) >> 16) + 1, lx + 1);
+                    vlast = tile_at(tb, oy + ly - k, ox + lx - k);
+                }
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+#ifdef SCPR_PROF
+                r_pub += clock64() - td__;
+#endif
+            }
             if (xe <= sw && ptype != 4) {
                 // the run stays in its row (the common case; at most 16 pixels): every source is one fixed step
                 // away -- left: the pixel before the run; top: one tile row up; top-left: one row up, one left;
                 // type 3 keeps the previous frame's pixel that is already in the tile
-                const uint32_t al = ca + 4u * (uint32_t)(n - 1);
-                const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
-                uint32_t v = c;
-                vlast = c;
-                if (ptype == 1) {
-                    v = vlast = lds32(ca - 4u);
-                } else if (ptype == 2) {
-                    v = lds32(a - 68u);
-                    vlast = lds32(al - 68u);
-                } else if (ptype == 5) {
-                    v = lds32(a - 72u);
-                    vlast = lds32(al - 72u);
-                } else if (ptype == 3) {
-                    vlast = lds32(al);
+                if (ptype != 3) {
+                    const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
+                    uint32_t v = c;
+                    if (ptype == 1) v = lds32(ca - 4u);
+                    else if (ptype == 2) v = lds32(a - 68u);
+                    else if (ptype == 5) v = lds32(a - 72u);
+                    if (lane < n) sts32(a, v);
                 }
-                // the chain warp may be waiting for this pixel: out it goes before the fill
-                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
-                if (ptype != 3 && lane < n) sts32(a, v);
                 __syncwarp();
             } else {
                 if (ptype == 4) {  // gradient chains through the left pixel: serial
@@ -1695,9 +1717,11 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
                     }
                 }
                 __syncwarp();
-                const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
-                vlast = tile_at(tb, oy + ly, ox + li - ly * sw);
-                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+                if (ptype == 4) {
+                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16);
+                    const uint32_t vlast = tile_at(tb, oy + ly, ox + li - ly * sw);
+                    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+                }
             }
             pos += n;
             xx0 = xe;
@@ -1708,13 +1732,7 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
                 yy0 += q;
                 ca = tb + (uint32_t)((oy + yy0) * 17 + ox + xx0) * 4u;
             }
-        } else if (op == RQ_BEGIN) {
-            bi = (int)(cmd.x >> 8);
-            f = (int)cmd.y;
-            frame = w.out + (size_t)f * g.frame_bytes;
-            const int by = bi / g.nbx, bx = bi - by * g.nbx;
-            bx0 = bx * 16; by0 = by * 16;
-            bw = min(16, g.X - bx0); bh = min(16, g.Y - by0);
+        } else if (op == RQ_BEGIN) {  // the sub-rect the runs cover
             const int x1 = (int)(cmd.z & 15u), y1 = (int)((cmd.z >> 4) & 15u), x2 = (int)((cmd.z >> 8) & 15u) + 1;
             sw = x2 - x1;
             swinv = (65536u + (uint32_t)sw - 1) / (uint32_t)sw;    // idx / sw == (idx * swinv) >> 16 for idx < 272
@@ -1722,6 +1740,13 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             ox = 1 + x1; oy = 1 + y1;
             pos = 0; xx0 = 0; yy0 = 0;
             ca = tb + (uint32_t)(oy * 17 + ox) * 4u;
+        } else if (op == RQ_LOAD) {  // block and frame: load the tile
+            bi = (int)(cmd.x >> 8);
+            f = (int)cmd.y;
+            frame = w.out + (size_t)f * g.frame_bytes;
+            const int by = bi / g.nbx, bx = bi - by * g.nbx;
+            bx0 = bx * 16; by0 = by * 16;
+            bw = min(16, g.X - bx0); bh = min(16, g.Y - by0);
             // neighbours may be motion-vector blocks of this frame: every copy posted so far must have landed
             while (ldv_shared(sy + 8) != ldv_shared(sy)) __nanosleep(50);
             __threadfence_block();
@@ -1732,15 +1757,20 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             const PixSrc sP = resolve_src(w, src_before(map.get(bi), f));
             // block rows 2u + (lane >> 4), column lane & 15; then the row above (17 pixels with the corner) and the column to
             // the left: ten loads per lane with additive addressing
+            // All ten loads are issued unconditionally from clamped coordinates and masked afterwards: with a branch around
+            // each of them they went to memory one after the other (ten round trips instead of one).
             uint32_t tv[10];
             const int cxl = lane & 15, ryl = lane >> 4;
+            const int xc = min(bx0 + cxl, g.X - 1);
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int yy = 2 * u + ryl;
-                tv[u] = (cxl < bw && yy < bh) ? src_px(sP, g, bx0 + cxl, by0 + yy) : 0u;
-            }
-            tv[8] = (lane < 17 && by > 0 && (lane > 0 ? lane - 1 < bw : bx > 0)) ? src_px(lane == 0 ? sA : sT, g, bx0 + lane - 1, by0 - 1) : 0u;
-            tv[9] = (lane < 16 && bx > 0 && lane < bh) ? src_px(sL, g, bx0 - 1, by0 + lane) : 0u;
+            for (int u = 0; u < 8; u++) tv[u] = load_px(sP.base, g, xc, min(by0 + 2 * u + ryl, g.Y - 1));
+            const PixSrc& sH = lane == 0 ? sA : sT;
+            tv[8] = load_px(sH.base, g, min(max(bx0 + lane - 1, 0), g.X - 1), max(by0 - 1, 0));
+            tv[9] = load_px(sL.base, g, max(bx0 - 1, 0), min(by0 + (lane & 15), g.Y - 1));
+#pragma unroll
+            for (int u = 0; u < 8; u++) tv[u] = (cxl < bw && 2 * u + ryl < bh) ? (sP.flat ? sP.clr : tv[u]) : 0u;
+            tv[8] = (lane < 17 && by > 0 && (lane > 0 ? lane - 1 < bw : bx > 0)) ? (sH.flat ? sH.clr : tv[8]) : 0u;
+            tv[9] = (lane < 16 && bx > 0 && lane < bh) ? (sL.flat ? sL.clr : tv[9]) : 0u;
             const uint32_t a0 = tb + (uint32_t)((1 + (lane >> 4)) * 17 + 1 + (lane & 15)) * 4u;
 #pragma unroll
             for (int u = 0; u < 8; u++) sts32(a0 + (uint32_t)u * 136u, tv[u]);
@@ -1763,8 +1793,16 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             }
             __syncwarp();
         }
-        __threadfence_block();
-        stv_shared(rs + 4, ridx + 1);
+#ifdef SCPR_PROF
+        if (op == RQ_RUN) { r_run += clock64() - td__; r_nrun++; }
+        else if (op == RQ_LOAD) { r_load += clock64() - td__; r_nload++; }
+        else if (op == RQ_END) r_end += clock64() - td__;
+#endif
+        // executed-command count: the chain warp needs it when it drains (always right after an END) and, coarsely, for ring space
+        if (op != RQ_RUN || (ridx & 15u) == 15u) {
+            __threadfence_block();
+            stv_shared(rs + 4, ridx + 1);
+        }
     }
 }
 
@@ -1891,10 +1929,10 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
 #ifdef SCPR_PROF
     if (lane == 0)
         printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc; %lld serial, %lld rescales) | "
-               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f | cache misses %lld\n",
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f | cache misses %lld | lastpx waits %.1f / %lld\n",
                (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
-               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6, e.n_miss);
+               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6, e.n_miss, e.c_lpwait * 1e-6, e.n_lpwait);
 #endif
     // leave the cached contexts, the fixed tables and the kinds behind for the next call (v2 tables are already in place)
     __syncwarp();
