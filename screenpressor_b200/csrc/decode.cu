@@ -1440,14 +1440,20 @@ __device__ void helper_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t 
         uint32_t idx = 0;
         if (lane == 0) idx = atom_add_shared(sy + 4, 1u);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-        for (uint32_t ns = 64;;) {  // idle most of the time on sparse content: back off so the polls stay out of the chain warp's way
-            if ((int)(ldv_shared(sy) - idx) > 0) break;
-            if (ldv_shared(sy + 12)) return;  // quit is only raised after a drain: nothing published is left behind
+        // the slot carries the sequence number of the command it holds (written last, as one 64-bit word with the first
+        // argument): poll the slot itself.  Idle most of the time on sparse content: back off.
+        uint4 cmd;
+        const uint32_t slot = sb + S_RING + 16u * (idx % RING);
+        for (uint32_t ns = 64;;) {
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.x), "=r"(cmd.w) : "r"(slot) : "memory");
+            if (cmd.w == idx + 1u) {
+                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.y), "=r"(cmd.z) : "r"(slot + 8u) : "memory");
+                break;
+            }
+            if (ldv_shared(sy + 12)) return;  // quit is only raised after a drain: nothing posted is left behind
             __nanosleep(ns);
             ns = min(ns * 2u, 2048u);
         }
-        __threadfence_block();
-        const uint4 cmd = lds128(sb + S_RING + 16u * (idx % RING));
         mv_copy<SM>(w, map, (int)(cmd.x >> 16), (int)(cmd.x & 0xFFFFu), cmd.y, (int)(int16_t)(cmd.z & 0xFFFFu), (int)(int16_t)(cmd.z >> 16), lane);
         __threadfence_block();
         __syncwarp();
@@ -1458,11 +1464,13 @@ __device__ void helper_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t 
 // reused only while fewer than RING - DEC_WARPS commands are outstanding.
 __device__ __forceinline__ void cmd_push(Ent& e, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t sy = e.sb + S_SYNC;
-    while (e.head - ldv_shared(sy + 8) > (uint32_t)(RING - DEC_WARPS)) __nanosleep(100);
-    sts128(e.sb + S_RING + 16u * (e.head % RING), x, y, z, 0u);
-    __threadfence_block();
+    if ((e.head & 15u) == 0u)  // ring space, checked once per 16 commands
+        while (e.head - ldv_shared(sy + 8) > (uint32_t)(RING - DEC_WARPS - 16)) __nanosleep(100);
+    const uint32_t slot = e.sb + S_RING + 16u * (e.head % RING);
     e.head++;
-    stv_shared(sy, e.head);
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot + 8u), "r"(y), "r"(z) : "memory");
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(x), "r"(e.head) : "memory");
+    stv_shared(sy, e.head);  // the count, for "have all copies landed" (cmd_drain, recon_loop)
 }
 // every frame below f is final (its copies have drained): tell the host, which overlaps the gather of untouched blocks
 // and the download of finished frames with the rest of the chain
@@ -1824,6 +1832,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
         sts32(sb + S_RSYNC + 4u * threadIdx.x, 0u);
     }
     for (int i = threadIdx.x; i < RQ; i += 32 * DEC_WARPS) sts128(sb + S_RQ + 16u * i, 0u, 0u, 0u, 0u);  // no slot carries a sequence number yet
+    for (int i = threadIdx.x; i < RING; i += 32 * DEC_WARPS) sts128(sb + S_RING + 16u * i, 0u, 0u, 0u, 0u);
     for (int i = threadIdx.x; i < g.nb; i += 32 * DEC_WARPS) map.set(i, 0xFFFFFFFFu);  // everything lives in prev0
     __threadfence_block();
     __syncthreads();
