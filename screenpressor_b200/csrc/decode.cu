@@ -45,6 +45,7 @@ struct DecChain {
 struct DecWork {
     Geo g;              // geometry of the OUTPUT frames (pitch = caller's pitch)
     const uint8_t* stream;
+    uint32_t stream_bytes;  // bytes of the device copy incl. its zero padding, a multiple of 4
     const DecFrame* frames;
     const DecChain* chains;
     uint8_t* states;
@@ -223,6 +224,7 @@ struct Ent {
     uint32_t x;
     uint32_t w0, w1, k8;      // window: stream bytes from bit k8 of w0 on
     const uint32_t* wp;       // address of w1
+    const uint32_t* wend;     // end of the stream copy (bytes of all frames of the call + padding)
     int nleft;                // symbols until the next RansDecInit
     uint32_t lastpx;          // the pixel before the next run: the colour contexts are functions of it (screencap.cpp:371-372, 616-624)
     uint32_t sb;              // shared-memory base address
@@ -251,7 +253,8 @@ __device__ __forceinline__ void rd_skip(Ent& e, uint32_t bits) {  // bits = 8 * 
     if (e.k8 >= 32) {
         e.k8 -= 32;
         e.w0 = e.w1;
-        e.w1 = __ldg(++e.wp);
+        ++e.wp;
+        e.w1 = e.wp < e.wend ? __ldg(e.wp) : 0u;  // a corrupt stream may ask for more bytes than the call was given: zeros
     }
 }
 __device__ __forceinline__ void rdec_init(Ent& e) {  // RansDecInit
@@ -1040,7 +1043,8 @@ __device__ __noinline__ int rc_val(Ent& e, uint32_t* cnt, int maxc, uint32_t ste
     // Decode (sub.cpp:49-61)
     uint32_t code = e.rc_code - cum * r, range = r * f;
     while (range < RC_TOP) {
-        code = (code << 8) | *e.rc_p++;
+        code = (code << 8) | (e.rc_p < reinterpret_cast<const uint8_t*>(e.wend) ? *e.rc_p : 0u);
+        e.rc_p++;
         range <<= 8;
     }
     e.rc_code = code;
@@ -1852,6 +1856,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     e.x = 0;
     e.w0 = e.w1 = e.k8 = 0;
     e.wp = nullptr;
+    e.wend = reinterpret_cast<const uint32_t*>(w.stream + w.stream_bytes);
     e.sb = sb;
     e.lane = lane;
     e.v2 = reinterpret_cast<uint32_t*>(e.m);
@@ -2164,6 +2169,7 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     memset(&w, 0, sizeof(w));
     w.g = g;
     w.stream = (const uint8_t*)c->dec_stream.p;
+    w.stream_bytes = (uint32_t)(((size_t)off + 64) & ~(size_t)3);
     w.frames = (const DecFrame*)c->dec_desc.p;
     w.chains = d_chains;
     w.states = (uint8_t*)c->dec_state.p;

@@ -378,6 +378,41 @@ def test_vfw_session_and_avi_container(scpr, tmp_path):
         assert lossy.Compress(clip[i], quality=5000)[0] == ref.CompressFrame(clip[i], 0 if i == 0 else 1, loss=2)[0]
 
 
+def test_corrupt_streams_do_not_take_the_device_down(scpr):
+    """truncated and random payloads: the decoder may produce garbage but must return, stay inside its buffers (reads past
+    the stream see zeros) and leave the CUDA context usable"""
+    w, h, n = 200, 120, 16
+    clip, keys = fuzz_clip(w, h, n, 41, 32, 16)
+    stream, sizes, fts = _new(scpr, w, h, 32).CompressClip(clip, keys)
+    frames, pos = [], 0
+    for i in range(n):
+        frames.append(bytes(stream[pos:pos + int(sizes[i])])); pos += int(sizes[i])
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        bad = list(frames)
+        for i in range(n):
+            if len(bad[i]) > 8 and rng.random() < 0.6:
+                body = bytearray(bad[i])
+                if trial % 2 == 0:
+                    body = body[: 1 + len(body) // 3]                      # truncated
+                else:
+                    k = rng.integers(1, len(body), size=max(1, len(body) // 8))
+                    for j in k:
+                        body[j] = int(rng.integers(0, 256))                 # noise, header byte kept
+                bad[i] = bytes(body)
+        dec = _new(scpr, w, h, 32)
+        data = np.frombuffer(b"".join(bad), np.uint8)
+        out = dec.DecompressClip(data, np.array([len(b) for b in bad], np.uint32), fts)
+        assert out.shape == (n, w * h * 4)
+    for ver_byte in (0x32, 0x22, 0x12):   # pure noise behind a valid I-frame header of every generation
+        dec = _new(scpr, w, h, 32)
+        junk = bytes([ver_byte]) + bytes(rng.integers(0, 256, 4000, dtype=np.uint8))
+        dec.DecompressFrame(junk, None, 0)
+        dec.DecompressFrame(b"\x01" + bytes(rng.integers(0, 256, 500, dtype=np.uint8)), None, 1)
+    good = _new(scpr, w, h, 32).DecompressClip(stream, sizes, fts)
+    assert np.array_equal(good.reshape(n, -1), clip.reshape(n, -1))
+
+
 def test_error_behaviour(scpr):
     dec = _new(scpr, 64, 48, 32)
     with pytest.raises(scpr.ScprError):          # P before any I: the reference returns 0 (screencap.cpp:1699)
