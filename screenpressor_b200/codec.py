@@ -20,7 +20,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscpr_b200.so")
+LIB_PATH = os.environ.get("SCPR_LIB") or os.path.join(_HERE, "libscpr_b200.so")  # SCPR_LIB: A/B runs of two builds (tools/ab.sh)
 
 SCPR_E_CUDA, SCPR_E_PARAM, SCPR_E_UNSUPPORTED, SCPR_E_DSTSIZE, SCPR_E_NODEVICE = -1000, -1001, -1002, -1003, -1004
 
