@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <vector>
 
 #include "../../include/scpr_c.h"
@@ -221,6 +222,10 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     CK(cudaSetDevice(c->device));
     if (n <= 0) return 0;
     StageTimer tm(st);
+    // host wall clock between the synchronisation points (SCPR_TIMING): what a per-frame caller pays besides the kernels
+    const auto hw0 = std::chrono::steady_clock::now();
+    double hw[6] = {0, 0, 0, 0, 0, 0};
+    auto hmark = [&](int k) { hw[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hw0).count(); };
 
     // ---- pass 1: frame scan + changed-block lists for every frame ------------------------------
     TRY(c->blkinfo.ensure((size_t)n * g.nb * 4));
@@ -256,6 +261,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         for (int f = 0; f < n; f++) summary[f].changed = s2[f].changed;
     }
     CK(cudaStreamSynchronize(st));
+    hmark(0);
 
     // ---- host plan: frame types and chains (CScreenCapt::CompressFrame, screencap.cpp:1456-1518) --
     std::vector<uint8_t> ftype(n);
@@ -400,6 +406,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     if (n_p) CK(cudaMemcpyAsync(hdr.data(), c->hdr.p, (size_t)n * sizeof(PFrameHdr), cudaMemcpyDeviceToHost, st));
     if (n_i) CK(cudaMemcpyAsync(ihdr.data(), c->ihdr.p, (size_t)n_i * sizeof(IFrameHdr), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    hmark(1);
 
     // ---- event layout, chains, rANS blocks ----------------------------------------------------
     std::vector<uint32_t> frame_ev_off(n + 1, 0), frame_nev(n, 0);
@@ -474,6 +481,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         launch_replay(rw, st, &c->launches);
         tm.mark("replay");
         CK(cudaStreamSynchronize(st));  // `cb` and `chains` are host vectors read by the async copies above
+        hmark(2);
     }
     if (n_rb) {
         TRY(c->rblks.ensure((size_t)n_rb * sizeof(RansBlk)));
@@ -484,6 +492,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         CK(cudaMemcpyAsync(rblks.data(), c->rblks.p, (size_t)n_rb * sizeof(RansBlk), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    hmark(3);
 
     // ---- output layout -----------------------------------------------------------------------------
     std::vector<uint64_t> frame_out(n + 1, 0);
@@ -529,6 +538,10 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     CK(cudaMemcpyAsync(c->prev.p, d_frames + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
     tm.mark("assemble+d2h");
     CK(cudaStreamSynchronize(st));
+    hmark(4);
+    if (tm.on)
+        fprintf(stderr, "[scpr timing] encode_batch host wall: scan+sync %.3f | stage A+sync %.3f | replay+sync %.3f | rans+sync %.3f | out+sync %.3f ms\n",
+                hw[0], hw[1] - hw[0], hw[2] ? hw[2] - hw[1] : 0.0, hw[3] - (hw[2] ? hw[2] : hw[1]), hw[4] - hw[3]);
     tm.report("encode_batch");
     if (tm.on) mv_stats_report();
     for (int f = 0; f < n; f++) {
