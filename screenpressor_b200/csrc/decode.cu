@@ -1289,19 +1289,21 @@ __device__ __forceinline__ void irow_flush(const Geo& g, uint8_t* frame, uint32_
         for (int x = lane; x < g.X; x += 32) store_px(frame, g, x, y, lds32(row + 4u * (uint32_t)x));
     }
 }
+// commands to the reconstruction warp (uint4): x = op | ..., see recon_loop
+constexpr uint32_t RQ_BEGIN = 1u, RQ_RUN = 2u, RQ_END = 3u, RQ_LOAD = 4u, RQ_IBEGIN = 5u, RQ_IRUN = 6u;
+// Chain-warp side: symbols only.  Every run goes to the reconstruction warp (recon_loop: RQ_IBEGIN / RQ_IRUN), which
+// owns the two row buffers, fills and flushes; the pixel before a literal comes back through fetch_lastpx.
+__device__ __forceinline__ void rq_post(Ent& e, uint32_t x, uint32_t y, uint32_t z);
 template <bool V2>
-__device__ void decode_i_rows(const DecWork& w, Ent& e, uint8_t* frame, int lane, uint32_t rb) {
-    const Geo& g = w.g;
-    const int X = g.X, Y = g.Y;
-    const bool padded = ((X * 3 + 3) & ~3) != X * 3;
-    const uint32_t rowbytes = (uint32_t)X * 4u;
+__device__ void decode_i_rows(const DecWork& w, Ent& e, int f, int lane) {
+    const int X = w.g.X, Y = w.g.Y;
     int x = 0, y = 0;    // the next pixel
     int ptype = 0;
     int hdr = X + 1;
-    uint32_t lastv = 0;  // the pixel before it in raster order
     bool header = true;
+    rq_post(e, RQ_IBEGIN, (uint32_t)f, 0u);
     while (y < Y) {
-        uint32_t c = lastv;  // type 1: the previous pixel in raster order, whatever the row
+        uint32_t c = 0;
         int n;
         if (header) {  // first row and one pixel: (rgb, n) pairs, lengths in ntab[0] (screencap.cpp:423-438)
             c = V2 ? rc_rgb(e) : dec_rgb(e);
@@ -1312,62 +1314,13 @@ __device__ void decode_i_rows(const DecWork& w, Ent& e, uint8_t* frame, int lane
         } else
             n = dec_run<V2>(e, ptype, c);
         if (n <= 0) break;
-        PROF_T0
-        const uint32_t r0 = rb + (uint32_t)(y & 1) * rowbytes, r1 = rb + (uint32_t)((y + 1) & 1) * rowbytes;  // rows y (and y - 2) / y + 1 (and y - 1)
-        if (ptype == 0 || ptype == 1) {
-            for (int i = lane; i < n; i += 32) {
-                const int xi = x + i;
-                if (xi < X) sts32(r0 + 4u * (uint32_t)xi, c);
-                else if (y + 1 < Y) sts32(r1 + 4u * (uint32_t)(xi - X), c);
-            }
-            lastv = c;
-        } else if (ptype == 2 || ptype == 5) {  // sources lie strictly before the run: the lanes work independently
-            uint32_t myv = 0;
-            for (int i = lane; i < n; i += 32) {
-                int xi = x + i, yi = y;
-                uint32_t cur = r0, up = r1;
-                if (xi >= X) {
-                    xi -= X; yi++;
-                    cur = r1; up = r0;
-                }
-                if (yi < Y) {
-                    if (ptype == 2) myv = lds32(up + 4u * (uint32_t)xi);
-                    else if (xi > 0) myv = lds32(up + 4u * (uint32_t)(xi - 1));
-                    else myv = padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1));  // tail of row yi - 2
-                    sts32(cur + 4u * (uint32_t)xi, myv);
-                }
-            }
-            lastv = __shfl_sync(0xFFFFFFFFu, myv, (n - 1) & 31);
-        } else {  // gradient chains through the left pixel: one lane
-            uint32_t myv = 0;
-            if (lane == 0) {
-                int xi = x, yi = y;
-                uint32_t cur = r0, up = r1, left = lastv;
-                for (int i = 0; i < n && yi < Y; i++) {
-                    const uint32_t top = lds32(up + 4u * (uint32_t)xi);
-                    const uint32_t tlv = xi > 0 ? lds32(up + 4u * (uint32_t)(xi - 1))
-                                                : (padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1)));
-                    myv = grad_px(left, top, tlv);
-                    sts32(cur + 4u * (uint32_t)xi, myv);
-                    left = myv;
-                    if (++xi == X) {
-                        xi = 0; yi++;
-                        const uint32_t t = cur; cur = up; up = t;
-                    }
-                }
-            }
-            lastv = __shfl_sync(0xFFFFFFFFu, myv, 0);
-        }
-        __syncwarp();
+        rq_post(e, RQ_IRUN | ((uint32_t)ptype << 8) | ((uint32_t)n << 16), c, 0u);
+        if (ptype) e.lp_wait = e.rposted;  // the run's last pixel comes from the reconstruction warp
         x += n;
-        if (x >= X) {  // the raster left row y: it is complete
-            irow_flush(g, frame, r0, y, lane);
-            __syncwarp();
+        if (x >= X) {
             x -= X;
             y++;
         }
-        e.lastpx = lastv;
-        PROF_ADD(c_ifill)
     }
 }
 
@@ -1494,8 +1447,6 @@ __device__ __forceinline__ void cmd_drain(Ent& e) {
     __threadfence_block();
 }
 
-// commands to the reconstruction warp (uint4): x = op | ..., see recon_loop
-constexpr uint32_t RQ_BEGIN = 1u, RQ_RUN = 2u, RQ_END = 3u, RQ_LOAD = 4u;
 __device__ __forceinline__ void rq_post(Ent& e, uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t rs = e.sb + S_RSYNC;
     if ((e.rposted & 63u) == 0u)  // ring space, checked once per 64 commands
@@ -1634,6 +1585,11 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
     int bi = 0, f = 0, bx0 = 0, by0 = 0, bw = 16, bh = 16, sw = 1, pos = 0, xx0 = 0, yy0 = 0, ox = 1, oy = 1;
     uint32_t swinv = 65536u, sw1inv = 32768u, ca = tb;
     uint8_t* frame = w.out;
+    // I frame state (row buffers, see irow_flush)
+    const bool padded = ((g.X * 3 + 3) & ~3) != g.X * 3;
+    const uint32_t rb = sb + w.irows, rowbytes = (uint32_t)g.X * 4u;
+    int ix = 0, iy = 0;
+    uint32_t ilast = 0, rdone = 0;
 #ifdef SCPR_PROF
     long long r_pub = 0, r_run = 0, r_nrun = 0, r_load = 0, r_nload = 0, r_end = 0, r_idle = 0;
 #endif
@@ -1648,6 +1604,11 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             if (cmd.w == ridx + 1u) {
                 asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.y), "=r"(cmd.z) : "r"(slot + 8u) : "memory");
                 break;
+            }
+            if (spins == 0u && rdone != ridx) {  // nothing waiting: let the chain warp see how far this warp has come (drains)
+                __threadfence_block();
+                stv_shared(rs + 4, ridx);
+                rdone = ridx;
             }
             if ((spins & 31u) == 31u) {
 #ifdef SCPR_PROF
@@ -1744,6 +1705,87 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
                 yy0 += q;
                 ca = tb + (uint32_t)((oy + yy0) * 17 + ox + xx0) * 4u;
             }
+        } else if (op == RQ_IRUN) {
+            // ---- I frame run through the two row buffers: every predictor reaches at most one row up (the corner pixel
+            // at x == 0 reaches the tail of row y - 2, which still sits in the buffer row y is about to reuse); a run is at
+            // most 255 pixels and the frame at least 256 wide, so it touches at most two rows
+            const int X = g.X, Y = g.Y;
+            const int ptype = (int)((cmd.x >> 8) & 0xFFu), n = (int)(cmd.x >> 16);
+            const uint32_t c = cmd.y;
+            const uint32_t r0 = rb + (uint32_t)(iy & 1) * rowbytes, r1 = rb + (uint32_t)((iy + 1) & 1) * rowbytes;  // rows y (and y - 2) / y + 1 (and y - 1)
+            uint32_t vlast = ptype == 0 ? c : ilast;  // type 1: the previous pixel in raster order, whatever the row
+            if (ptype == 2 || ptype == 5) {  // the last pixel first (its sources lie before the run), then the fill
+                int xl = ix + n - 1, yl = iy;
+                uint32_t cur = r0, up = r1;
+                if (xl >= X) {
+                    xl -= X; yl++;
+                    cur = r1; up = r0;
+                }
+                if (yl < Y) {
+                    if (ptype == 2) vlast = lds32(up + 4u * (uint32_t)xl);
+                    else if (xl > 0) vlast = lds32(up + 4u * (uint32_t)(xl - 1));
+                    else vlast = padded ? tl_padded(frame, g, yl) : lds32(cur + 4u * (uint32_t)(X - 1));
+                } else
+                    vlast = 0;
+            }
+            if (ptype != 4) asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+            if (ptype == 0 || ptype == 1) {
+                for (int i = lane; i < n; i += 32) {
+                    const int xi = ix + i;
+                    if (xi < X) sts32(r0 + 4u * (uint32_t)xi, vlast);
+                    else if (iy + 1 < Y) sts32(r1 + 4u * (uint32_t)(xi - X), vlast);
+                }
+            } else if (ptype == 2 || ptype == 5) {
+                for (int i = lane; i < n; i += 32) {
+                    int xi = ix + i, yi = iy;
+                    uint32_t cur = r0, up = r1;
+                    if (xi >= X) {
+                        xi -= X; yi++;
+                        cur = r1; up = r0;
+                    }
+                    if (yi < Y) {
+                        uint32_t v;
+                        if (ptype == 2) v = lds32(up + 4u * (uint32_t)xi);
+                        else if (xi > 0) v = lds32(up + 4u * (uint32_t)(xi - 1));
+                        else v = padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1));  // tail of row yi - 2
+                        sts32(cur + 4u * (uint32_t)xi, v);
+                    }
+                }
+            } else {  // gradient chains through the left pixel: one lane
+                uint32_t myv = 0;
+                if (lane == 0) {
+                    int xi = ix, yi = iy;
+                    uint32_t cur = r0, up = r1, left = ilast;
+                    for (int i = 0; i < n && yi < Y; i++) {
+                        const uint32_t top = lds32(up + 4u * (uint32_t)xi);
+                        const uint32_t tlv = xi > 0 ? lds32(up + 4u * (uint32_t)(xi - 1))
+                                                    : (padded ? tl_padded(frame, g, yi) : lds32(cur + 4u * (uint32_t)(X - 1)));
+                        myv = grad_px(left, top, tlv);
+                        sts32(cur + 4u * (uint32_t)xi, myv);
+                        left = myv;
+                        if (++xi == X) {
+                            xi = 0; yi++;
+                            const uint32_t t = cur; cur = up; up = t;
+                        }
+                    }
+                }
+                vlast = __shfl_sync(0xFFFFFFFFu, myv, 0);
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+            }
+            __syncwarp();
+            ilast = vlast;
+            ix += n;
+            if (ix >= X) {  // the raster left row y: it is complete
+                if (iy < Y) irow_flush(g, frame, r0, iy, lane);
+                __syncwarp();
+                ix -= X;
+                iy++;
+            }
+        } else if (op == RQ_IBEGIN) {
+            f = (int)cmd.y;
+            frame = w.out + (size_t)f * g.frame_bytes;
+            ix = iy = 0;
+            ilast = 0;
         } else if (op == RQ_BEGIN) {  // the sub-rect the runs cover
             const int x1 = (int)(cmd.z & 15u), y1 = (int)((cmd.z >> 4) & 15u), x2 = (int)((cmd.z >> 8) & 15u) + 1;
             sw = x2 - x1;
@@ -1811,9 +1853,10 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
         else if (op == RQ_END) r_end += clock64() - td__;
 #endif
         // executed-command count: the chain warp needs it when it drains (always right after an END) and, coarsely, for ring space
-        if (op != RQ_RUN || (ridx & 15u) == 15u) {
+        if ((op != RQ_RUN && op != RQ_IRUN) || (ridx & 15u) == 15u) {
             __threadfence_block();
             stv_shared(rs + 4, ridx + 1);
+            rdone = ridx + 1;
         }
     }
 }
@@ -1920,7 +1963,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
                     e.nleft = RANS_BLOCK;
                     rdec_init(e);
                 }
-                if (w.irows) decode_i_rows<V2>(w, e, frame, lane, sb + w.irows);
+                if (w.irows) decode_i_rows<V2>(w, e, f, lane);
                 else decode_i<V2>(w, e, frame, lane);
             }
             continue;
