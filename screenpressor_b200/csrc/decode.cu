@@ -974,8 +974,8 @@ __device__ __forceinline__ uint32_t dec_rgb(Ent& e) {  // DecodeRGB, screencap.c
     fetch_lastpx(e);
     uint32_t px = 0;
     uint32_t cx = (e.lastpx >> 18) & 63u, cx1 = (e.lastpx >> 4) & 0xFC0u;
-#pragma unroll 1
-    for (int ch = 0; ch < 3; ch++) {  // one copy of the colour decoder in the instruction stream
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
         const uint32_t v = (uint32_t)dec_color<CNT>(e, ch * 4096 + (int)(cx + cx1)) & 255u;
         cx1 = cx << 6;
         cx = v >> 2;
