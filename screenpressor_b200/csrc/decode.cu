@@ -1132,10 +1132,34 @@ __device__ __forceinline__ int dec_run(Ent& e, int& ptype, uint32_t& c) {
     if (V2) return rc_run(e, ptype, c);
     int n;
     if (e.nleft > 8) {
-        ptype = dec_ptype<false>(e, ptype);
-        if (!ptype) c = dec_rgb<false>(e);
-        n = dec_n<false>(e, ptype);
-        e.nleft -= ptype ? 2 : 5;
+        // type and length, software-pipelined by hand (a lone warp has nobody else to fill its load latencies): the run
+        // length's table look-up is issued as soon as the type is known, the type table is counted while it is in flight
+        const int t = 15 + ptype, off = 3144 + 8 * ptype;
+        const uint32_t la1 = e.sb + S_LEFT + (uint32_t)t * 4u;
+        const uint32_t left1 = lds32(la1);
+        const uint32_t v = e.x & (PROB_SCALE - 1);
+        const uint32_t fc = lds32(e.sb + S_FC + (uint32_t)(off + (e.lane & 7)) * 4u);
+        const uint32_t d = v - (fc & 0xFFFFu), f = fc >> 16;
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, e.lane < 6 && d < f);
+        const int pt = 31 - __clz(bh | 1u);
+        const uint32_t xk = f * (e.x >> PROB_BITS) + d;
+        rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, pt));
+        ptype = pt;
+        if (!pt) {
+            fx_update<false>(e, t, la1, left1, off);
+            c = dec_rgb<false>(e);
+            n = dec_n<false>(e, 0);
+        } else {
+            const uint32_t la2 = e.sb + S_LEFT + (uint32_t)pt * 4u;
+            const uint32_t left2 = lds32(la2);
+            const uint32_t v2 = e.x & (PROB_SCALE - 1);
+            const uint32_t en = lds32(e.sb + S_LUT32 + ((uint32_t)pt << 14) + (v2 << 2));
+            fx_update<false>(e, t, la1, left1, off + pt);
+            n = (int)(en >> 24);
+            rdec_advance(e, v2 - (en & 0xFFFu), (en >> 12) & 0xFFFu);
+            fx_update<false>(e, pt, la2, left2, (pt << 8) + n);
+        }
+        e.nleft -= pt ? 2 : 5;
     } else {
         ptype = dec_ptype<true>(e, ptype);
         if (!ptype) c = dec_rgb<true>(e);
