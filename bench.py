@@ -167,6 +167,8 @@ def run_cuda(args):
     # pinned host copies for the end-to-end leg, device-resident copy for `value`
     h_in = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
     h_in.numpy()[:] = clip.reshape(-1)
+    if world > 1:
+        clip = None  # N ranks share the host's memory: keep only the pinned copy (the CPU baseline runs at N = 1 only)
     h_out = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
     d_in = h_in.cuda(non_blocking=True)
     d_out = torch.empty(frames * fb, dtype=torch.uint8, device="cuda")
