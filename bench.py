@@ -159,7 +159,19 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to stdout when the first communicator comes up: send it to stderr, rank 0's
+        # stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     frames = args.frames
     cfg, clip, keys = make_workload(rank, frames)
     W, H = cfg.width, cfg.height
