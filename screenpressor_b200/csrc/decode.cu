@@ -1125,6 +1125,39 @@ __device__ __forceinline__ int sym_fx(Ent& e) {
     return dec_fxc<NSYM, T>(e);
 }
 
+// the four sub-rect symbols of a partial block (SXY tables 9..12, 16 symbols each; screencap.cpp:1321-1331), packed
+// x1 | y1 << 4 | x2-1 << 8 | y2-1 << 12 relative to the block.  The four tables are distinct, so their intervals and
+// countdowns are fetched up front and the four decodes run back to back on registers.
+template <bool V2>
+__device__ __forceinline__ uint32_t dec_rect(Ent& e) {
+    uint32_t r = 0;
+    if (V2) {
+        r = (uint32_t)rc_fx<9>(e);
+        r |= (uint32_t)rc_fx<10>(e) << 4;
+        r |= (uint32_t)rc_fx<11>(e) << 8;
+        r |= (uint32_t)rc_fx<12>(e) << 12;
+    } else {
+    uint32_t fc[4], left[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        fc[k] = lds32(e.sb + S_FC + (uint32_t)(2056 + 16 * k + (e.lane & 15)) * 4u);
+        left[k] = lds32(e.sb + S_LEFT + (uint32_t)(9 + k) * 4u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t v = e.x & (PROB_SCALE - 1);
+        const uint32_t d = v - (fc[k] & 0xFFFFu), f = fc[k] >> 16;
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, e.lane < 16 && d < f);
+        const int j = 31 - __clz(bh | 1u);
+        const uint32_t xk = f * (e.x >> PROB_BITS) + d;
+        rdec_renorm(e, __shfl_sync(0xFFFFFFFFu, xk, j));
+        fx_update<true>(e, 9 + k, e.sb + S_LEFT + (uint32_t)(9 + k) * 4u, left[k], 2056 + 16 * k + j);
+        r |= (uint32_t)j << (4 * k);
+    }
+    }
+    return r;
+}
+
 // the symbols of one pixel run: type, colour of a literal, length (screencap.cpp:478-486, 1400-1412).  At most five
 // symbols: when the rANS block cannot end within them they are counted with one subtraction.
 template <bool V2 = false>
@@ -1537,12 +1570,7 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
             // executes it clips the rectangle to the block and records the block's new owner in the map.
             PROF_T0
             uint32_t rect = 0xFF00u;  // the whole block
-            if ((bt - 1) & 1) {
-                rect = (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
-                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e) << 4;
-                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) << 8;
-                rect |= (uint32_t)sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) << 12;
-            }
+            if ((bt - 1) & 1) rect = dec_rect<V2>(e);
             int mx = lastmx, my = lastmy;
             if (V2) {  // no repeat flag before v3, vectors offset by the stream's own motion range (screencap.cpp:1358-1361)
                 mx = rc_fx<13>(e) - e.msr_x;
@@ -1563,10 +1591,11 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
         // ---- pixel-coded block: the chain warp decodes its symbols, the reconstruction warp builds its pixels ----
         rq_post(e, RQ_LOAD | ((uint32_t)bi << 8), (uint32_t)f, 0u);  // the tile load starts while the sub-rect is still being decoded
         if ((bt - 1) & 1) {
-            x1 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 0>(e);
-            y1 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 1>(e);
-            x2 = bx0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 2>(e) + 1;
-            y2 = by0 + sym_fx<V2, 16, CX_SXY - CX_NTAB + 3>(e) + 1;
+            const uint32_t rc4 = dec_rect<V2>(e);
+            x1 = bx0 + (int)(rc4 & 15u);
+            y1 = by0 + (int)((rc4 >> 4) & 15u);
+            x2 = bx0 + (int)((rc4 >> 8) & 15u) + 1;
+            y2 = by0 + (int)((rc4 >> 12) & 15u) + 1;
             if (x2 > bx0 + bw) x2 = bx0 + bw;  // corrupt input guards
             if (y2 > by0 + bh) y2 = by0 + bh;
             if (x1 >= x2) x1 = x2 - 1;
