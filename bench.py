@@ -18,6 +18,7 @@ no data-path collective (weak scaling).  torch.distributed is only used for the 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,6 +35,16 @@ from screenpressor_b200 import synth  # noqa: E402
 
 WORKLOAD = "cfg2_1080p_rgb32"
 METRIC = "1080p_rgb32_encode_decode_frames_per_s"
+
+
+def workload_config(frames: int):
+    """`config` of the JSON line -- the same dict in both arms (the driver compares them)."""
+    cfg = synth.CONFIGS[WORKLOAD]
+    keys = synth.keyframe_flags(frames, cfg.key_interval)
+    return {"workload": f"{WORKLOAD}: {cfg.width}x{cfg.height} RGB32 synthetic desktop capture, {frames} frames per clip, keyframe interval "
+                        f"{cfg.key_interval} ({int(keys.sum())} GOPs), one step = encode all frames + decode them again",
+            "frames": frames, "key_interval": cfg.key_interval, "gops_per_clip": int(keys.sum()),
+            "l2": "inputs (5 GB/step) exceed L2; no flush needed", "statistic": "mean over the timed steps"}
 
 
 def make_workload(rank: int, frames: int):
@@ -85,8 +96,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference(clip, keys, cfg, threads: int):
-    """encode+decode `clip` with the compiled reference core (oracle/_ref); returns (seconds enc, seconds dec, kind)."""
+def time_reference(clip, keys, cfg, threads: int, keep=None):
+    """encode+decode `clip` with the compiled reference core (oracle/_ref); returns (seconds enc, seconds dec, kind).
+    keep: a list that receives every frame's (bytes, ftype) -- the parity check of the CUDA stream."""
     from oracle import pyref  # the one place bench.py may execute oracle/: the CPU baseline
 
     kind = "reference" if pyref.have_ref() else "port"
@@ -106,6 +118,8 @@ def time_reference(clip, keys, cfg, threads: int):
         t2 = time.perf_counter()
         te += t1 - t0
         td += t2 - t1
+        if keep is not None:
+            keep.append((data, ft))
         if i % 97 == 0:
             assert np.array_equal(out, flat[i]), "reference round trip failed"
     enc.close()
@@ -114,34 +128,38 @@ def time_reference(clip, keys, cfg, threads: int):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle/_ref: the unmodified reference core; the plain-C port only
+    if it could not be built) on the same clip, the same step and the same statistic as the CUDA arm: every step encodes
+    and decodes all frames, `value` is the mean over the K timed steps after W warm-up steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    sample = min(args.ref_frames, synth.CONFIGS[WORKLOAD].frames)
-    cfg, clip, keys = make_workload(0, sample)
+    frames = args.frames
+    cfg, clip, keys = make_workload(0, frames)
     nby = (cfg.height + 15) // 16
     nthr = max(1, min(os.cpu_count() or 1, nby))  # cap: the reference's tls[] overflows past nby threads (SURVEY.md 0.1)
-    results = {}
+    # all the host threads it can use: one probe step per thread count, the timed steps run with the faster one
+    probe = {}
     for thr in sorted({1, nthr}):
-        for _ in range(args.warmup if thr == 1 else 0):
-            time_reference(clip, keys, cfg, thr)
-        ts = [time_reference(clip, keys, cfg, thr) for _ in range(args.steps)]
-        best = min(t[0] + t[1] for t in ts)
-        results[thr] = {"fps": sample / best, "enc_fps": sample / min(t[0] for t in ts), "dec_fps": sample / min(t[1] for t in ts),
-                        "kind": ts[0][2]}
-    thr_best = max(results, key=lambda k: results[k]["fps"])
-    r = results[thr_best]
-    per_step = sample / r["fps"]
+        t = time_reference(clip, keys, cfg, thr)
+        probe[thr] = frames / (t[0] + t[1])
+    thr = max(probe, key=lambda k: probe[k])
+    for _ in range(max(0, args.warmup - 1)):
+        time_reference(clip, keys, cfg, thr)
+    ts = [time_reference(clip, keys, cfg, thr) for _ in range(args.steps)]
+    te, td = sum(t[0] for t in ts), sum(t[1] for t in ts)
+    fps = frames * args.steps / (te + td)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 1920x1080 RGB32, keyframe interval 500, first {sample} of 600 frames per step, encode+decode"},
-        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": thr_best, "kind": r["kind"],
-                         "sample": f"first {sample} frames of the 600-frame clip, encode then decode each frame, best of {args.steps}",
-                         "encode_fps": r["enc_fps"], "decode_fps": r["dec_fps"],
-                         "by_threads": {str(k): v["fps"] for k, v in results.items()}},
-        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(frames),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": thr, "kind": ts[0][2],
+                         "sample": f"all {frames} frames of the clip per step, one CompressFrame + one DecompressFrame call per frame, "
+                                   f"mean of {args.steps} steps",
+                         "encode_fps": frames * args.steps / te, "decode_fps": frames * args.steps / td,
+                         "probe_fps_by_threads": {str(k): v for k, v in probe.items()}},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -208,7 +226,7 @@ def run_cuda(args):
         e2.synchronize()
         stage["enc_ms"] += e0.elapsed_time(e1)
         stage["dec_ms"] += e1.elapsed_time(e2)
-        return s, sizes
+        return s, sizes, fts
 
     def step_host():
         fresh()
@@ -220,7 +238,7 @@ def run_cuda(args):
         assert out == 1, out
         stage["e2e_enc_s"] += t1 - t0  # both calls are synchronous: host clocks bracket them exactly
         stage["e2e_dec_s"] += t2 - t1
-        return s, sizes
+        return s, sizes, fts
 
     def barrier():
         if world > 1:
@@ -253,7 +271,8 @@ def run_cuda(args):
         sampler.start()
     l0 = enc.kernel_launches() + dec.kernel_launches()
     stage["enc_ms"] = stage["dec_ms"] = 0.0
-    ms, (s, sizes) = timed(step_device, args.steps)
+    ms, (s, sizes, fts) = timed(step_device, args.steps)
+    s_keep, sizes_keep, fts_keep = s.copy(), sizes.copy(), fts.copy()
     launches = enc.kernel_launches() + dec.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * frames * args.steps / (ms / 1e3)
@@ -265,7 +284,8 @@ def run_cuda(args):
     torch.cuda.synchronize()
     assert np.array_equal(h_out.numpy(), h_in.numpy()), "decode(encode(x)) != x on the host-buffer path"
     stage["e2e_enc_s"] = stage["e2e_dec_s"] = 0.0
-    ms_e2e, (s2, sizes2) = timed(step_host, args.steps)
+    ms_e2e, (s2, sizes2, fts2) = timed(step_host, args.steps)
+    assert np.array_equal(s2, s_keep) and np.array_equal(sizes2, sizes_keep), "host-buffer stream differs from the device-resident one"
     e2e_enc_fps = frames * args.steps / stage["e2e_enc_s"]
     e2e_dec_fps = frames * args.steps / stage["e2e_dec_s"]
     e2e = world * frames * args.steps / (ms_e2e / 1e3)
@@ -327,20 +347,33 @@ def run_cuda(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = None
+    cpu = parity = None
     if world == 1 and not args.no_cpu_baseline:
+        # the reference on one host thread (its canonical bitstream) over the same frames; every frame it codes is
+        # byte-compared with the CUDA stream of the timed steps
         sample = min(args.ref_frames, frames)
-        te, td, kind = time_reference(clip[:sample], keys[:sample], cfg, 1)
+        ref_frames = []
+        te, td, kind = time_reference(clip[:sample], keys[:sample], cfg, 1, keep=ref_frames)
         cpu = {"value": sample / (te + td), "unit": "frames/s", "cores": 1, "kind": kind,
-               "sample": f"first {sample} frames of the same clip, encode then decode each frame, 1 thread (canonical bitstream)",
+               "sample": f"the first {sample} of {frames} frames of the same clip, one CompressFrame + DecompressFrame call per frame, 1 thread "
+                         "(canonical bitstream), one pass",
                "encode_fps": sample / te, "decode_fps": sample / td}
+        pos, bad = 0, []
+        for i, (data, ft) in enumerate(ref_frames):
+            got = bytes(s_keep[pos:pos + int(sizes_keep[i])])
+            pos += int(sizes_keep[i])
+            if got != data or int(fts_keep[i]) != ft:
+                bad.append(i)
+        parity = {"frames": len(ref_frames), "identical": not bad, "against": "oracle/_ref (unmodified reference, 1 thread)" if kind == "reference" else "oracle port",
+                  "first_mismatches": bad[:5], "stream_md5": hashlib.md5(bytes(s_keep)).hexdigest()}
+        assert not bad, f"CUDA bitstream differs from the reference at frames {bad[:5]}"
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 1920x1080 RGB32, {frames} frames per clip per GPU, keyframe interval 500, encode+decode, "
-                               "bit-exact round trip asserted", "l2": "inputs (5 GB/step) exceed L2; no flush needed",
-                   "gops_per_clip": int(keys.sum()), "stream_bytes_per_clip": stream_bytes},
+        "config": workload_config(frames),
+        "stream_bytes_per_clip": stream_bytes,
+        "parity": parity,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
                 "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps,
                 "encode_fps": e2e_enc_fps, "decode_fps": e2e_dec_fps,
@@ -374,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--frames", type=int, default=synth.CONFIGS[WORKLOAD].frames)
-    ap.add_argument("--ref-frames", type=int, default=200, help="bounded sample for the CPU arm")
+    ap.add_argument("--ref-frames", type=int, default=600, help="frames the cpu_baseline / parity leg of the CUDA arm runs through the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", type=int, default=8, help="also measure N independent clips in flight on one GPU (0 = skip)")
     args = ap.parse_args()

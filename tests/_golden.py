@@ -18,6 +18,12 @@ def digests():
         return json.load(f)
 
 
+def digests_long():
+    """full-length BASELINE configs: per-frame [type, size, md5] written by the unmodified reference (make_golden.py)"""
+    with open(os.path.join(GOLDEN_DIR, "ref_digests_long.json")) as f:
+        return json.load(f)
+
+
 def streams():
     return np.load(os.path.join(GOLDEN_DIR, "ref_streams.npz"))
 

@@ -39,6 +39,14 @@ CASES = [
     ("fuzz_130x130_rgb32_l4", "fuzz", (130, 130, 40, 17, 32, 4)),
 ]
 STREAM_CASES = {"fuzz_97x45_rgb32", "fuzz_64x64_rgb32_l16", "fuzz_33x17_rgb24", "fuzz_130x130_rgb32_l4"}
+# full-length cases of the BASELINE configs (ref_digests_long.json): the headline clip with its 500-frame GOP of model
+# adaptation and mvs[] staleness, a 4K scrolling GOP, intra-only photo/noise frames, the sparse multi-monitor clip
+LONG_CASES = [
+    ("cfg2_1080p_rgb32_f600_k500", "synth", ("cfg2_1080p_rgb32", 600, 500)),
+    ("cfg3_2160p_rgb32_f64_k450", "synth", ("cfg3_2160p_rgb32", 64, 450)),
+    ("cfg4_1440p_intra_f4", "synth", ("cfg4_1440p_intra", 4, 1)),
+    ("cfg5_5120x1440_f120_k500", "synth", ("cfg5_5120x1440", 120, 500)),
+]
 
 
 def load_case(kind, args):
@@ -51,10 +59,9 @@ def load_case(kind, args):
     return clip, keys, w, h, bpp
 
 
-def main():
-    build()
+def encode_cases(cases, keep_streams=()):
     digests, streams = {}, {}
-    for name, kind, args in CASES:
+    for name, kind, args in cases:
         clip, keys, w, h, bpp = load_case(kind, args)
         ref = RefCodec(w, h, bpp, threads=1)
         rows, blobs = [], []
@@ -63,14 +70,24 @@ def main():
             rows.append([ft, len(data), hashlib.md5(data).hexdigest()])
             blobs.append(data)
         digests[name] = {"kind": kind, "args": list(args), "frames": rows}
-        if name in STREAM_CASES:
+        if name in keep_streams:
             streams[name + "/sizes"] = np.array([len(b) for b in blobs], dtype=np.int32)
             streams[name + "/types"] = np.array([r[0] for r in rows], dtype=np.uint8)
             streams[name + "/data"] = np.frombuffer(b"".join(blobs), dtype=np.uint8)
         print(name, len(rows), "frames", sum(r[1] for r in rows), "bytes")
-    with open(os.path.join(HERE, "ref_digests.json"), "w") as f:
-        json.dump(digests, f, indent=0)
-    np.savez_compressed(os.path.join(HERE, "ref_streams.npz"), **streams)
+    return digests, streams
+
+
+def main():
+    build()
+    if "--long-only" not in sys.argv:
+        digests, streams = encode_cases(CASES, STREAM_CASES)
+        with open(os.path.join(HERE, "ref_digests.json"), "w") as f:
+            json.dump(digests, f, indent=0)
+        np.savez_compressed(os.path.join(HERE, "ref_streams.npz"), **streams)
+    digests, _ = encode_cases(LONG_CASES)
+    with open(os.path.join(HERE, "ref_digests_long.json"), "w") as f:
+        json.dump(digests, f, separators=(",", ":"))
 
 
 if __name__ == "__main__":

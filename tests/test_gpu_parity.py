@@ -126,6 +126,11 @@ def test_stage_outputs_match_oracle(scpr, oracle_built):
     lib.orc_last_freqs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32))]
     lib.orc_last_bts.restype = C.POINTER(C.c_uint8)
     lib.orc_last_bts.argtypes = [C.c_void_p]
+    lib.orc_last_sxy.restype = C.POINTER(C.c_int)
+    lib.orc_last_sxy.argtypes = [C.c_void_p, C.c_int]
+    lib.orc_last_mvs.restype = C.POINTER(C.c_int)
+    lib.orc_last_mvs.argtypes = [C.c_void_p, C.c_int]
+    checked_blocks = checked_mvs = 0
     enc = _new(scpr, w, h, 32)
     nb = ((w + 15) // 16) * ((h + 15) // 16)
     for i in range(len(clip)):
@@ -144,6 +149,43 @@ def test_stage_outputs_match_oracle(scpr, oracle_built):
             bts, sxy, mv = enc.debug_blocks(0)
             obts = np.ctypeslib.as_array(lib.orc_last_bts(orc.h_), shape=(nb,))
             assert np.array_equal(bts, obts), f"frame {i}: block types differ"
+            osxy = np.stack([np.ctypeslib.as_array(lib.orc_last_sxy(orc.h_, k), shape=(nb,)) for k in range(4)], axis=1)
+            omv = np.stack([np.ctypeslib.as_array(lib.orc_last_mvs(orc.h_, k), shape=(nb,)) for k in range(2)], axis=1)
+            chg, moved = obts != 0, obts >= 3
+            checked_blocks += int(chg.sum())
+            checked_mvs += int(moved.sum())
+            assert np.array_equal(sxy[chg], osxy[chg]), f"frame {i}: changed sub-rects differ"
+            assert np.array_equal(mv[moved], omv[moved]), f"frame {i}: motion vectors differ"
+    assert checked_blocks > 100 and checked_mvs > 10, (checked_blocks, checked_mvs)
+
+
+LONG = _golden.digests_long()
+
+
+@pytest.mark.parametrize("name", sorted(LONG))
+def test_full_length_configs_match_reference(scpr, name):
+    """BASELINE configs at full resolution and length (the headline clip with its 500-frame GOP, a 4K scrolling GOP,
+    intra-only photo / noise frames, the sparse multi-monitor clip): every frame's type, size and md5 must equal what the
+    unmodified reference wrote with one worker thread (tests/golden/ref_digests_long.json), through the clip calls with
+    the frames resident on the device and again through the host-buffer calls; decode must be bit-exact."""
+    import torch
+
+    entry = LONG[name]
+    clip, keys, w, h, bpp = _golden.load_case(entry)
+    n = len(clip)
+    enc = _new(scpr, w, h, bpp)
+    d_in = torch.from_numpy(clip.reshape(-1)).cuda()
+    stream, sizes, fts = enc.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=n)
+    _golden.check_frames(name, entry["frames"], _split(stream, sizes, fts))
+    d_out = torch.empty_like(d_in)
+    dec = _new(scpr, w, h, bpp)
+    dec.DecompressClip(stream, sizes, fts, device_ptr=d_out.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_in), f"{name}: decode is not bit-exact"
+    del d_out
+    enc2 = _new(scpr, w, h, bpp)
+    stream2, sizes2, fts2 = enc2.CompressClip(clip, keys)
+    assert np.array_equal(stream2, stream) and np.array_equal(sizes2, sizes) and np.array_equal(fts2, fts), f"{name}: host-buffer call differs"
 
 
 def test_full_size_round_trip_properties(scpr):
