@@ -54,8 +54,13 @@ int scpr_reset(scpr_codec* c);
  * src: host frame, rows top to bottom, pitch width*4 (32 bpp), (width*3+3)&~3 (24 bpp) or width*2 (16 bpp).
  * *ftype in: 0 = I requested, 1 = P requested; out: type actually coded (first and flat frames
  * are always I, screencap.cpp:1488-1511).  loss = bits of loss for this frame (the clip entry points use
- * the value given at creation); in lossy mode the `_dev` clip variant masks the caller's frames in place,
- * as the reference mutates its source buffer.  Returns the byte count written to dst, or < 0. */
+ * the value given at creation).  Returns the byte count written to dst, or < 0.
+ * The source is never written to.  (The reference does write to a 24 bpp source: it zeroes the row padding when the width
+ * is not a multiple of 4 and applies the loss mask in the caller's buffer, screencap.cpp:215-219, 857-859; a host that relied
+ * on seeing the masked pixels must mask its own copy.  32 and 16 bpp sources are repacked first by the reference as well.)
+ * Errors: after any error that is returned once device work has started (SCPR_E_CUDA, SCPR_E_DSTSIZE, "batch too large")
+ * the frames of that call are not part of the stream and the next coded frame is forced to be an I frame with fresh
+ * models, so the stream the caller holds stays decodable. */
 int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst_cap, int* ftype, int loss);
 
 /* replaces ScreenCodec::DecompressFrame (screencap.cpp:1695-1743).
@@ -74,7 +79,7 @@ int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_
  * keyflags : n bytes, 1 = the host requests an I frame (ftype 0), 0 = P requested.
  * dst      : concatenated frame bitstreams; sizes[i] / ftypes[i] describe frame i.
  * Returns total bytes written or < 0.  `*_dev` variants take device pointers for the frames
- * (inputs/outputs already resident in HBM); bitstreams stay host-side in both. */
+ * (inputs/outputs already resident in HBM, 16-byte aligned, never written to by the encoder); bitstreams stay host-side in both. */
 int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const uint8_t* keyflags,
                            uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes);
 int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags,

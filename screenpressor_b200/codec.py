@@ -245,8 +245,8 @@ class ScreenCodec:
                 r = self._lib.scpr_compress_clip_dev(self._h, device_ptr, n, _ptr(keyflags), _ptr(self._clip_dst), cap,
                                                      _ptr(sizes), _ptr(ftypes))
             if r == SCPR_E_DSTSIZE:
-                raise ScprError(r, "destination too small (codec state already advanced): pass a larger capacity via "
-                                   "reserve_clip_output() before the call")
+                raise ScprError(r, "destination too small: the frames of this call were dropped and the next frame will be coded as an I "
+                                   "frame; pass a larger capacity via reserve_clip_output()")
             self._check(r)
             return self._clip_dst[:r], sizes, ftypes
 

@@ -239,7 +239,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
                       &c->launches);
     if (c->loss) {
         // lossy mode: the flat test above ran on the raw frames (IsFlat precedes DoLoss); now mask the
-        // non-flat frames in place and redo the differencing on the masked pixels
+        // non-flat frames in place (d_frames is the codec's own buffer in lossy mode) and redo the differencing on the masked pixels
         launch_apply_loss(const_cast<uint8_t*>(d_frames), n, g, (const FrameSummary*)c->summary.p, c->loss, st, &c->launches);
         TRY(c->summary2.ensure((size_t)n * sizeof(FrameSummary)));
         CK(cudaMemsetAsync(c->summary2.p, 0, (size_t)n * sizeof(FrameSummary), st));
@@ -278,25 +278,30 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     };
     // the persistent state (if any) is chain "-1": it is referenced lazily by the first P frame
     const int persistent_state = c->cur_state;
+    // The plan works on copies of the codec's host state; they are committed only after the last synchronisation of
+    // the call succeeded (a failed call must not leave fn / last_was_flat / have_models ahead of the stream).
+    unsigned l_fn = c->fn;
+    bool l_last_was_flat = c->last_was_flat, l_have_models = c->have_models;
+    uint8_t l_last_flat_clr[3] = {c->last_flat_clr[0], c->last_flat_clr[1], c->last_flat_clr[2]};
     for (int f = 0; f < n; f++) {
         const bool flat = !summary[f].notflat;
         const uint8_t clr[3] = {(uint8_t)summary[f].pixel0, (uint8_t)(summary[f].pixel0 >> 8), (uint8_t)(summary[f].pixel0 >> 16)};
         if (flat) {
             ftype[f] = FT_FLAT;
-            if (!(c->last_was_flat && !memcmp(clr, c->last_flat_clr, 3))) {
-                memcpy(c->last_flat_clr, clr, 3);
+            if (!(l_last_was_flat && !memcmp(clr, l_last_flat_clr, 3))) {
+                memcpy(l_last_flat_clr, clr, 3);
                 ChainDesc cd = {0, 0, -1, 1};  // RenewI with no events of its own (screencap.cpp:1490-1494)
                 chains.push_back(cd);
                 chain_first.push_back(f);
                 open_chain = (int)chains.size() - 1;
-                c->have_models = true;
+                l_have_models = true;
             }
-            c->last_was_flat = true;
+            l_last_was_flat = true;
             continue;
         }
-        c->last_was_flat = false;
-        if (c->fn && !keyflags[f]) {
-            c->fn++;
+        l_last_was_flat = false;
+        if (l_fn && !keyflags[f]) {
+            l_fn++;
             if (!summary[f].changed) {
                 ftype[f] = FT_PSAME;
                 continue;
@@ -304,6 +309,13 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
             ftype[f] = FT_P;
             pframes.push_back(f);
             if (open_chain < 0) {  // continue the chain left open by the previous call
+                if (!l_have_models) {
+                    // reachable through scpr_import_range_state with a small (full = 0) blob whose range does not start
+                    // on a frame that renews the models: there is no model state to continue
+                    set_error("P frame without model state: the codec was handed a frame-range state without models (use a full blob, or cut the "
+                              "range on a frame that is coded as an I frame)");
+                    return SCPR_E_PARAM;
+                }
                 ChainDesc cd = {0, 0, -2, 0};
                 chains.push_back(cd);
                 chain_first.push_back(f);
@@ -311,7 +323,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
             }
             chain_of[f] = open_chain;
         } else {
-            c->fn++;
+            l_fn++;
             ftype[f] = FT_I;
             iframes.push_back(f);
             ChainDesc cd = {0, 0, -1, 1};
@@ -319,9 +331,24 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
             chain_first.push_back(f);
             open_chain = (int)chains.size() - 1;
             chain_of[f] = open_chain;
-            c->have_models = true;
+            l_have_models = true;
         }
     }
+    // From here on device state that later frames depend on is modified in place (mvs[] by the resolve, the open chain's
+    // models by the replay).  If the call fails after this point the codec cannot continue the stream it was writing: the
+    // guard below then makes the next coded frame an I frame with fresh models, so whatever the caller did receive stays
+    // decodable (the frames of the failed call are lost to the stream, as with the reference when its caller drops a frame).
+    struct Poison {
+        scpr_codec* c;
+        bool armed = true;
+        ~Poison() {
+            if (armed) {
+                c->fn = 0;
+                c->have_models = false;
+                c->last_was_flat = false;
+            }
+        }
+    } poison{c};
     // model states: the continued chain keeps the persistent slot, every new chain gets its own
     {
         int need = (int)chains.size() + 1;
@@ -335,8 +362,8 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
                 chains[k].state = s;
             }
         }
-        if (!chains.empty()) c->cur_state = chains.back().state;
     }
+    const int new_cur_state = chains.empty() ? c->cur_state : chains.back().state;
 
     // ---- stage A --------------------------------------------------------------------------------
     int total_blocks = 0;
@@ -558,6 +585,13 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         case FT_I: o[0] = 0x32; break;     // 2 + (version-1)*16, screencap.cpp:1509
         }
     }
+    // commit the host state: the stream the caller now holds and the codec agree
+    poison.armed = false;
+    c->fn = l_fn;
+    c->last_was_flat = l_last_was_flat;
+    c->have_models = l_have_models;
+    memcpy(c->last_flat_clr, l_last_flat_clr, 3);
+    c->cur_state = new_cur_state;
     // keep what the debug hooks need
     c->dbg_n = n;
     c->dbg_frame_ev_off = frame_ev_off;
@@ -571,6 +605,16 @@ extern "C" {
 int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags, uint8_t* dst,
                                size_t dst_cap, uint32_t* sizes, uint8_t* ftypes) {
     if (!c || !d_frames || !keyflags || !dst || n < 0) return SCPR_E_PARAM;
+    if ((reinterpret_cast<uintptr_t>(d_frames) & 15) != 0) {  // the frame scan reads 128 bits at a time
+        set_error("device frames must be 16-byte aligned");
+        return SCPR_E_PARAM;
+    }
+    if (!c->rgb16 && c->loss && n > 0) {  // the loss mask is applied in place: on a copy, the caller's frames stay as they are
+        CK(cudaSetDevice(c->device));
+        TRY(c->frames.ensure((size_t)n * c->g.frame_bytes));
+        CK(cudaMemcpyAsync(c->frames.p, d_frames, (size_t)n * c->g.frame_bytes, cudaMemcpyDeviceToDevice, c->st));
+        d_frames = (const uint8_t*)c->frames.p;
+    }
     if (c->rgb16 && n > 0) {  // device frames of 2*X bytes per row -> the RGB24 image the codec works on
         CK(cudaSetDevice(c->device));
         TRY(c->frames.ensure((size_t)n * c->g.frame_bytes));
@@ -711,6 +755,9 @@ int scpr_import_range_state(scpr_codec* c, const uint8_t* blob, size_t len) {
     memcpy(c->last_flat_clr, h.last_flat_clr, 3);
     CK(cudaMemcpy(c->mvs.p, p, (size_t)c->g.nb * sizeof(int2), cudaMemcpyHostToDevice));
     p += (size_t)c->g.nb * sizeof(int2);
+    // a small blob carries no models: a P frame that would continue a chain is refused (encode_batch) instead of
+    // being coded on whatever the state pool holds
+    if (!h.full) c->have_models = false;
     if (h.full) {
         CK(cudaMemcpy(c->prev.p, p, c->g.frame_bytes, cudaMemcpyHostToDevice));
         p += c->g.frame_bytes;

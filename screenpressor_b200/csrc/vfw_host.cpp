@@ -48,6 +48,7 @@ struct scpr_avi {
     uint64_t movi_pos = 0;   // file offset of the 'movi' fourcc
     uint32_t max_chunk = 0;
     size_t hdr_bytes = 0;
+    bool io_failed = false;  // writer: a chunk could not be written; close reports it instead of leaving a silent truncated file
 };
 
 static void put32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
@@ -200,16 +201,30 @@ int scpr_avi_write_frame(scpr_avi* a, const uint8_t* data, uint32_t len, int is_
     }
     uint8_t ch[8];
     put32(ch, fcc("00dc")); put32(ch + 4, len);
-    fwrite(ch, 1, 8, a->f);
-    if (len) fwrite(data, 1, len, a->f);
-    if (len & 1) fputc(0, a->f);  // chunks are word aligned
-    a->idx.push_back(AviIndexEntry{pos + 8, len, is_key ? AVIIF_KEYFRAME : 0u});
+    bool io = fwrite(ch, 1, 8, a->f) == 8;
+    if (io && len) io = fwrite(data, 1, len, a->f) == len;
+    if (io && (len & 1)) io = fputc(0, a->f) != EOF;  // chunks are word aligned
+    if (!io) {
+        a->io_failed = true;
+        scpr::set_error("AVI write failed (disk full?)");
+        return SCPR_E_PARAM;
+    }
+    try {
+        a->idx.push_back(AviIndexEntry{pos + 8, len, is_key ? AVIIF_KEYFRAME : 0u});
+    } catch (...) {
+        return SCPR_E_PARAM;
+    }
     if (len > a->max_chunk) a->max_chunk = len;
     return SCPR_OK;
 }
 
 static int avi_finish_write(scpr_avi* a) {
-    const uint64_t movi_end = (uint64_t)ftell(a->f);
+    const long at = ftell(a->f);
+    if (at < 0 || a->io_failed) {
+        scpr::set_error("AVI file is incomplete: an earlier write failed");
+        return SCPR_E_PARAM;
+    }
+    const uint64_t movi_end = (uint64_t)at;
     std::vector<uint8_t> ix(8 + 16 * a->idx.size());
     put32(ix.data(), fcc("idx1")); put32(ix.data() + 4, (uint32_t)(16 * a->idx.size()));
     for (size_t i = 0; i < a->idx.size(); i++) {
@@ -218,25 +233,43 @@ static int avi_finish_write(scpr_avi* a) {
         put32(p + 8, (uint32_t)(a->idx[i].off - 8 - a->movi_pos));  // offset of the chunk header relative to 'movi'
         put32(p + 12, a->idx[i].size);
     }
-    fwrite(ix.data(), 1, ix.size(), a->f);
+    if (fwrite(ix.data(), 1, ix.size(), a->f) != ix.size()) {
+        scpr::set_error("AVI index write failed (disk full?)");
+        return SCPR_E_PARAM;
+    }
     const uint64_t total = (uint64_t)ftell(a->f);
     const std::vector<uint8_t> h = build_header(a->info, (uint32_t)a->idx.size(), a->max_chunk, (uint32_t)(movi_end - a->movi_pos),
                                                 (uint32_t)(total - 8));
-    fseek(a->f, 0, SEEK_SET);
-    fwrite(h.data(), 1, h.size(), a->f);
+    if (fseek(a->f, 0, SEEK_SET) != 0 || fwrite(h.data(), 1, h.size(), a->f) != h.size() || fflush(a->f) != 0) {
+        scpr::set_error("AVI header rewrite failed");
+        return SCPR_E_PARAM;
+    }
     return SCPR_OK;
 }
 
 int scpr_avi_close(scpr_avi* a) {
     if (!a) return SCPR_E_PARAM;
     int r = SCPR_OK;
-    if (a->writing) r = avi_finish_write(a);
-    if (a->f) fclose(a->f);
+    try {
+        if (a->writing) r = avi_finish_write(a);
+    } catch (...) {
+        r = SCPR_E_PARAM;
+    }
+    if (a->f && fclose(a->f) != 0 && r == SCPR_OK && a->writing) r = SCPR_E_PARAM;
     delete a;
     return r;
 }
 
+static int avi_open_impl(const char* path, scpr_avi** out, scpr_avi_info* info);
 int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info) {
+    try {  // no exception crosses the C ABI (a hostile file must not turn into std::bad_alloc in the caller)
+        return avi_open_impl(path, out, info);
+    } catch (...) {
+        scpr::set_error("out of memory while reading %s", path ? path : "(null)");
+        return SCPR_E_PARAM;
+    }
+}
+static int avi_open_impl(const char* path, scpr_avi** out, scpr_avi_info* info) {
     if (!path || !out) return SCPR_E_PARAM;
     FILE* f = fopen(path, "rb");
     if (!f) {
@@ -248,13 +281,13 @@ int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info) {
     memset(&a->info, 0, sizeof(a->info));
     uint8_t h[12];
     bool ok = fread(h, 1, 12, f) == 12 && get32(h) == fcc("RIFF") && get32(h + 8) == fcc("AVI ");
-    uint64_t idx_pos = 0, idx_len = 0, movi_end = 0;
+    uint64_t idx_pos = 0, idx_len = 0, movi_end = 0, fsize = 0;
     bool have_strf = false;
     // walk the top-level chunks; descend into hdrl / strl, remember movi and idx1
     std::vector<std::pair<uint64_t, uint64_t>> todo;  // (start, end) ranges to scan
     if (ok) {
         fseek(f, 0, SEEK_END);
-        const uint64_t fsize = (uint64_t)ftell(f);
+        fsize = (uint64_t)ftell(f);
         todo.push_back({12, fsize});
         while (!todo.empty()) {
             auto [pos, end] = todo.back();
@@ -270,7 +303,7 @@ int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info) {
                     const uint32_t lt = get32(ch + 8);
                     if (lt == fcc("movi")) {
                         a->movi_pos = body;
-                        movi_end = body + sz;
+                        movi_end = body + sz < fsize ? body + sz : fsize;  // sizes come from the file: never past its end
                     } else if (lt == fcc("hdrl") || lt == fcc("strl"))
                         todo.push_back({body + 4, body + sz});
                 } else if (id == fcc("avih") && sz >= 40) {
@@ -300,7 +333,7 @@ int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info) {
                     have_strf = true;
                 } else if (id == fcc("idx1")) {
                     idx_pos = body;
-                    idx_len = sz;
+                    idx_len = body + sz <= fsize ? sz : (body < fsize ? fsize - body : 0);
                 }
                 pos = body + sz + (sz & 1);
             }
@@ -322,17 +355,24 @@ int scpr_avi_open(const char* path, scpr_avi** out, scpr_avi_info* info) {
             const uint32_t id = get32(ix.data() + i);
             if ((id >> 16) != (fcc("00dc") >> 16) && (id >> 16) != (fcc("00db") >> 16)) continue;  // video chunks of stream 0
             if ((id & 0xFFFF) != (fcc("00dc") & 0xFFFF)) continue;
-            a->idx.push_back(AviIndexEntry{base + get32(ix.data() + i + 8) + 8, get32(ix.data() + i + 12), get32(ix.data() + i + 4)});
+            const uint64_t off = base + get32(ix.data() + i + 8) + 8;
+            const uint32_t len = get32(ix.data() + i + 12);
+            if (off + len > fsize) continue;  // entry points outside the file
+            a->idx.push_back(AviIndexEntry{off, len, get32(ix.data() + i + 4)});
         }
     } else if (ok) {  // no index: scan the movi list; frame types are then inferred from the data by the decoder
         uint64_t pos = a->movi_pos + 4;
         while (pos + 8 <= movi_end) {
-            uint8_t ch[8];
+            uint8_t ch[12];
             fseek(f, (long)pos, SEEK_SET);
             if (fread(ch, 1, 8, f) != 8) break;
             const uint32_t id = get32(ch), sz = get32(ch + 4);
-            if (id == fcc("00dc") || id == fcc("00db")) a->idx.push_back(AviIndexEntry{pos + 8, sz, 0});
-            pos += 8 + sz + (sz & 1);
+            if (id == fcc("LIST")) {  // 'rec ' lists group the chunks of one interleave period: their frames are inside
+                pos += 12;
+                continue;
+            }
+            if ((id == fcc("00dc") || id == fcc("00db")) && pos + 8 + sz <= fsize) a->idx.push_back(AviIndexEntry{pos + 8, sz, 0});
+            pos += 8 + (uint64_t)sz + (sz & 1);
         }
     }
     if (!ok) {

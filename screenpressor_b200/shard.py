@@ -26,17 +26,34 @@ class FrameRange:
     rank: int    # owner
 
 
-def gop_ranges(keyflags: np.ndarray) -> list[tuple[int, int]]:
-    """[(first, count)] of the GOPs of a clip: every keyframe starts one (frame 0 always does)."""
+def gop_ranges(keyflags: np.ndarray, not_cuttable=()) -> list[tuple[int, int]]:
+    """[(first, count)] of the GOPs of a clip: every keyframe starts one (frame 0 always does), except the frames in
+    `not_cuttable` (see flat_keyframes)."""
     n = len(keyflags)
-    starts = [0] + [i for i in range(1, n) if keyflags[i]]
+    skip = set(int(i) for i in not_cuttable)
+    starts = [0] + [i for i in range(1, n) if keyflags[i] and i not in skip]
     return [(s, (starts[k + 1] if k + 1 < len(starts) else n) - s) for k, s in enumerate(starts)]
 
 
-def assign_ranges(keyflags: np.ndarray, world: int) -> list[FrameRange]:
+def flat_keyframes(frames: np.ndarray, keyflags: np.ndarray) -> list[int]:
+    """Requested keyframes that are single-colour frames.  The reference codes such a frame as a 4-byte flat frame and
+    does NOT start a new GOP with it: its frame counter keeps running and, when the colour repeats the last flat frame's,
+    not even the models are renewed (screencap.cpp:1488-1511) -- so the frames after it are P frames on state a fresh
+    codec does not have.  A range must not start there; the planner treats the frame as part of the GOP before it."""
+    out = []
+    for i in range(1, len(keyflags)):
+        if keyflags[i]:
+            f = np.asarray(frames[i])
+            px = f.reshape(-1, f.shape[-1])[:, :3] if f.ndim == 3 else None
+            if px is not None and (px == px[0]).all():
+                out.append(i)
+    return out
+
+
+def assign_ranges(keyflags: np.ndarray, world: int, not_cuttable=()) -> list[FrameRange]:
     """Contiguous GOP-aligned ranges, one per rank (fewer when the clip has fewer GOPs than ranks), balanced by
     frame count: GOP boundaries are the only cuts that keep the bitstream identical without moving model state."""
-    gops = gop_ranges(keyflags)
+    gops = gop_ranges(keyflags, not_cuttable)
     n = len(keyflags)
     parts = min(world, len(gops))
     out, g = [], 0
@@ -58,7 +75,8 @@ def assign_ranges(keyflags: np.ndarray, world: int) -> list[FrameRange]:
     return out
 
 
-def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, dist=None, device_ptr=None, pipelined: bool = True):
+def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, dist=None, device_ptr=None, pipelined: bool = True,
+                   not_cuttable=()):
     """Encode this rank's range of the clip.  `frames`: this rank's frames only (host ndarray, or None with a device
     pointer).  Returns (FrameRange | None, stream, sizes, ftypes) for the range.  `dist` = torch.distributed (already
     initialised) or None for a single process; the mvs[] blob travels rank -> rank + 1.
@@ -68,7 +86,7 @@ def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, d
     search, pixel typing, model replay, rANS -- runs concurrently on all ranks.  Otherwise whole ranges are serialised."""
     import torch
 
-    ranges = assign_ranges(keyflags, world)
+    ranges = assign_ranges(keyflags, world, not_cuttable)
     mine = next((r for r in ranges if r.rank == rank), None)
     if mine is None:
         return None, np.zeros(0, np.uint8), np.zeros(0, np.uint32), np.zeros(0, np.uint8)

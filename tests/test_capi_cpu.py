@@ -133,5 +133,23 @@ def test_avi_container_round_trip(tmp_path):
     open(path, "wb").write(cut)
     with codec.AviReader(path) as r:
         assert [r.read(i)[0] for i in range(len(r))] == chunks
+    # the same chunks grouped in 'rec ' lists (interleaved files), no index: the scan descends into the lists
+    movi_t = next(t for t in tree if t[1] == b"movi")
+    body = raw[movi_t[2] + 12:movi_t[2] + 8 + movi_t[3]]
+    rec = b"LIST" + struct.pack("<I", 4 + len(body)) + b"rec " + body
+    new_movi = b"LIST" + struct.pack("<I", 4 + len(rec)) + b"movi" + rec
+    grouped = raw[:movi_t[2]] + new_movi
+    grouped = grouped[:4] + struct.pack("<I", len(grouped) - 8) + grouped[8:]
+    open(path, "wb").write(grouped)
+    with codec.AviReader(path) as r:
+        assert [r.read(i)[0] for i in range(len(r))] == chunks
+    # hostile sizes: an index chunk that claims 4 GB, index entries that point past the end of the file
+    bad = bytearray(raw)
+    bad[idx[2] + 4:idx[2] + 8] = struct.pack("<I", 0xFFFFFFF0)
+    bad[idx[2] + 8 + 16 + 12:idx[2] + 8 + 16 + 16] = struct.pack("<I", 0x7FFFFFFF)   # second entry: absurd length
+    open(path, "wb").write(bytes(bad))
+    with codec.AviReader(path) as r:
+        got = [r.read(i)[0] for i in range(len(r))]
+        assert got == chunks[:1] + chunks[2:]
     with pytest.raises(codec.ScprError):
         codec.AviReader(str(tmp_path / "missing.avi"))

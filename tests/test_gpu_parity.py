@@ -301,6 +301,69 @@ def test_frame_range_sharding_is_byte_identical(scpr):
         pytest.skip("mvs[] did not influence this clip (hand-off still verified above)")
 
 
+def test_sharding_with_a_flat_frame_at_a_keyframe(scpr):
+    """a requested keyframe that is a flat frame (here: repeating the previous flat colour, so not even the models
+    are renewed) does not start a GOP in the reference.  The planner keeps it inside the previous range; a codec that is
+    nevertheless handed a small blob there refuses the P frame that has no models to continue instead of coding garbage."""
+    from screenpressor_b200 import shard
+
+    w, h, n = 160, 96, 20
+    clip = motion_clip(w, h, n, 9)
+    for f in (9, 10):                      # two flat frames of one colour; frame 10 is a requested keyframe
+        clip[f, ..., :3] = (40, 50, 60)
+    keys = np.zeros(n, np.uint8)
+    keys[[0, 10, 15]] = 1
+    whole = _split(*_new(scpr, w, h, 32).CompressClip(clip, keys))
+    assert [len(x[0]) for x in whole[9:11]] == [4, 4] and whole[11][1] == 1   # flat, flat, then a P frame on the old models
+    skip = shard.flat_keyframes(clip, keys)
+    assert skip == [10]
+    ranges = shard.assign_ranges(keys, 3, skip)
+    assert [(r.first, r.count) for r in ranges] == [(0, 15), (15, 5)]
+    blob, parts = None, []
+    for r in ranges:
+        c = _new(scpr, w, h, 32)
+        if blob is not None:
+            c.ImportRangeState(blob)
+        parts += _split(*c.CompressClip(clip[r.first:r.first + r.count], keys[r.first:r.first + r.count]))
+        blob = c.ExportRangeState(False)
+    assert parts == whole
+    # the bad cut: range [10, 15) on a small blob
+    a = _new(scpr, w, h, 32)
+    a.CompressClip(clip[:10], keys[:10])
+    b = _new(scpr, w, h, 32)
+    b.ImportRangeState(a.ExportRangeState(False))
+    with pytest.raises(scpr.ScprError):
+        b.CompressClip(clip[10:15], keys[10:15])
+    # ... and the same cut on a full blob is exact
+    b2 = _new(scpr, w, h, 32)
+    b2.ImportRangeState(a.ExportRangeState(True))
+    assert _split(*b2.CompressClip(clip[10:15], keys[10:15])) == whole[10:15]
+
+
+def test_failed_call_leaves_a_decodable_stream(scpr):
+    """an error after device work has started (here: destination too small) drops the frames of that call; the
+    next coded frame is an I frame with fresh models and the stream the caller holds decodes bit-exactly."""
+    w, h, n = 160, 96, 12
+    clip = motion_clip(w, h, n, 3)
+    keys = np.zeros(n, np.uint8)
+    keys[0] = 1
+    enc = _new(scpr, w, h, 32)
+    got = _split(*enc.CompressClip(clip[:4], keys[:4]))
+    sizes = np.zeros(4, np.uint32)
+    fts = np.zeros(4, np.uint8)
+    tiny = np.zeros(8, np.uint8)
+    r = enc._lib.scpr_compress_clip(enc._h, clip[4:8].ctypes.data, 4, keys[4:8].ctypes.data, tiny.ctypes.data, tiny.size, sizes.ctypes.data,
+                                    fts.ctypes.data)
+    assert r == scpr.SCPR_E_DSTSIZE
+    rest = _split(*enc.CompressClip(clip[8:], keys[8:]))
+    assert rest[0][1] == 0 and rest[0][0][0] == 0x32          # forced I frame
+    dec = _new(scpr, w, h, 32)
+    frames = got + rest
+    out = dec.DecompressClip(np.frombuffer(b"".join(x[0] for x in frames), np.uint8), np.array([len(x[0]) for x in frames], np.uint32),
+                             np.array([x[1] for x in frames], np.uint8))
+    assert np.array_equal(out.reshape(8, -1), np.concatenate([clip[:4], clip[8:]]).reshape(8, -1))
+
+
 def test_full_state_checkpoint_resume_at_any_frame(scpr):
     """full = 1: previous frame + adaptive models + mvs[]; an encode resumed in another codec object continues byte-exactly"""
     w, h, n = 200, 120, 30

@@ -143,6 +143,16 @@ def test_assign_ranges_cuts_only_at_keyframes():
     r = shard.assign_ranges(synth.keyframe_flags(600, 500), 8)   # cfg 2 has two GOPs: ranks beyond them stay idle
     assert [(x.first, x.count) for x in r] == [(0, 500), (500, 100)]
     assert shard.gop_ranges(np.array([0, 0, 1, 0, 1], np.uint8)) == [(0, 2), (2, 2), (4, 1)]
+    # a requested keyframe that is a single-colour frame does not start a GOP in the reference (screencap.cpp:1488-1511):
+    # the planner must not cut there
+    clip = np.zeros((6, 4, 8, 4), np.uint8)
+    clip[:, 1, 2, 0] = 7            # not flat ...
+    clip[2] = 0
+    clip[2, ..., :3] = (9, 9, 9)    # ... except frame 2
+    keys = np.array([1, 0, 1, 0, 1, 0], np.uint8)
+    assert shard.flat_keyframes(clip, keys) == [2]
+    assert shard.gop_ranges(keys, shard.flat_keyframes(clip, keys)) == [(0, 4), (4, 2)]
+    assert [(x.first, x.count) for x in shard.assign_ranges(keys, 3, [2])] == [(0, 4), (4, 2)]
 
 
 def _shard_rank_main(rank, world, port, q, pipelined):
