@@ -4,20 +4,28 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference codec core on the host CPU
 
-Workload (config.workload): BASELINE.json configs[1], 1920x1080 RGB32 synthetic desktop capture,
-600 frames, keyframes at 0 and 500 (the VfW default interval).  One *step* = encoding all 600
-frames and decoding them again.  `value` = frames / second with the input frames already resident
-in HBM when the timed region starts (bitstreams still travel to the host and back, they are tiny);
-`e2e` = the same through the host-buffer API (pinned host frames in, pinned host frames out), which
-is what a drop-in user of the reference's ScreenCodec sees.  Inputs (5 GB per step) exceed the
-126 MB L2, so no explicit L2 flush is needed between steps.
+N = 1 (config.workload): BASELINE.json configs[1], 1920x1080 RGB32 synthetic desktop capture, 600 frames, keyframes at 0 and
+500 (the VfW default interval).  One *step* = encoding all 600 frames and decoding them again.  `value` = frames / second with
+the input frames already resident in HBM when the timed region starts (bitstreams still travel to the host and back, they are
+tiny); `e2e` = the same through the host-buffer API (pinned host frames in, pinned host frames out), which is what a drop-in
+user of the reference's ScreenCodec sees.  Inputs (5 GB per step) exceed the 126 MB L2, so no explicit L2 flush is needed.
+Further legs of the N = 1 line (each can be switched off with --skip):
+  parity          every frame of the CUDA stream byte-compared with the reference's (oracle/_ref, one thread), in `cpu_baseline`
+  roofline        the HBM-bound frame scan kernel, timed alone, against MEASURED_PEAKS.json
+  gops_in_flight  decode throughput against the number of independent GOPs in one scpr_decompress_clips call, beside the
+                  reference decoding the same clips on as many host threads
+  frame_api       the drop-in call pattern: one CompressFrame / DecompressFrame per frame with host buffers
+  all_configs     BASELINE configs 1, 3, 4, 5: fps, GOP count, byte parity against the committed reference digests
 
-Multi-GPU: clips are independent, so each rank encodes+decodes its own clip (seed + rank); there is
-no data-path collective (weak scaling).  torch.distributed is only used for the timing barrier.
+N > 1: the north-star split -- ONE clip cut by contiguous GOP-aligned frame ranges across the N ranks; every
+rank encodes and decodes its range on its own GPU, the persistent motion-vector array travels rank to rank around the in-order
+resolve (a 64 KB point-to-point message, no collective on the data path), rank 0 concatenates the bitstreams on the host and
+checks them byte for byte against its own single-GPU encode of the whole clip.  Total work is fixed: "scaling": "strong".
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import hashlib
 import json
 import os
@@ -35,6 +43,7 @@ from screenpressor_b200 import synth  # noqa: E402
 
 WORKLOAD = "cfg2_1080p_rgb32"
 METRIC = "1080p_rgb32_encode_decode_frames_per_s"
+SPLIT_GOPS = 8
 
 
 def workload_config(frames: int):
@@ -47,10 +56,17 @@ def workload_config(frames: int):
             "l2": "inputs (5 GB/step) exceed L2; no flush needed", "statistic": "mean over the timed steps"}
 
 
+def split_config(frames: int, interval: int, world: int):
+    cfg = synth.CONFIGS[WORKLOAD]
+    return {"workload": f"{WORKLOAD} content: {cfg.width}x{cfg.height} RGB32 synthetic desktop capture, ONE clip of {frames} frames, keyframe "
+                        f"interval {interval} ({SPLIT_GOPS} GOPs), cut by GOP-aligned frame ranges across the ranks; one step = every rank "
+                        "encodes + decodes its range, bitstreams concatenated on the host",
+            "frames": frames, "key_interval": interval, "gops_per_clip": SPLIT_GOPS,
+            "l2": "inputs (>= 1 GB per rank and step) exceed L2; no flush needed", "statistic": "mean over the timed steps"}
+
+
 def make_workload(rank: int, frames: int):
     cfg = synth.CONFIGS[WORKLOAD]
-    if rank:
-        cfg = synth.ClipConfig(cfg.name, cfg.width, cfg.height, cfg.bpp, cfg.frames, cfg.key_interval, cfg.seed + 100 * rank, cfg.kind)
     clip = synth.make_clip(cfg, frames)
     keys = synth.keyframe_flags(frames, cfg.key_interval)
     return cfg, clip, keys
@@ -96,9 +112,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference(clip, keys, cfg, threads: int, keep=None):
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference on the host CPU (the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------------------------------
+def time_reference(clip, keys, cfg, threads: int, keep=None, per_frame=None):
     """encode+decode `clip` with the compiled reference core (oracle/_ref); returns (seconds enc, seconds dec, kind).
-    keep: a list that receives every frame's (bytes, ftype) -- the parity check of the CUDA stream."""
+    keep: a list that receives every frame's (bytes, ftype) -- the parity check of the CUDA stream.
+    per_frame: a list that receives (encode seconds, decode seconds, ftype) per frame."""
     from oracle import pyref  # the one place bench.py may execute oracle/: the CPU baseline
 
     kind = "reference" if pyref.have_ref() else "port"
@@ -120,11 +140,32 @@ def time_reference(clip, keys, cfg, threads: int, keep=None):
         td += t2 - t1
         if keep is not None:
             keep.append((data, ft))
+        if per_frame is not None:
+            per_frame.append((t1 - t0, t2 - t1, ft))
         if i % 97 == 0:
             assert np.array_equal(out, flat[i]), "reference round trip failed"
     enc.close()
     dec.close()
     return te, td, kind
+
+
+def reference_decode_many(cfg, stream, sizes, ftypes, n_clips: int, n_threads: int):
+    """n_clips copies of one clip decoded by the reference on n_threads host threads (oracle/ref_capi.cpp ref_decode_many);
+    returns wall seconds, or None when only the plain-C port is available."""
+    from oracle import pyref
+
+    if not pyref.have_ref():
+        return None
+    lib = C.CDLL(pyref.REF_SO)
+    if not hasattr(lib, "ref_decode_many"):
+        return None
+    lib.ref_decode_many.restype = C.c_double
+    lib.ref_decode_many.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_int] * 3
+    stream = np.ascontiguousarray(stream, np.uint8)
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    ftypes = np.ascontiguousarray(ftypes, np.uint8)
+    return float(lib.ref_decode_many(cfg.width, cfg.height, cfg.bpp, stream.ctypes.data, sizes.ctypes.data, ftypes.ctypes.data,
+                                     int(sizes.size), n_clips, n_threads))
 
 
 def run_reference(args):
@@ -134,8 +175,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    frames = args.frames
-    cfg, clip, keys = make_workload(0, frames)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = synth.CONFIGS[WORKLOAD]
+    if world > 1 or args.gpus > 1:
+        # the N > 1 workload of the CUDA arm: the one long clip (all of it: the CPU has no ranks to cut it across)
+        frames, interval = args.split_frames, args.split_frames // SPLIT_GOPS
+        clip = synth.make_clip(cfg, frames)
+        keys = synth.keyframe_flags(frames, interval)
+        config = split_config(frames, interval, max(world, args.gpus))
+    else:
+        frames = args.frames
+        cfg, clip, keys = make_workload(0, frames)
+        config = workload_config(frames)
     nby = (cfg.height + 15) // 16
     nthr = max(1, min(os.cpu_count() or 1, nby))  # cap: the reference's tls[] overflows past nby threads
     # all the host threads it can use: one probe step per thread count, the timed steps run with the faster one
@@ -151,9 +202,10 @@ def run_reference(args):
     fps = frames * args.steps / (te + td)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if (world > 1 or args.gpus > 1) else "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": workload_config(frames),
+        "config": config,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": thr, "kind": ts[0][2],
                          "sample": f"all {frames} frames of the clip per step, one CompressFrame + one DecompressFrame call per frame, "
                                    f"mean of {args.steps} steps",
@@ -162,6 +214,153 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# N = 1 legs
+# ---------------------------------------------------------------------------------------------------------------------------
+def leg_gops_in_flight(torch, ScreenCodec, CodecParameters, cfg, d_in, keys, local, gop_frames, cpu: bool):
+    """Decode throughput against the number of independent GOPs in one call.  The GOP is the first `gop_frames` frames of the
+    clip (its I frame and what follows); G copies of it are G independent clips for scpr_decompress_clips_dev: G chains, one
+    thread block each, in one launch.  Beside it the reference decoding the same G clips on min(G, cores) host threads."""
+    W, H = cfg.width, cfg.height
+    fb = W * H * 4
+    L = gop_frames
+    enc, dec = ScreenCodec(local), ScreenCodec(local)
+    for c in (enc, dec):
+        c.Init(CodecParameters(W, H, 32))
+    s, sizes, fts = enc.CompressClip(None, keys[:L], device_ptr=d_in.data_ptr(), n=L)
+    s, sizes, fts = s.copy(), sizes.copy(), fts.copy()
+    free, _ = torch.cuda.mem_get_info()
+    cores = os.cpu_count() or 1
+    rows = []
+    for G in (1, 2, 8, 32, 148):
+        if G * L * fb > free - (8 << 30):
+            rows.append({"gops": G, "skipped": "not enough free HBM for the decoded frames"})
+            continue
+        d_out = torch.empty(G * L * fb, dtype=torch.uint8, device="cuda")
+        clips = [(s, sizes, fts)] * G
+        dec.DecompressClips(clips, device_ptr=d_out.data_ptr())  # warm-up (workspaces)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        e0.record()
+        for _ in range(reps):
+            res, _ = dec.DecompressClips(clips, device_ptr=d_out.data_ptr())
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        assert all(r == 1 for r in res)
+        ref_px = d_in[:L * fb]
+        assert torch.equal(d_out[:L * fb], ref_px) and torch.equal(d_out[(G - 1) * L * fb:], ref_px), "multi-clip decode is not bit-exact"
+        row = {"gops": G, "frames": G * L, "ms": ms, "decode_fps": G * L / (ms / 1e3)}
+        if cpu:
+            thr = min(G, cores)
+            sec = reference_decode_many(cfg, s, sizes, fts, G, thr)
+            if sec:
+                row.update({"cpu_ref_decode_fps": G * L / sec, "cpu_threads": thr})
+        rows.append(row)
+        del d_out
+        torch.cuda.empty_cache()
+    return {"gop_frames": L, "note": "decode only, frames resident in HBM; one scpr_decompress_clips_dev call per row; cpu_ref = the "
+                                     "reference decoding the same clips, one clip per host thread (oracle/_ref ref_decode_many)",
+            "host_cores": cores, "curve": rows}
+
+
+def leg_frame_api(torch, ScreenCodec, CodecParameters, cfg, clip, keys, local, n_api, ref_per_frame):
+    """The drop-in call pattern (screenpressor.cpp:425, 620): one scpr_compress_frame / scpr_decompress_frame per frame, pinned
+    host buffers both ways, wall clock per call."""
+    W, H = cfg.width, cfg.height
+    fb = W * H * 4
+    n = min(n_api, len(clip))
+    enc, dec = ScreenCodec(local), ScreenCodec(local)
+    for c in (enc, dec):
+        c.Init(CodecParameters(W, H, 32))
+    h_src = torch.empty(fb, dtype=torch.uint8, pin_memory=True)
+    h_dst = torch.empty(fb, dtype=torch.uint8, pin_memory=True)
+    h_bits = torch.empty(W * H * 6, dtype=torch.uint8, pin_memory=True)
+    times = []
+    for rep in range(2):  # the first pass warms the workspaces up
+        enc.Reset()
+        dec.Reset()
+        times = []
+        for i in range(n):
+            h_src.numpy()[:] = clip[i].reshape(-1)
+            ft = C.c_int(0 if keys[i] else 1)
+            t0 = time.perf_counter()
+            sz = enc._lib.scpr_compress_frame(enc._h, h_src.data_ptr(), h_bits.data_ptr(), h_bits.numel(), C.byref(ft), 0)
+            t1 = time.perf_counter()
+            assert sz > 0, sz
+            r = dec._lib.scpr_decompress_frame(dec._h, h_bits.data_ptr(), sz, h_dst.data_ptr(), W * 4, ft.value)
+            t2 = time.perf_counter()
+            assert r == 1, r
+            if rep == 1:
+                assert torch.equal(h_dst, h_src), f"frame {i}: per-frame decode is not bit-exact"
+            times.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, ft.value, int(sz)))
+    p = [t for t in times if t[2] == 1]
+    i_fr = [t for t in times if t[2] == 0]
+    out = {"frames": n, "enc_ms_p50": float(np.median([t[0] for t in p])), "dec_ms_p50": float(np.median([t[1] for t in p])),
+           "enc_ms_p90": float(np.percentile([t[0] for t in p], 90)), "dec_ms_p90": float(np.percentile([t[1] for t in p], 90)),
+           "enc_ms_max": float(max(t[0] for t in p)), "dec_ms_max": float(max(t[1] for t in p)),
+           "I_enc_ms": float(np.mean([t[0] for t in i_fr])), "I_dec_ms": float(np.mean([t[1] for t in i_fr])),
+           "note": "P-frame statistics over the P frames of the first frames of the clip (cursor moves, text edits, a window drag, scrolls)"}
+    if ref_per_frame:
+        rp = [t for t in ref_per_frame[:n] if t[2] == 1]
+        ri = [t for t in ref_per_frame[:n] if t[2] == 0]
+        out["reference_1_thread"] = {"enc_ms_p50": float(np.median([t[0] for t in rp]) * 1e3), "dec_ms_p50": float(np.median([t[1] for t in rp]) * 1e3),
+                                     "enc_ms_p90": float(np.percentile([t[0] for t in rp], 90) * 1e3),
+                                     "dec_ms_p90": float(np.percentile([t[1] for t in rp], 90) * 1e3),
+                                     "I_enc_ms": float(np.mean([t[0] for t in ri]) * 1e3), "I_dec_ms": float(np.mean([t[1] for t in ri]) * 1e3)}
+    return out
+
+
+def leg_all_configs(torch, ScreenCodec, CodecParameters, local, cpu: bool):
+    """BASELINE configs 1, 3, 4, 5 at the lengths tests/golden holds reference digests for: fps with frames resident in HBM,
+    GOP count, byte parity of every frame against what the unmodified reference wrote (committed md5s), bit-exact decode."""
+    gold = {}
+    for name in ("ref_digests_long.json", "ref_digests.json"):
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            gold.update(json.load(f))
+    cases = [("cfg1_720p_rgb24_f24", "cfg1_720p_rgb24", 24, 500), ("cfg3_2160p_rgb32_f64_k450", "cfg3_2160p_rgb32", 64, 450),
+             ("cfg4_1440p_intra_f4", "cfg4_1440p_intra", 4, 1), ("cfg5_5120x1440_f120_k500", "cfg5_5120x1440", 120, 500)]
+    rows = []
+    for gname, cname, n, interval in cases:
+        cfg = synth.CONFIGS[cname]
+        clip = synth.make_clip(cfg, n)
+        keys = synth.keyframe_flags(n, interval)
+        d_in = torch.from_numpy(clip.reshape(-1)).cuda()
+        d_out = torch.empty_like(d_in)
+        enc, dec = ScreenCodec(local), ScreenCodec(local)
+        for c in (enc, dec):
+            c.Init(CodecParameters(cfg.width, cfg.height, cfg.bpp))
+        enc.reserve_clip_output(64 << 20)
+        for rep in range(2):
+            enc.Reset()
+            dec.Reset()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            s, sizes, fts = enc.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=n)
+            e1.record()
+            dec.DecompressClip(s, sizes, fts, device_ptr=d_out.data_ptr())
+            e2.record()
+            e2.synchronize()
+        ok_dec = bool(torch.equal(d_out, d_in))
+        pos, same = 0, True
+        for i, (gft, gsz, gmd5) in enumerate(gold[gname]["frames"]):
+            data = bytes(s[pos:pos + int(sizes[i])])
+            pos += int(sizes[i])
+            same = same and int(fts[i]) == gft and len(data) == gsz and hashlib.md5(data).hexdigest() == gmd5
+        row = {"config": cname, "size": f"{cfg.width}x{cfg.height}x{cfg.bpp}", "frames": n, "gops": int(keys.sum()),
+               "encode_fps": n / (e0.elapsed_time(e1) / 1e3), "decode_fps": n / (e1.elapsed_time(e2) / 1e3), "stream_bytes": int(sizes.sum()),
+               "identical_to_reference": bool(same), "decode_bit_exact": ok_dec}
+        if cpu:
+            m = min(n, 24 if cname != "cfg4_1440p_intra" else 2)
+            te, td, kind = time_reference(clip[:m], keys[:m], cfg, 1)
+            row.update({"ref_encode_fps": m / te, "ref_decode_fps": m / td, "ref_sample": f"first {m} frames, 1 thread, {kind}"})
+        rows.append(row)
+        assert same and ok_dec, f"{cname}: parity failure"
+        del d_in, d_out
+        torch.cuda.empty_cache()
+    return rows
 
 
 def run_cuda(args):
@@ -177,19 +376,8 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its version banner to stdout when the first communicator comes up: send it to stderr, rank 0's
-        # stdout carries exactly one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        return run_cuda_split(args, torch, dist, world, rank, local)
+    skip = set(args.skip.split(",")) if args.skip else set()
     frames = args.frames
     cfg, clip, keys = make_workload(rank, frames)
     W, H = cfg.width, cfg.height
@@ -197,8 +385,6 @@ def run_cuda(args):
     # pinned host copies for the end-to-end leg, device-resident copy for `value`
     h_in = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
     h_in.numpy()[:] = clip.reshape(-1)
-    if world > 1:
-        clip = None  # N ranks share the host's memory: keep only the pinned copy (the CPU baseline runs at N = 1 only)
     h_out = torch.empty(frames * fb, dtype=torch.uint8, pin_memory=True)
     d_in = h_in.cuda(non_blocking=True)
     d_out = torch.empty(frames * fb, dtype=torch.uint8, device="cuda")
@@ -240,25 +426,15 @@ def run_cuda(args):
         stage["e2e_dec_s"] += t2 - t1
         return s, sizes, fts
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, steps):
-        barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
             res = fn()
         e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, res
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), res
 
     # correctness gate before timing: decode(encode(clip)) must reproduce the clip bit for bit
     step_device()
@@ -267,17 +443,17 @@ def run_cuda(args):
     for _ in range(max(0, args.warmup - 1)):
         step_device()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     l0 = enc.kernel_launches() + dec.kernel_launches()
     stage["enc_ms"] = stage["dec_ms"] = 0.0
     ms, (s, sizes, fts) = timed(step_device, args.steps)
     s_keep, sizes_keep, fts_keep = s.copy(), sizes.copy(), fts.copy()
     launches = enc.kernel_launches() + dec.kernel_launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * frames * args.steps / (ms / 1e3)
+    clocks = sampler.stop()
+    value = frames * args.steps / (ms / 1e3)
     enc_fps = frames * args.steps / (stage["enc_ms"] / 1e3)
     dec_fps = frames * args.steps / (stage["dec_ms"] / 1e3)
+    dec_share = stage["dec_ms"] / ms
 
     # end-to-end leg
     step_host()
@@ -288,45 +464,8 @@ def run_cuda(args):
     assert np.array_equal(s2, s_keep) and np.array_equal(sizes2, sizes_keep), "host-buffer stream differs from the device-resident one"
     e2e_enc_fps = frames * args.steps / stage["e2e_enc_s"]
     e2e_dec_fps = frames * args.steps / stage["e2e_dec_s"]
-    e2e = world * frames * args.steps / (ms_e2e / 1e3)
-    stream_bytes = int(sizes.sum())
-
-    # several independent clips in flight on one GPU (decode parallelism is per GOP chain):
-    # `multi` codec pairs, one CUDA stream + host thread each, same clip
-    multi = None
-    if args.multi > 1 and world == 1:
-        import threading as th
-
-        pairs = []
-        for k in range(args.multi):
-            st_k = torch.cuda.Stream()
-            e_k, d_k = ScreenCodec(local), ScreenCodec(local)
-            for c in (e_k, d_k):
-                c.Init(CodecParameters(W, H, 32))
-                c.set_stream(st_k.cuda_stream)
-            e_k.reserve_clip_output(64 << 20)
-            pairs.append((e_k, d_k, torch.empty(frames * fb, dtype=torch.uint8, device="cuda")))
-
-        def work(e_k, d_k, out_k):
-            e_k.Reset(); d_k.Reset()
-            s_k, sz_k, ft_k = e_k.CompressClip(None, keys, device_ptr=d_in.data_ptr(), n=frames)
-            d_k.DecompressClip(s_k, sz_k, ft_k, device_ptr=out_k.data_ptr())
-
-        def run_all():
-            ts = [th.Thread(target=work, args=p) for p in pairs]
-            [t.start() for t in ts]
-            [t.join() for t in ts]
-
-        run_all()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run_all()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert all(torch.equal(p[2], d_in) for p in pairs)
-        multi = {"clips_in_flight": args.multi, "value": args.multi * frames / dt, "unit": "frames/s",
-                 "note": "same metric with several independent 600-frame clips decoded/encoded concurrently on one GPU (wall clock)"}
-        del pairs
+    e2e = frames * args.steps / (ms_e2e / 1e3)
+    stream_bytes = int(sizes_keep.sum())
 
     # roofline leg: the frame-scan kernel (stage A pass 1), timed alone with CUDA events on its stream
     fresh()
@@ -342,18 +481,27 @@ def run_cuda(args):
     tpath = os.path.join(ROOT, "profiles", "frame_scan_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch_600f")
+    roofline = {"kernel": "k_frame_scan32", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms,
+                "share_of_step": scan_ms / (ms / args.steps)}
+    if traffic:
+        # frame f - 1, read as "prev" of frame f, is still in the 126 MB L2: about half of the algorithmic bytes never cross
+        # HBM.  What does cross, per second, against the same peak:
+        roofline.update({"dram_GBps": traffic / (scan_ms / 1e3) / 1e9, "dram_frac": traffic / (scan_ms / 1e3) / 1e9 / peak,
+                         "note": "`achieved` counts algorithmic bytes (cur + prev per frame); `traffic` = dram bytes of the same launch "
+                                 "from ncu (profiles/): the previous frame is served by L2, so dram_frac is the honest HBM figure. This "
+                                 "kernel is a fraction of a percent of the step; the step is the decoder's serial GOP chain, see dominant_kernel"})
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    cpu_on = not args.no_cpu_baseline
     cpu = parity = None
-    if world == 1 and not args.no_cpu_baseline:
+    ref_per_frame = []
+    if cpu_on:
         # the reference on one host thread (its canonical bitstream) over the same frames; every frame it codes is
         # byte-compared with the CUDA stream of the timed steps
         sample = min(args.ref_frames, frames)
         ref_frames = []
-        te, td, kind = time_reference(clip[:sample], keys[:sample], cfg, 1, keep=ref_frames)
+        te, td, kind = time_reference(clip[:sample], keys[:sample], cfg, 1, keep=ref_frames, per_frame=ref_per_frame)
         cpu = {"value": sample / (te + td), "unit": "frames/s", "cores": 1, "kind": kind,
                "sample": f"the first {sample} of {frames} frames of the same clip, one CompressFrame + DecompressFrame call per frame, 1 thread "
                          "(canonical bitstream), one pass",
@@ -364,11 +512,23 @@ def run_cuda(args):
             pos += int(sizes_keep[i])
             if got != data or int(fts_keep[i]) != ft:
                 bad.append(i)
-        parity = {"frames": len(ref_frames), "identical": not bad, "against": "oracle/_ref (unmodified reference, 1 thread)" if kind == "reference" else "oracle port",
+        parity = {"frames": len(ref_frames), "identical": not bad,
+                  "against": "oracle/_ref (unmodified reference, 1 thread)" if kind == "reference" else "oracle port",
                   "first_mismatches": bad[:5], "stream_md5": hashlib.md5(bytes(s_keep)).hexdigest()}
         assert not bad, f"CUDA bitstream differs from the reference at frames {bad[:5]}"
+
+    gops = frame_api = all_cfg = None
+    if "gops" not in skip:
+        gops = leg_gops_in_flight(torch, ScreenCodec, CodecParameters, cfg, d_in, keys, local, args.gop_frames, cpu_on)
+    if "frame_api" not in skip:
+        frame_api = leg_frame_api(torch, ScreenCodec, CodecParameters, cfg, clip, keys, local, args.api_frames, ref_per_frame)
+    del d_out, h_out
+    torch.cuda.empty_cache()
+    if "all_configs" not in skip:
+        all_cfg = leg_all_configs(torch, ScreenCodec, CodecParameters, local, cpu_on)
+
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": workload_config(frames),
@@ -380,24 +540,190 @@ def run_cuda(args):
                 "note": "this rank's host-buffer calls: pinned frames in -> bitstream out, bitstream in -> pinned frames out"},
         "gpu_launches": launches,
         "encode_fps": enc_fps, "decode_fps": dec_fps,
-        "multi_clip": multi,
+        "mpix_per_s": value * W * H / 1e6,
         "clocks": clocks,
-        "roofline": {"kernel": "k_frame_scan32", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms,
-                     "share_of_step": scan_ms / (ms / args.steps),
-                     "note": "the HBM-bound stage (delta / changed-block detection); the step itself is dominated by the "
-                             "decoder's serial GOP chain, see dominant_kernel"},
-        "dominant_kernel": {"kernel": "k_dec_chain", "share_of_step": (stage["dec_ms"] / args.steps) / (ms / args.steps),
-                            "bound": "serial dependency chain of one GOP: one chain warp per GOP (~6 cycles per issued instruction) + helper warps for "
-                                     "motion-vector copies; see profiles/ and multi_clip for the throughput with more chains in flight",
+        "roofline": roofline,
+        "dominant_kernel": {"kernel": "k_dec_chain", "share_of_step": dec_share,
+                            "bound": "serial dependency chain of one GOP: one chain warp per GOP at IPC 0.2 (dependent-chain latency, "
+                                     "profiles/r02_chain_variants.txt) + a reconstruction warp and copy warps; throughput comes from chains in "
+                                     "flight, see gops_in_flight",
                             "algorithmic_decode_bytes_per_step": frames * W * H * 8,
                             "achieved_GBps": frames * W * H * 8 / (stage["dec_ms"] / args.steps / 1e3) / 1e9},
+        "gops_in_flight": gops,
+        "frame_api": frame_api,
+        "all_configs": all_cfg,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# N > 1: one clip cut by frame ranges across the ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------------------------------------
+def run_cuda_split(args, torch, dist, world, rank, local):
+    from screenpressor_b200 import shard
+    from screenpressor_b200.codec import CodecParameters, ScreenCodec
+
+    # NCCL writes its version banner to stdout when the first communicator comes up: send it to stderr, rank 0's
+    # stdout carries exactly one JSON line.  CPU tensors (the 64 KB hand-off blob) go over gloo, the barrier over NCCL.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    cfg = synth.CONFIGS[WORKLOAD]
+    W, H = cfg.width, cfg.height
+    fb = W * H * 4
+    frames, interval = args.split_frames, args.split_frames // SPLIT_GOPS
+    keys = synth.keyframe_flags(frames, interval)
+    ranges = shard.assign_ranges(keys, world)
+    mine = next((r for r in ranges if r.rank == rank), None)
+    # rank 0 holds the whole clip (it also produces the single-GPU stream everything is compared with), the others their range
+    if rank == 0:
+        clip = synth.make_clip(cfg, frames)
+        mine_np = clip[mine.first:mine.first + mine.count]
+    else:
+        clip = None
+        mine_np = synth.make_clip_range(cfg, mine.first, mine.count) if mine else None
+    n_mine = mine.count if mine else 0
+    h_in = torch.empty(max(n_mine, 1) * fb, dtype=torch.uint8, pin_memory=True)
+    if n_mine:
+        h_in.numpy()[:n_mine * fb] = mine_np.reshape(-1)
+    h_out = torch.empty(max(n_mine, 1) * fb, dtype=torch.uint8, pin_memory=True)
+    d_in = h_in.cuda()
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.current_stream()
+    enc, dec = ScreenCodec(local), ScreenCodec(local)
+    for c in (enc, dec):
+        c.Init(CodecParameters(W, H, 32))
+        c.set_stream(stream.cuda_stream)
+    enc.reserve_clip_output(64 << 20)
+    stage = {"enc": 0.0, "dec": 0.0}
+
+    def one_step(host: bool):
+        """every rank: encode its range (the mvs[] blob arrives before / leaves after its in-order resolve), decode it again"""
+        enc.Reset()
+        dec.Reset()
+        t0 = time.perf_counter()
+        if host:
+            rng, s, sizes, fts = shard.encode_sharded(enc, h_in.numpy()[:n_mine * fb] if n_mine else None, keys, rank, world, dist)
+        else:
+            rng, s, sizes, fts = shard.encode_sharded(enc, None, keys, rank, world, dist, device_ptr=d_in.data_ptr() if n_mine else None)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if n_mine:
+            if host:
+                r = dec._lib.scpr_decompress_clip(dec._h, s.ctypes.data, sizes.ctypes.data, fts.ctypes.data, n_mine, h_out.data_ptr(), W * 4)
+                assert r == 1, r
+            else:
+                dec.DecompressClip(s, sizes, fts, device_ptr=d_out.data_ptr())
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        stage["enc"] += t1 - t0
+        stage["dec"] += t2 - t1
+        return rng, s, sizes, fts
+
+    def timed(host: bool, steps: int):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage["enc"] = stage["dec"] = 0.0
+        e0.record(stream)
+        for _ in range(steps):
+            res = one_step(host)
+        e1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), stage["enc"] * 1e3, stage["dec"] * 1e3], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()], res
+
+    # correctness gate + warm-up
+    rng, s, sizes, fts = one_step(False)
+    if n_mine:
+        assert torch.equal(d_out[:n_mine * fb], d_in[:n_mine * fb]), "decode(encode(range)) != range"
+    for _ in range(max(0, args.warmup - 1)):
+        one_step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = enc.kernel_launches() + dec.kernel_launches()
+    (ms, enc_ms, dec_ms), (rng, s, sizes, fts) = timed(False, args.steps)
+    launches = enc.kernel_launches() + dec.kernel_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    (ms_e2e, e2e_enc_ms, e2e_dec_ms), (_, s2, sizes2, _) = timed(True, args.steps)
+    if n_mine:
+        assert np.array_equal(h_out.numpy()[:n_mine * fb], h_in.numpy()[:n_mine * fb]), "host-buffer decode(encode(range)) != range"
+        assert np.array_equal(s2, s), "host-buffer stream differs from the device-resident one"
+    # host-side concatenation on rank 0
+    parts = [None] * world
+    dist.gather_object((rng, np.array(s), np.array(sizes), np.array(fts)), parts if rank == 0 else None, dst=0)
+    if rank != 0:
+        dist.barrier()
         dist.destroy_process_group()
+        return
+    cs, csz, cft = shard.gather_streams(parts)
+    # the same clip on this rank's GPU alone: the single-GPU stream (parity) and the single-GPU time (what N ranks are set against)
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    d_all = torch.from_numpy(clip.reshape(-1)).cuda()
+    d_all_out = torch.empty_like(d_all)
+    whole, wdec = ScreenCodec(local), ScreenCodec(local)
+    for c in (whole, wdec):
+        c.Init(CodecParameters(W, H, 32))
+    whole.reserve_clip_output(256 << 20)
+    single = {}
+    for rep in range(2):
+        whole.Reset()
+        wdec.Reset()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        ws, wsz, wft = whole.CompressClip(None, keys, device_ptr=d_all.data_ptr(), n=frames)
+        e1.record()
+        wdec.DecompressClip(ws, wsz, wft, device_ptr=d_all_out.data_ptr())
+        e2.record()
+        e2.synchronize()
+        single = {"value": frames / (e0.elapsed_time(e2) / 1e3), "encode_fps": frames / (e0.elapsed_time(e1) / 1e3),
+                  "decode_fps": frames / (e1.elapsed_time(e2) / 1e3), "unit": "frames/s",
+                  "note": "the whole clip on rank 0's GPU alone, same box, one pass after a warm-up pass (all 8 GOP chains decode "
+                          "concurrently on one GPU)"}
+    assert torch.equal(d_all_out, d_all)
+    same = bool(np.array_equal(cs, ws) and np.array_equal(csz, wsz) and np.array_equal(cft, wft))
+    assert same, "sharded bitstream differs from the single-GPU bitstream"
+    stream_bytes = int(csz.sum())
+    value = frames * args.steps / (ms / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": split_config(frames, interval, world),
+        "ranges": [[r.first, r.count] for r in ranges],
+        "stream_bytes_per_clip": stream_bytes,
+        "parity": {"frames": frames, "identical": same, "against": "this rank's single-GPU encode of the whole clip (pinned to the reference by "
+                   "tests/golden and the N = 1 bench line)", "stream_md5": hashlib.md5(cs.tobytes()).hexdigest()},
+        "encode_fps": frames * args.steps / (enc_ms / 1e3), "decode_fps": frames * args.steps / (dec_ms / 1e3),
+        "mpix_per_s": value * W * H / 1e6,
+        "single_gpu": single,
+        "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
+                "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps,
+                "encode_fps": frames * args.steps / (e2e_enc_ms / 1e3), "decode_fps": frames * args.steps / (e2e_dec_ms / 1e3),
+                "note": "every rank: its pinned host frames in -> bitstream out, bitstream in -> pinned host frames out; bytes are the sum over ranks"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "serialised_by": "decode: the GOP is one dependency chain -- a rank with one GOP takes as long as a GPU with all of them (one chain per "
+                         "SM), so frame ranges only pay once a GPU holds more GOPs than SMs, or for the host transfers (e2e); encode: the in-order "
+                         "motion-vector resolves of consecutive ranges run one after the other (mvs[] hand-off), everything else overlaps",
+        "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -409,7 +735,10 @@ def main():
     ap.add_argument("--frames", type=int, default=synth.CONFIGS[WORKLOAD].frames)
     ap.add_argument("--ref-frames", type=int, default=600, help="frames the cpu_baseline / parity leg of the CUDA arm runs through the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi", type=int, default=8, help="also measure N independent clips in flight on one GPU (0 = skip)")
+    ap.add_argument("--skip", default="", help="comma list of N = 1 legs to leave out: gops,frame_api,all_configs")
+    ap.add_argument("--gop-frames", type=int, default=50, help="frames per GOP in the gops_in_flight leg")
+    ap.add_argument("--api-frames", type=int, default=120, help="frames of the frame_api leg")
+    ap.add_argument("--split-frames", type=int, default=1200, help="N > 1: frames of the one clip that is cut across the ranks (8 GOPs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

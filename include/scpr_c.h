@@ -85,11 +85,30 @@ int64_t scpr_compress_clip(scpr_codec* c, const uint8_t* frames, int n, const ui
 int64_t scpr_compress_clip_dev(scpr_codec* c, const uint8_t* d_frames, int n, const uint8_t* keyflags,
                                uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes);
 /* stream: concatenated frame bitstreams, sizes[i] bytes each, ftypes[i] = 0 I / 1 P.
- * frames: n decoded frames back to back with row pitch `pitch`. Returns 1, 0 or < 0 as above. */
+ * frames: n decoded frames back to back with row pitch `pitch` (may differ from call to call; only width * bytes-per-pixel bytes
+ * of every row are written, the rest of the pitch is the caller's).  Returns 1, 0 or < 0 as above. */
 int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes,
                          int n, uint8_t* frames, int pitch);
 int scpr_decompress_clip_dev(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes,
                              int n, uint8_t* d_frames, int pitch);
+
+/* Many independent clips (or GOPs cut out of a long clip) in ONE call: decoding is one serial dependency chain per GOP
+ * (SURVEY.md 0.4), so what fills a GPU is the number of chains in flight -- every GOP of every clip becomes one thread block of
+ * the same launch.  Each clip must start with an I frame and is decoded as by a fresh codec; `result` reports per clip what
+ * scpr_decompress_clip would have returned (1, 0 = starts with a P frame, -v / SCPR_E_* = cannot be decoded); the call returns 1
+ * when every clip decoded, else the first failure.  The decoder state of `c` is reset by the call.
+ *   scpr_decompress_clips     : clips[k].frames = host destination of clip k (n frames back to back, row pitch `pitch`).
+ *   scpr_decompress_clips_dev : all frames go to `d_frames` (device memory), clip after clip in the order given; clips[k].frames is ignored. */
+typedef struct scpr_clip {
+    const uint8_t* stream;   /* the clip's frame bitstreams back to back */
+    const uint32_t* sizes;   /* n sizes */
+    const uint8_t* ftypes;   /* n frame types, 0 = I, 1 = P */
+    int n;
+    uint8_t* frames;         /* host destination (scpr_decompress_clips) */
+    int result;              /* out */
+} scpr_clip;
+int scpr_decompress_clips(scpr_codec* c, scpr_clip* clips, int n_clips, int pitch);
+int scpr_decompress_clips_dev(scpr_codec* c, scpr_clip* clips, int n_clips, uint8_t* d_frames, int pitch);
 
 /* ---- frame-range sharding and checkpoint / resume of the encoder (no reference equivalent) ------
  * A clip is cut into contiguous frame ranges that are encoded by different codec objects (one per GPU) and the

@@ -6,6 +6,11 @@
 // tests and bench.py's cpu_baseline / --impl reference legs can drive the real reference.
 // It also supplies the three symbols the excluded VfW files normally provide
 // (drvproc.cpp:191-197 Set/GetThreadLocalInt, screencap.cpp:222 hmoduleSCPR, logging.cpp logF).
+#include <atomic>   // (standard headers first: the windows.h shim defines min / max macros)
+#include <chrono>
+#include <thread>
+#include <vector>
+
 #include "screencap.h"
 
 FILE* logF = NULL;
@@ -58,3 +63,43 @@ int ref_decompress(void* h, unsigned char* src, int src_len, unsigned char* dst,
 }
 
 }  // extern "C"
+
+// ---- the reference with several clips in flight: one clip per host thread ---------------------------------------------------
+// bench.py's gops_in_flight leg sets the GPU (all GOP chains of a batch of clips in one launch) beside the reference given the
+// same courtesy: n_clips copies of one clip decoded by n_threads host threads, every thread with its own ScreenCodec and frame
+// buffer, no Python in between.  Returns the wall-clock seconds from the moment all threads are ready until the last is done.
+extern "C" double ref_decode_many(int width, int height, int bits_per_pixel, const unsigned char* stream, const unsigned* sizes,
+                                  const unsigned char* ftypes, int n, int n_clips, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_clips) n_threads = n_clips;
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += sizes[i];
+    std::vector<unsigned char> padded(stream, stream + total);
+    padded.resize(total + 64, 0);  // the decoder's refill may read a few bytes past the end of a frame
+    std::atomic<int> ready(0), next(0);
+    std::atomic<bool> go(false);
+    std::vector<std::thread> pool;
+    const int pitch = ((width * bits_per_pixel / 8) + 3) & ~3;
+    for (int t = 0; t < n_threads; t++)
+        pool.emplace_back([&, t]() {
+            std::vector<unsigned char> out((size_t)pitch * height);
+            ready++;
+            while (!go.load()) std::this_thread::yield();
+            for (;;) {
+                const int k = next++;
+                if (k >= n_clips) break;
+                void* h = ref_create(width, height, bits_per_pixel, 0, 1);
+                size_t pos = 0;
+                for (int i = 0; i < n; i++) {
+                    ref_decompress(h, padded.data() + pos, (int)sizes[i], out.data(), pitch, ftypes[i]);
+                    pos += sizes[i];
+                }
+                ref_destroy(h);
+            }
+        });
+    while (ready.load() < n_threads) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true);
+    for (auto& th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}

@@ -48,6 +48,11 @@ class _Params(C.Structure):
     ]
 
 
+class _Clip(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("sizes", C.c_void_p), ("ftypes", C.c_void_p), ("n", C.c_int), ("frames", C.c_void_p),
+                ("result", C.c_int)]
+
+
 class _Policy(C.Structure):
     _fields_ = [("force_interval", C.c_int), ("kf_interval", C.c_int), ("force_loss", C.c_int), ("conf_loss", C.c_int)]
 
@@ -104,6 +109,10 @@ def load_library() -> C.CDLL:
         fn.restype = i32
         fn.argtypes = [vp, vp, vp, vp, i32, vp, i32]
     lib.scpr_reset.restype = i32
+    lib.scpr_decompress_clips.restype = i32
+    lib.scpr_decompress_clips.argtypes = [vp, C.POINTER(_Clip), i32, i32]
+    lib.scpr_decompress_clips_dev.restype = i32
+    lib.scpr_decompress_clips_dev.argtypes = [vp, C.POINTER(_Clip), i32, vp, i32]
     lib.scpr_reset.argtypes = [vp]
     lib.scpr_set_stream.restype = i32
     lib.scpr_set_stream.argtypes = [vp, vp]
@@ -274,6 +283,33 @@ class ScreenCodec:
             raise ScprError(0, "P frame before any I frame")
         self._check(r)
         return out
+
+    def DecompressClips(self, clips, pitch: int | None = None, device_ptr: int | None = None, out: list | None = None):
+        """Many independent clips in one call: every GOP of every clip is one thread block of the same launch
+        (scpr_decompress_clips).  clips: [(stream, sizes, ftypes), ...], each starting with an I frame.
+        -> (results, frames): results[k] = 1 / 0 / error code of clip k; frames[k] = ndarray (n_k, height*pitch), or None when
+        decoding into device_ptr (all clips back to back).  `out`: optional preallocated host arrays, one per clip."""
+        pitch = self.pitch if pitch is None else pitch
+        arr = (_Clip * len(clips))()
+        keep, frames = [], []
+        for k, (stream, sizes, ftypes) in enumerate(clips):
+            stream = np.ascontiguousarray(stream, dtype=np.uint8)
+            sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+            ftypes = np.ascontiguousarray(ftypes, dtype=np.uint8)
+            keep.append((stream, sizes, ftypes))
+            arr[k].stream, arr[k].sizes, arr[k].ftypes, arr[k].n = _ptr(stream), _ptr(sizes), _ptr(ftypes), int(sizes.size)
+            if device_ptr is None:
+                o = out[k] if out is not None else np.zeros((int(sizes.size), self.params.height * pitch), dtype=np.uint8)
+                frames.append(o)
+                arr[k].frames = _ptr(o)
+        if device_ptr is None:
+            r = self._lib.scpr_decompress_clips(self._h, arr, len(clips), pitch)
+        else:
+            r = self._lib.scpr_decompress_clips_dev(self._h, arr, len(clips), device_ptr, pitch)
+        results = [int(arr[k].result) for k in range(len(clips))]
+        if r in (SCPR_E_PARAM, SCPR_E_CUDA):
+            self._check(r)
+        return results, (frames if device_ptr is None else None)
 
     # ---- frame-range sharding / checkpoint (include/scpr_c.h) ----------------------------------------
     def ExportRangeState(self, full: bool = False) -> np.ndarray:

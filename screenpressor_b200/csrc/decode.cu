@@ -2158,53 +2158,114 @@ static int ensure_dec_states(scpr_codec* c, int n) {
     return SCPR_OK;
 }
 
-// n frames, bitstreams on the host, decoded frames to device memory `d_out` (pitch bytes per row)
-static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* d_out,
-                        int pitch, uint8_t* h_out = nullptr) {
+// Bytes of one output row that carry pixels (the rest of `pitch` is the caller's padding, never written: the reference
+// writes X * bytes-per-pixel per row, screencap.cpp:1713-1738)
+static size_t row_bytes(const scpr_codec* c) { return (size_t)c->g.X * (c->rgb16 ? 2 : c->g.bpp); }
+
+// device -> host copy of frames [a, b) of a batch that keeps the padding of the caller's rows
+static cudaError_t download_frames(uint8_t* h, const uint8_t* d, size_t frame_bytes, int pitch, size_t rowb, int Y, int a, int b, cudaStream_t s) {
+    if ((size_t)pitch == rowb) return cudaMemcpyAsync(h, d, (size_t)(b - a) * frame_bytes, cudaMemcpyDeviceToHost, s);
+    return cudaMemcpy2DAsync(h, (size_t)pitch, d, (size_t)pitch, rowb, (size_t)(b - a) * Y, cudaMemcpyDeviceToHost, s);
+}
+
+// What one decode call works on.  Single-stream calls (clip_start == nullptr) continue the codec's decoder state -- open
+// model chain, previous frame, flat-frame memory -- exactly as consecutive DecompressFrame calls do.  Multi-clip calls mark
+// the first frame of every independent clip: each starts like a fresh codec (its first frame must be an I frame) and all
+// chains of all clips run in ONE launch of the chain kernel, one CTA each.
+struct DecJob {
+    const uint8_t* stream;      // host: the frames' bitstreams back to back
+    const uint32_t* sizes;
+    const uint8_t* ftypes;
+    int n;
+    uint8_t* d_out;             // device: n frames back to back
+    int pitch;
+    const uint8_t* clip_start;  // n flags or nullptr
+    uint8_t* const* h_clip;     // multi-clip: host destination of every clip (frames back to back), or nullptr
+    uint8_t* h_out;             // single stream: host destination, or nullptr
+    int* clip_result;           // multi-clip: per clip 1 / 0 / < 0
+};
+
+// n frames, bitstreams on the host, decoded frames to device memory (pitch bytes per row) and, when asked, on to host memory
+static int decode_range(scpr_codec* c, const DecJob& j) {
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->st;
+    const int n = j.n, pitch = j.pitch;
     if (n <= 0) return 1;
+    const bool multi = j.clip_start != nullptr;
     Geo g = c->g;
     g.pitch = pitch;
     g.frame_bytes = (size_t)pitch * g.Y;
     if (pitch < g.X * g.bpp) return SCPR_E_PARAM;
-    // ---- host plan: frame kinds, versions, chains (DecompressFrame, screencap.cpp:1695-1702, 1522-1557)
+    // ---- host plan: frame kinds, versions, chains (DecompressFrame, screencap.cpp:1695-1702, 1522-1557).  The plan works
+    // on copies of the codec's decoder state; they are committed after the kernels have run (a rejected call must
+    // not change the renew decision or the version of the next valid frame).
+    bool created = multi ? false : c->dec_created, last_was_flat = multi ? false : c->dec_last_was_flat;
+    int version = multi ? 0 : c->dec_version;
+    uint8_t last_flat_clr[3] = {c->dec_last_flat_clr[0], c->dec_last_flat_clr[1], c->dec_last_flat_clr[2]};
     std::vector<DecFrame> frames(n);
     std::vector<DecChain> chains;
+    std::vector<int> clip_of(multi ? n : 0), clip_first;
     uint64_t off = 0;
+    int clip = -1;
+    bool clip_dead = false;  // multi: this clip was refused, its frames are left alone
     for (int f = 0; f < n; f++) {
         DecFrame& d = frames[f];
         memset(&d, 0, sizeof(d));
         d.src_off = (uint32_t)off;
-        d.size = sizes[f];
-        const uint8_t* s = stream + off;
-        off += sizes[f];
-        if (sizes[f] < 1) return SCPR_E_PARAM;
-        if (!c->dec_created) {
-            if (ftypes[f] > 0) return 0;  // P frame before any I frame
-            const int version = (s[0] >> 4) + 1;
-            if (version < 2 || version > 4) return -version;  // BadVersionException (screencap.cpp:1589-1590)
-            if (version == 2 && (c->p.high_range_x < 1 || c->p.high_range_x > 256 || c->p.high_range_y < 1 || c->p.high_range_y > 256)) {
-                set_error("v2 stream: motion range %u x %u outside 1..256", c->p.high_range_x, c->p.high_range_y);
-                return SCPR_E_UNSUPPORTED;
+        d.size = j.sizes[f];
+        const uint8_t* s = j.stream + off;
+        off += j.sizes[f];
+        if (j.sizes[f] < 1) return SCPR_E_PARAM;
+        if (multi) {
+            if (j.clip_start[f] || f == 0) {
+                clip++;
+                clip_first.push_back(f);
+                created = last_was_flat = clip_dead = false;
+                j.clip_result[clip] = 1;
             }
-            c->dec_version = version;
-            c->dec_created = true;
+            clip_of[f] = clip;
+            if (clip_dead) {
+                d.kind = DK_PSAME;
+                continue;
+            }
         }
-        if (ftypes[f]) {
-            c->dec_last_was_flat = false;
+        if (!created) {
+            int bad = 1;
+            const int v = (s[0] >> 4) + 1;
+            if (j.ftypes[f] > 0) bad = 0;  // P frame before any I frame
+            else if (v < 2 || v > 4) bad = -v;  // BadVersionException (screencap.cpp:1589-1590)
+            else if (v == 2 && (c->p.high_range_x < 1 || c->p.high_range_x > 256 || c->p.high_range_y < 1 || c->p.high_range_y > 256)) {
+                set_error("v2 stream: motion range %u x %u outside 1..256", c->p.high_range_x, c->p.high_range_y);
+                bad = SCPR_E_UNSUPPORTED;
+            } else if (multi && version && v != version) {
+                set_error("clips of one call must share a stream version (%d and %d)", version, v);
+                bad = SCPR_E_UNSUPPORTED;
+            }
+            if (bad != 1) {
+                if (!multi) return bad;
+                j.clip_result[clip] = bad;
+                clip_dead = true;
+                d.kind = DK_PSAME;
+                continue;
+            }
+            version = v;
+            created = true;
+        }
+        const bool fresh_clip = multi && f == clip_first.back();
+        if (j.ftypes[f]) {
+            last_was_flat = false;
             d.kind = (s[0] & 1) ? DK_P : DK_PSAME;
-            if (chains.empty()) chains.push_back(DecChain{f, 0, -2});  // continues the previous call's chain
+            if (chains.empty()) chains.push_back(DecChain{f, 0, -2});  // continues the previous call's chain (single stream only: a clip starts with an I frame)
         } else if ((s[0] & 0x0F) == 1) {
-            if (sizes[f] < 4) return SCPR_E_PARAM;
+            if (j.sizes[f] < 4) return SCPR_E_PARAM;
             d.kind = DK_FLAT;
             d.flat_clr = (uint32_t)s[1] | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 16);
-            d.renew = !(c->dec_last_was_flat && !memcmp(c->dec_last_flat_clr, s + 1, 3));
-            c->dec_last_was_flat = true;
-            memcpy(c->dec_last_flat_clr, s + 1, 3);
+            d.renew = fresh_clip || !(last_was_flat && !memcmp(last_flat_clr, s + 1, 3));
+            last_was_flat = true;
+            memcpy(last_flat_clr, s + 1, 3);
             if (d.renew || chains.empty()) chains.push_back(DecChain{f, 0, d.renew ? -1 : -2});
         } else {
-            c->dec_last_was_flat = false;
+            last_was_flat = false;
             d.kind = DK_I;
             chains.push_back(DecChain{f, 0, -1});
         }
@@ -2212,7 +2273,9 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     }
     if (off >= 0xFFFF0000ull) return SCPR_E_PARAM;
     const int n_chains = (int)chains.size();
+    if (n_chains == 0) return 1;  // multi: every clip was refused
     TRY(ensure_dec_states(c, n_chains + 1));
+    int new_cur_state = c->dec_cur_state;
     {
         int next = 0;
         for (auto& ch : chains) {
@@ -2224,7 +2287,7 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
             }
         }
         // note: states of new chains must differ from the persistent one only while it is in use by chain 0
-        c->dec_cur_state = chains.back().state;
+        new_cur_state = chains.back().state;
     }
     // ---- device buffers ---------------------------------------------------------------------------
     TRY(c->dec_stream.ensure((size_t)off + 64));
@@ -2247,16 +2310,19 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     const size_t map_bytes = map_shared ? 0 : (size_t)n_chains * g.nb * 4;
     const size_t upd_bytes = ((size_t)n * g.nb + 15) & ~(size_t)15, fsrc_bytes = ((size_t)n * g.nb * 2 + 15) & ~(size_t)15;
     TRY(c->dec_ws.ensure(map_bytes + upd_bytes + fsrc_bytes + (size_t)n_chains * g.nb * 2 + 64));
-    if (c->dec_prev_pitch != pitch) {  // previous frame is kept in output format
-        TRY(c->dec_prev.ensure(g.frame_bytes));
-        if (c->dec_prev_pitch == 0) CK(cudaMemsetAsync(c->dec_prev.p, 0, g.frame_bytes, st));
-        else {
-            set_error("output pitch changed between calls");
-            return SCPR_E_PARAM;
-        }
+    if (c->dec_prev_pitch != pitch) {  // the previous frame is kept in output format: the reference takes the pitch per call (screencap.cpp:1705-1708)
+        DBuf nb;
+        TRY(nb.ensure(g.frame_bytes));
+        if (c->dec_prev_pitch == 0 || !c->dec_prev.p)
+            CK(cudaMemsetAsync(nb.p, 0, g.frame_bytes, st));
+        else  // same pixels, new row pitch
+            CK(cudaMemcpy2DAsync(nb.p, (size_t)pitch, c->dec_prev.p, (size_t)c->dec_prev_pitch, (size_t)g.X * g.bpp, (size_t)g.Y, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        c->dec_prev.release();
+        c->dec_prev = nb;
         c->dec_prev_pitch = pitch;
     }
-    CK(cudaMemcpyAsync(c->dec_stream.p, stream, (size_t)off, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->dec_stream.p, j.stream, (size_t)off, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync((uint8_t*)c->dec_stream.p + off, 0, 64, st));
     CK(cudaMemcpyAsync(c->dec_desc.p, frames.data(), (size_t)n * sizeof(DecFrame), cudaMemcpyHostToDevice, st));
     DecChain* d_chains = reinterpret_cast<DecChain*>((uint8_t*)c->dec_desc.p + (size_t)n * sizeof(DecFrame));
@@ -2269,8 +2335,8 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.frames = (const DecFrame*)c->dec_desc.p;
     w.chains = d_chains;
     w.states = (uint8_t*)c->dec_state.p;
-    w.f0 = c->dec_version == 3 ? 64 : 32;  // setCx6f0, screencap.cpp:1613-1614
-    w.out = d_out;
+    w.f0 = version == 3 ? 64 : 32;  // setCx6f0, screencap.cpp:1613-1614
+    w.out = j.d_out;
     w.prev0 = (const uint8_t*)c->dec_prev.p;
     uint8_t* ws = (uint8_t*)c->dec_ws.p;
     w.gmap = (uint32_t*)ws;
@@ -2282,7 +2348,14 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     w.msr_y = (int)c->p.high_range_y;
     w.irows = irows_off;
     w.progress = nullptr;
-    if (h_out && n >= 64) {  // worth overlapping: progress words in mapped host memory, a second stream for the tail work
+    const bool to_host = j.h_out || j.h_clip;
+    const size_t rowb = (size_t)g.X * g.bpp;
+    auto host_of = [&](int f) -> uint8_t* {  // where frame f goes on the host
+        if (j.h_out) return j.h_out + (size_t)f * g.frame_bytes;
+        const int k = clip_of[f];
+        return j.h_clip[k] ? j.h_clip[k] + (size_t)(f - clip_first[k]) * g.frame_bytes : nullptr;
+    };
+    if (to_host && n >= 64) {  // worth overlapping: progress words in mapped host memory, a second stream for the tail work
         if (!c->copy_st) CK(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
         if (c->dec_progress_cap < n_chains) {
             if (c->dec_progress) cudaFreeHost((void*)c->dec_progress);
@@ -2300,7 +2373,7 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     }
     CK(cudaMemsetAsync(w.upd, 0, (size_t)n * g.nb, st));
     StageTimer tm(st);
-    const bool v2 = c->dec_version == 2;
+    const bool v2 = version == 2;
 #define LAUNCH_CHAIN(SMV, V2V)                                                                                      \
     do {                                                                                                            \
         CK(cudaFuncSetAttribute(k_dec_chain<SMV, V2V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
@@ -2320,9 +2393,10 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
         const long strips = (long)(b - a) * g.nby * ((g.nbx + 7) >> 3);
         k_dec_fill<<<(unsigned)((strips + 7) / 8), 256, 0, s2>>>(r);
         c->launches += 2;
-        if (h_out)
-            cudaMemcpyAsync(h_out + (size_t)a * g.frame_bytes, d_out + (size_t)a * g.frame_bytes, (size_t)(b - a) * g.frame_bytes,
-                            cudaMemcpyDeviceToHost, s2);
+        if (to_host) {
+            uint8_t* h = host_of(a);
+            if (h) download_frames(h, j.d_out + (size_t)a * g.frame_bytes, g.frame_bytes, pitch, rowb, g.Y, a, b, s2);
+        }
     };
     if (w.progress) {
         // the chain kernel reports finished frames; finished ranges are completed and sent home while it keeps going
@@ -2359,9 +2433,20 @@ static int decode_range(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     tm.mark("sources+fill");
     tm.report("decode_batch");
     CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpyAsync(c->dec_prev.p, d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
+    if (!multi) CK(cudaMemcpyAsync(c->dec_prev.p, j.d_out + (size_t)(n - 1) * g.frame_bytes, g.frame_bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    // commit the decoder state: the frames have been decoded
+    if (multi) {  // a multi-clip call leaves no stream open
+        c->dec_created = false;
+        c->dec_last_was_flat = false;
+    } else {
+        c->dec_created = created;
+        c->dec_version = version;
+        c->dec_last_was_flat = last_was_flat;
+        memcpy(c->dec_last_flat_clr, last_flat_clr, 3);
+        c->dec_cur_state = new_cur_state;
+    }
     return 1;
 }
 
@@ -2375,7 +2460,8 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
         for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
             const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
             TRY(c->dec24.ensure((size_t)m * c->g.frame_bytes));
-            const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, (uint8_t*)c->dec24.p, c->g.pitch);
+            const DecJob j = {stream, sizes + f0, ftypes + f0, m, (uint8_t*)c->dec24.p, c->g.pitch, nullptr, nullptr, nullptr, nullptr};
+            const int r = decode_range(c, j);
             if (r != 1) return r;
             launch_pack16((const uint8_t*)c->dec24.p, d16 + (size_t)f0 * pitch * c->g.Y, m, c->g, pitch, c->m16, c->st, &c->launches);
             CK(cudaStreamSynchronize(c->st));
@@ -2386,12 +2472,58 @@ static int decode_batch(scpr_codec* c, const uint8_t* stream, const uint32_t* si
     const size_t frame_bytes = (size_t)pitch * c->g.Y;
     for (int f0 = 0; f0 < n; f0 += DEC_MAX_FRAMES) {
         const int m = n - f0 < DEC_MAX_FRAMES ? n - f0 : DEC_MAX_FRAMES;
-        const int r = decode_range(c, stream, sizes + f0, ftypes + f0, m, d_out + (size_t)f0 * frame_bytes, pitch,
-                                   h_out ? h_out + (size_t)f0 * frame_bytes : nullptr);
+        const DecJob j = {stream, sizes + f0, ftypes + f0, m, d_out + (size_t)f0 * frame_bytes, pitch, nullptr, nullptr,
+                          h_out ? h_out + (size_t)f0 * frame_bytes : nullptr, nullptr};
+        const int r = decode_range(c, j);
         if (r != 1) return r;
         for (int f = f0; f < f0 + m; f++) stream += sizes[f];
     }
     return 1;
+}
+
+// Independent clips, all their GOP chains in one launch per DEC_MAX_FRAMES frames.  d_base: device frames of all clips back to
+// back; h_out[k]: host destination of clip k or nullptr.
+static int decode_clips(scpr_codec* c, scpr_clip* clips, int n_clips, uint8_t* d_base, int pitch, bool to_host) {
+    const size_t frame_bytes = (size_t)pitch * c->g.Y;
+    int all_ok = 1;
+    for (int k0 = 0; k0 < n_clips;) {
+        // a group of clips of at most DEC_MAX_FRAMES frames
+        int k1 = k0;
+        long nf = 0;
+        while (k1 < n_clips && (k1 == k0 || nf + clips[k1].n <= DEC_MAX_FRAMES)) nf += clips[k1++].n;
+        size_t first_frame = 0;
+        for (int k = 0; k < k0; k++) first_frame += (size_t)clips[k].n;
+        if (k1 == k0 + 1 && clips[k0].n > DEC_MAX_FRAMES) {  // one very long clip: as a single stream, in several launches
+            scpr_clip& q = clips[k0];
+            c->dec_created = false;
+            c->dec_last_was_flat = false;
+            q.result = decode_batch(c, q.stream, q.sizes, q.ftypes, q.n, d_base + first_frame * frame_bytes, pitch, to_host ? q.frames : nullptr);
+            c->dec_created = false;
+        } else {
+            std::vector<uint8_t> stream, ftypes, starts;
+            std::vector<uint32_t> sizes;
+            std::vector<uint8_t*> hdst;
+            std::vector<int> results(k1 - k0, 1);
+            for (int k = k0; k < k1; k++) {
+                const scpr_clip& q = clips[k];
+                size_t bytes = 0;
+                for (int f = 0; f < q.n; f++) bytes += q.sizes[f];
+                stream.insert(stream.end(), q.stream, q.stream + bytes);
+                sizes.insert(sizes.end(), q.sizes, q.sizes + q.n);
+                ftypes.insert(ftypes.end(), q.ftypes, q.ftypes + q.n);
+                for (int f = 0; f < q.n; f++) starts.push_back(f == 0);
+                hdst.push_back(to_host ? q.frames : nullptr);
+            }
+            const DecJob j = {stream.data(), sizes.data(), ftypes.data(), (int)nf, d_base + first_frame * frame_bytes, pitch, starts.data(),
+                              to_host ? hdst.data() : nullptr, nullptr, results.data()};
+            const int r = nf ? decode_range(c, j) : 1;
+            for (int k = k0; k < k1; k++) clips[k].result = r == 1 ? results[k - k0] : r;
+        }
+        for (int k = k0; k < k1; k++)
+            if (clips[k].result != 1 && all_ok == 1) all_ok = clips[k].result;
+        k0 = k1;
+    }
+    return all_ok;
 }
 
 extern "C" {
@@ -2409,14 +2541,13 @@ int scpr_decompress_clip(scpr_codec* c, const uint8_t* stream, const uint32_t* s
     CK(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n * pitch * c->g.Y;
     TRY(c->dec_frames.ensure(bytes));
-    // row padding of the caller's buffer is not produced by the kernels: start from zeros
-    if (pitch != c->g.X * (c->rgb16 ? 2 : c->g.bpp)) CK(cudaMemsetAsync(c->dec_frames.p, 0, bytes, c->st));
-    // the download is part of decode_batch: finished frame ranges travel while the chains are still decoding
+    // the download is part of decode_batch: finished frame ranges travel while the chains are still decoding; only the
+    // pixel bytes of every row travel, the caller's row padding stays as it is
     const bool direct = !c->rgb16;
     const int r = decode_batch(c, stream, sizes, ftypes, n, (uint8_t*)c->dec_frames.p, pitch, direct ? frames : nullptr);
     if (r != 1) return r;
     if (!direct) {
-        CK(cudaMemcpyAsync(frames, c->dec_frames.p, bytes, cudaMemcpyDeviceToHost, c->st));
+        CK(download_frames(frames, (const uint8_t*)c->dec_frames.p, (size_t)pitch * c->g.Y, pitch, row_bytes(c), c->g.Y, 0, n, c->st));
         CK(cudaStreamSynchronize(c->st));
     }
     return 1;
@@ -2427,6 +2558,33 @@ int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_
     const uint32_t size = (uint32_t)src_len;
     const uint8_t ft = ftype ? 1 : 0;
     return scpr_decompress_clip(c, src, &size, &ft, 1, dst, pitch);
+}
+
+static int check_clips(const scpr_codec* c, const scpr_clip* clips, int n_clips, bool need_frames) {
+    if (!c || !clips || n_clips < 0) return SCPR_E_PARAM;
+    if (c->rgb16) {
+        set_error("multi-clip decoding of 16 bpp clients is not built");
+        return SCPR_E_UNSUPPORTED;
+    }
+    for (int k = 0; k < n_clips; k++)
+        if (clips[k].n < 0 || (clips[k].n && (!clips[k].stream || !clips[k].sizes || !clips[k].ftypes || (need_frames && !clips[k].frames)))) return SCPR_E_PARAM;
+    return SCPR_OK;
+}
+
+int scpr_decompress_clips_dev(scpr_codec* c, scpr_clip* clips, int n_clips, uint8_t* d_frames, int pitch) {
+    TRY(check_clips(c, clips, n_clips, false));
+    if (!d_frames) return SCPR_E_PARAM;
+    return decode_clips(c, clips, n_clips, d_frames, pitch, false);
+}
+
+int scpr_decompress_clips(scpr_codec* c, scpr_clip* clips, int n_clips, int pitch) {
+    TRY(check_clips(c, clips, n_clips, true));
+    CK(cudaSetDevice(c->device));
+    size_t nf = 0;
+    for (int k = 0; k < n_clips; k++) nf += (size_t)clips[k].n;
+    if (nf == 0) return 1;
+    TRY(c->dec_frames.ensure(nf * pitch * c->g.Y));
+    return decode_clips(c, clips, n_clips, (uint8_t*)c->dec_frames.p, pitch, true);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ from typing import Iterator, List
 
 import numpy as np
 
-__all__ = ["ClipConfig", "CONFIGS", "clip_frames", "keyframe_flags", "make_clip"]
+__all__ = ["ClipConfig", "CONFIGS", "clip_frames", "keyframe_flags", "make_clip", "make_clip_range"]
 
 
 def _hash32(x: np.ndarray | int) -> np.ndarray:
@@ -341,4 +341,17 @@ def make_clip(cfg: ClipConfig, n: int | None = None) -> np.ndarray:
     out[0] = first
     for i, fr in enumerate(it, start=1):
         out[i] = fr
+    return out
+
+
+def make_clip_range(cfg: ClipConfig, first: int, count: int) -> np.ndarray:
+    """Frames [first, first + count) of the clip (the generator is sequential: earlier frames are produced and dropped).
+    What one rank of a frame-range split holds."""
+    out = None
+    for i, fr in enumerate(clip_frames(cfg, first + count)):
+        if i < first:
+            continue
+        if out is None:
+            out = np.empty((count,) + fr.shape, dtype=np.uint8)
+        out[i - first] = fr
     return out

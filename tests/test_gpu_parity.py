@@ -364,6 +364,107 @@ def test_failed_call_leaves_a_decodable_stream(scpr):
     assert np.array_equal(out.reshape(8, -1), np.concatenate([clip[:4], clip[8:]]).reshape(8, -1))
 
 
+def test_many_clips_in_one_call(scpr):
+    """scpr_decompress_clips: every GOP of every clip is one thread block of one launch; each clip decodes as by a fresh
+    codec, a clip that starts with a P frame is refused without touching the others, host and device destinations agree"""
+    import torch
+
+    w, h = 160, 96
+    specs = [(20, 3, [0, 7]), (9, 4, [0]), (31, 5, [0, 10, 20, 30]), (12, 6, [0, 5])]
+    clips, want = [], []
+    for n, seed, kf in specs:
+        clip = motion_clip(w, h, n, seed)
+        keys = np.zeros(n, np.uint8)
+        keys[kf] = 1
+        stream, sizes, fts = _new(scpr, w, h, 32).CompressClip(clip, keys)
+        clips.append((stream.copy(), sizes.copy(), fts.copy()))
+        want.append(clip.reshape(n, -1))
+    # a fifth "clip" that starts on a P frame: the tail of clip 0
+    s0, z0, f0 = clips[0]
+    cut = int(z0[:3].sum())
+    clips.insert(2, (s0[cut:], z0[3:], f0[3:]))
+    want.insert(2, None)
+    dec = _new(scpr, w, h, 32)
+    results, frames = dec.DecompressClips(clips)
+    assert results == [1, 1, 0, 1, 1]
+    for k, wnt in enumerate(want):
+        if wnt is not None:
+            assert np.array_equal(frames[k], wnt), k
+    # device destination: clips back to back
+    total = sum(int(c[1].size) for c in clips)
+    d_out = torch.zeros(total * w * h * 4, dtype=torch.uint8, device="cuda")
+    results, _ = dec.DecompressClips(clips, device_ptr=d_out.data_ptr())
+    assert results == [1, 1, 0, 1, 1]
+    got = d_out.cpu().numpy().reshape(total, -1)
+    pos = 0
+    for k, wnt in enumerate(want):
+        n = int(clips[k][1].size)
+        if wnt is not None:
+            assert np.array_equal(got[pos:pos + n], wnt), k
+        pos += n
+    # the codec is usable as a single-stream decoder afterwards (its state was reset, not corrupted)
+    out = dec.DecompressClip(*clips[1])
+    assert np.array_equal(out, want[1])
+    # a bad stream version in one clip
+    bad = clips[1][0].copy()
+    bad[0] = 0x72  # version 8
+    results, frames = dec.DecompressClips([clips[0], (bad, clips[1][1], clips[1][2]), clips[3]])
+    assert results == [1, -8, 1] and np.array_equal(frames[0], want[0]) and np.array_equal(frames[2], want[3])
+
+
+def test_pitch_per_call_and_untouched_row_padding(scpr):
+    """the reference takes the output pitch per call and writes width * bytes-per-pixel bytes per row (screencap.cpp:1705-1738):
+    the pitch may change between calls of one stream, and the caller's row padding is never written"""
+    w, h, n = 150, 64, 10
+    clip = motion_clip(w, h, n, 11)
+    keys = np.zeros(n, np.uint8)
+    keys[0] = 1
+    stream, sizes, fts = _new(scpr, w, h, 32).CompressClip(clip, keys)
+    frames = _split(stream, sizes, fts)
+    dec = _new(scpr, w, h, 32)
+    for i, (data, ft) in enumerate(frames):
+        pitch = w * 4 + (0, 16, 64)[i % 3]
+        out = np.full(h * pitch, 0xA5, np.uint8)
+        src = np.frombuffer(data, np.uint8)
+        r = dec._lib.scpr_decompress_frame(dec._h, src.ctypes.data, len(data), out.ctypes.data, pitch, ft)
+        assert r == 1, (i, r)
+        rows = out.reshape(h, pitch)
+        assert np.array_equal(rows[:, :w * 4], clip[i].reshape(h, w * 4)), i
+        assert (rows[:, w * 4:] == 0xA5).all(), f"frame {i}: row padding was written"
+    # clip call with a padded pitch
+    dec2 = _new(scpr, w, h, 32)
+    pitch = w * 4 + 32
+    out = dec2.DecompressClip(stream, sizes, fts, pitch=pitch).reshape(n, h, pitch)
+    assert np.array_equal(out[:, :, :w * 4], clip.reshape(n, h, w * 4))
+
+
+def test_rejected_decode_call_leaves_the_decoder_state_alone(scpr):
+    """a call that is refused while it is being planned (here: a truncated flat frame in the middle of a batch) must
+    not change what the next valid call does"""
+    w, h = 64, 48
+    frames = np.zeros((6, h, w, 4), np.uint8)
+    frames[..., 3] = 255
+    frames[0, ..., :3] = (10, 20, 30)
+    frames[0, 3, 4, 0] = 9
+    frames[1] = frames[0]; frames[1, 8:12, 8:20, :3] = 77
+    frames[2, ..., :3] = (1, 2, 3)     # flat
+    frames[3, ..., :3] = (1, 2, 3)     # same flat colour: no renewal
+    frames[4] = frames[1]
+    frames[5] = frames[4]; frames[5, 20:24, 8:20, :3] = 99
+    keys = np.array([1, 0, 0, 0, 0, 0], np.uint8)
+    coded = _split(*_new(scpr, w, h, 32).CompressClip(frames, keys))
+    dec = _new(scpr, w, h, 32)
+    for i in range(3):
+        assert np.array_equal(dec.DecompressFrame(coded[i][0], None, coded[i][1]), frames[i].reshape(-1))
+    # a batch of a flat frame of ANOTHER colour followed by a truncated flat frame: refused as a whole.  Had the first of them
+    # been remembered as "the last flat colour", the next flat frame would renew the models and the P frames after it break.
+    bad_stream = np.frombuffer(bytes([0x31, 5, 5, 5]) + bytes([0x31, 9]), np.uint8)
+    with pytest.raises(scpr.ScprError):
+        dec.DecompressClip(bad_stream, np.array([4, 2], np.uint32), np.array([0, 0], np.uint8))
+    for i in range(3, 6):
+        assert np.array_equal(dec.DecompressFrame(coded[i][0], None, coded[i][1]), frames[i].reshape(-1)), i
+
+
 def test_full_state_checkpoint_resume_at_any_frame(scpr):
     """full = 1: previous frame + adaptive models + mvs[]; an encode resumed in another codec object continues byte-exactly"""
     w, h, n = 200, 120, 30

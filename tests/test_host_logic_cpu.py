@@ -49,13 +49,18 @@ def test_cfg5_contains_duplicate_frames_and_cfg2_scrolls():
 
 def test_bench_reference_arm_prints_contract_line(oracle_built):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-frames", "4"], capture_output=True, text=True, timeout=600)
+                          "--frames", "4"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
     assert line["metric"] == "1080p_rgb32_encode_decode_frames_per_s"
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert line["config"] == bench.workload_config(4)   # the dict the CUDA arm prints: the driver compares the two
+    assert "all 4 frames" in line["cpu_baseline"]["sample"] and line["scaling"] == "weak"
 
 
 def _rank_main(rank, world, port, q):
@@ -64,20 +69,28 @@ def _rank_main(rank, world, port, q):
 
     sys.path.insert(0, ROOT)
     import bench
+    from screenpressor_b200 import shard, synth
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cfg, clip, keys = bench.make_workload(rank, 2)
-    # each rank owns its own clip (weak scaling, no data-path collective); timing = max over ranks
+    # N > 1: ONE clip cut by GOP-aligned frame ranges (strong scaling); every rank generates its own range only
+    cfg = synth.CONFIGS["cfg1_720p_rgb24"]
+    frames, interval = 16, 2
+    keys = synth.keyframe_flags(frames, interval)
+    ranges = shard.assign_ranges(keys, world)
+    mine = next(r for r in ranges if r.rank == rank)
+    part = synth.make_clip_range(cfg, mine.first, mine.count)
     t = torch.tensor([10.0 + rank])
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    q.put((rank, cfg.seed, int(clip[1].astype(np.uint64).sum() % 1000003), float(t.item()), int(keys.sum())))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)     # timing = max over ranks
+    q.put((rank, mine.first, mine.count, int(part.astype(np.uint64).sum() % 1000003), float(t.item()), bench.split_config(1200, 150, world)["gops_per_clip"]))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_two_rank_sharding_and_max_reduction_gloo():
     import torch.multiprocessing as mp
+
+    from screenpressor_b200 import synth
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -89,10 +102,12 @@ def test_two_rank_sharding_and_max_reduction_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, seed0, sum0, t0, k0), (r1, seed1, sum1, t1, k1) = res
-    assert seed0 != seed1 and sum0 != sum1          # different clips per rank
+    (r0, f0, c0, sum0, t0, g0), (r1, f1, c1, sum1, t1, g1) = res
+    assert (f0, c0, f1, c1) == (0, 8, 8, 8)          # the two ranges partition the clip at a keyframe
+    whole = synth.make_clip(synth.CONFIGS["cfg1_720p_rgb24"], 16)
+    assert sum0 == int(whole[:8].astype(np.uint64).sum() % 1000003) and sum1 == int(whole[8:].astype(np.uint64).sum() % 1000003)
     assert t0 == t1 == 11.0                         # MAX over ranks
-    assert k0 == k1 == 1
+    assert g0 == g1 == 8
 
 
 def test_reference_arm_other_ranks_exit_silently():
