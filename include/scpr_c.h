@@ -131,6 +131,18 @@ size_t scpr_range_state_size(const scpr_codec* c, int full);
 int64_t scpr_export_range_state(scpr_codec* c, uint8_t* blob, size_t cap, int full);   /* bytes written or < 0 */
 int scpr_import_range_state(scpr_codec* c, const uint8_t* blob, size_t len);
 
+/* One clip cut across the GPUs of a box from ONE host process (csrc/multi.cu): GOP-aligned contiguous frame ranges, one per entry of
+ * `devices` (an ordinal may repeat; fewer ranges when the clip has fewer GOPs), a codec object and a host thread per range, the
+ * bitstreams concatenated on the host in frame order.  mvs[] travels device to device (cudaMemcpyPeerAsync) between the in-order
+ * resolves of neighbouring ranges; a range never starts at a requested keyframe that is a single-colour frame (the reference does
+ * not start a GOP there).  The result is byte-identical to scpr_compress_clip on one codec.  frames: host memory.
+ * range_first / n_ranges (optional): the plan that was used. */
+int64_t scpr_compress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* frames, int n, const uint8_t* keyflags,
+                                 uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes, int* range_first, int* n_ranges);
+/* The decoding counterpart: ranges start at coded I frames, no hand-off.  frames: host memory, row pitch `pitch`. */
+int scpr_decompress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* stream, const uint32_t* sizes,
+                               const uint8_t* ftypes, int n, uint8_t* frames, int pitch);
+
 /* ---- host layer above the codec object: VfW policy and the AVI container (csrc/vfw_host.cpp) -------------------
  * What CodecInst does around ScreenCodec (screenpressor.cpp:343-437, 579-620), for hosts that are not VfW. */
 typedef struct scpr_policy {

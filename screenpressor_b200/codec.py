@@ -78,6 +78,10 @@ class CodecParameters:
     low_range_y: int = 8
     loss: int = 0
 
+    def _c(self) -> "_Params":
+        return _Params(self.width, self.height, self.bits_per_pixel, self.redmask, self.greenmask, self.bluemask, self.high_range_x,
+                       self.high_range_y, self.low_range_x, self.low_range_y, self.loss)
+
 
 _lib = None
 
@@ -113,6 +117,10 @@ def load_library() -> C.CDLL:
     lib.scpr_decompress_clips.argtypes = [vp, C.POINTER(_Clip), i32, i32]
     lib.scpr_decompress_clips_dev.restype = i32
     lib.scpr_decompress_clips_dev.argtypes = [vp, C.POINTER(_Clip), i32, vp, i32]
+    lib.scpr_compress_clip_multi.restype = C.c_int64
+    lib.scpr_compress_clip_multi.argtypes = [C.POINTER(_Params), vp, i32, vp, i32, vp, vp, C.c_size_t, vp, vp, vp, vp]
+    lib.scpr_decompress_clip_multi.restype = i32
+    lib.scpr_decompress_clip_multi.argtypes = [C.POINTER(_Params), vp, i32, vp, vp, vp, i32, vp, i32]
     lib.scpr_reset.argtypes = [vp]
     lib.scpr_set_stream.restype = i32
     lib.scpr_set_stream.argtypes = [vp, vp]
@@ -424,6 +432,43 @@ class CodecInst:
         if r != 1:
             raise ScprError(r, self._lib.scpr_last_error().decode() if r < 0 else "P frame before any I frame")
         return out
+
+
+def compress_clip_multi(params: "CodecParameters", devices, frames: np.ndarray, keyflags: np.ndarray):
+    """One clip cut by GOP-aligned frame ranges across `devices` (CUDA ordinals, one range each) from this process
+    (scpr_compress_clip_multi).  -> (stream, sizes, ftypes, [first frame of every range])"""
+    lib = load_library()
+    p = params._c()
+    frames = np.ascontiguousarray(frames)
+    keyflags = np.ascontiguousarray(keyflags, dtype=np.uint8)
+    n = int(keyflags.size)
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    cap = min(n * params.width * params.height * 6, 1 << 31)
+    dst = np.empty(cap, dtype=np.uint8)
+    sizes, ftypes = np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+    first, nr = np.zeros(len(dev), np.int32), C.c_int(0)
+    r = lib.scpr_compress_clip_multi(C.byref(p), _ptr(dev), len(dev), _ptr(frames), n, _ptr(keyflags), _ptr(dst), cap, _ptr(sizes), _ptr(ftypes),
+                                     _ptr(first), C.addressof(nr))
+    if r < 0:
+        raise ScprError(int(r), lib.scpr_last_error().decode())
+    return dst[:r].copy(), sizes, ftypes, [int(x) for x in first[:nr.value]]
+
+
+def decompress_clip_multi(params: "CodecParameters", devices, stream, sizes, ftypes, pitch: int | None = None) -> np.ndarray:
+    """The decoding counterpart (scpr_decompress_clip_multi): ranges start at coded I frames.  -> ndarray (n, height*pitch)"""
+    lib = load_library()
+    p = params._c()
+    bpp = params.bits_per_pixel // 8
+    pitch = pitch or (((params.width * 3 + 3) & ~3) if bpp == 3 else params.width * bpp)
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+    ftypes = np.ascontiguousarray(ftypes, dtype=np.uint8)
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    out = np.zeros((int(sizes.size), params.height * pitch), dtype=np.uint8)
+    r = lib.scpr_decompress_clip_multi(C.byref(p), _ptr(dev), len(dev), _ptr(stream), _ptr(sizes), _ptr(ftypes), int(sizes.size), _ptr(out), pitch)
+    if r != 1:
+        raise ScprError(int(r), lib.scpr_last_error().decode())
+    return out
 
 
 class AviWriter:

@@ -153,3 +153,18 @@ def test_avi_container_round_trip(tmp_path):
         assert got == chunks[:1] + chunks[2:]
     with pytest.raises(codec.ScprError):
         codec.AviReader(str(tmp_path / "missing.avi"))
+
+
+def test_cpp_facade_compiles_and_fails_loudly_without_gpu(lib):
+    """include/screencodec_b200.h (the reference's ScreenCodec class over the C ABI) driven by a CodecInst-shaped C++ caller
+    (tests/cpp/vfw_caller.cpp, call sites of screenpressor.cpp:381, 425, 620-636): compiles with g++ -Wall -Werror and links the
+    library; without a device Init() marks the object crashed and CompressFrame returns 0 -- no CPU path."""
+    import torch
+
+    import _cppharness
+
+    exe = _cppharness.build()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([exe, "--nodevice"], capture_output=True, text=True)
+    assert r.returncode == 0 and "status -1004 size 0" in r.stdout, (r.stdout, r.stderr)

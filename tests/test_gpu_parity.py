@@ -465,6 +465,64 @@ def test_rejected_decode_call_leaves_the_decoder_state_alone(scpr):
         assert np.array_equal(dec.DecompressFrame(coded[i][0], None, coded[i][1]), frames[i].reshape(-1)), i
 
 
+def test_multi_device_entry_is_byte_identical(scpr):
+    """scpr_compress_clip_multi / scpr_decompress_clip_multi: the frame-range split driven from one host process, one codec
+    object and host thread per range, mvs[] relayed device to device around the resolves (here all ranges on device 0: the
+    relay logic is the same, cudaMemcpyPeerAsync within one device).  Byte-identical to one codec; a flat keyframe is not a cut."""
+    w, h, n = 320, 192, 60
+    clip = motion_clip(w, h, n, 5)
+    clip[30, ..., :3] = (9, 8, 7)          # a flat frame exactly where a keyframe is requested
+    keys = np.zeros(n, np.uint8)
+    keys[[0, 13, 30, 41, 52]] = 1
+    params = scpr.CodecParameters(w, h, 32)
+    whole = _new(scpr, w, h, 32).CompressClip(clip, keys)
+    want = (whole[0].copy(), whole[1].copy(), whole[2].copy())
+    for devs in ([0], [0, 0], [0, 0, 0], [0] * 8):
+        stream, sizes, fts, firsts = scpr.compress_clip_multi(params, devs, clip, keys)
+        assert np.array_equal(stream, want[0]) and np.array_equal(sizes, want[1]) and np.array_equal(fts, want[2]), devs
+        assert 30 not in firsts and all(keys[f] for f in firsts) and len(firsts) == min(len(devs), 4), (devs, firsts)
+        out = scpr.decompress_clip_multi(params, devs, stream, sizes, fts)
+        assert np.array_equal(out.reshape(n, -1), clip.reshape(n, -1)), devs
+
+
+def test_cpp_facade_driven_like_the_vfw_layer(scpr, oracle_built, tmp_path):
+    """include/screencodec_b200.h through a compiled C++ caller shaped like CodecInst (tests/cpp/vfw_caller.cpp: CompressBegin /
+    Compress with the forced keyframe interval and quality -> loss / Decompress with InferFrameType and the BadVersionException
+    handler, screenpressor.cpp:343-437, 579-640) -- no ctypes on this path.  Bytes, key flags and decoded frames must equal what the
+    unmodified reference produces under the same driving."""
+    import subprocess
+
+    import _cppharness
+
+    exe = _cppharness.build()
+    for (w, h, bpp, n, kf, quality) in [(322, 200, 32, 40, 12, 10000), (161, 90, 24, 30, 500, 10000), (256, 128, 32, 20, 7, 5000)]:
+        clip, _ = fuzz_clip(w, h, n, 77 + w, bpp=bpp, levels=16)
+        raw = tmp_path / "frames.raw"
+        clip.tofile(raw)
+        outs = [tmp_path / x for x in ("out.stream", "out.index", "out.decoded")]
+        r = subprocess.run([exe, str(w), str(h), str(bpp), str(n), str(kf), str(quality), str(raw)] + [str(o) for o in outs], capture_output=True, text=True)
+        assert r.returncode == 0, (r.stdout, r.stderr)
+        assert "bogus stream: result -2 version 10" in r.stdout, r.stdout
+        index = np.fromfile(outs[1], dtype=np.uint32).reshape(n, 2)
+        stream = np.fromfile(outs[0], dtype=np.uint8)
+        decoded = np.fromfile(outs[2], dtype=np.uint8).reshape(n, -1)
+        # the reference under the same policy: npframes + 1 >= interval forces a keyframe, loss from the quality
+        loss = min((10000 - quality) // 2000, 4)
+        ref = oracle_built.RefCodec(w, h, bpp, loss=loss) if oracle_built.have_ref() else oracle_built.OracleCodec(w, h, bpp, loss=loss)
+        refdec = oracle_built.RefCodec(w, h, bpp) if oracle_built.have_ref() else oracle_built.OracleCodec(w, h, bpp)
+        npf, pos = 0, 0
+        for i in range(n):
+            want_p = not (npf + 1 >= kf)
+            data, ft = ref.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), want_p, loss)
+            npf = 0 if ft == 0 else npf + 1
+            sz = int(index[i, 0])
+            assert bytes(stream[pos:pos + sz]) == data, (w, h, bpp, i)
+            assert (int(index[i, 1]) == 0x10) == (ft == 0), (w, h, bpp, i)
+            assert np.array_equal(decoded[i], refdec.decompress(data, ft)), (w, h, bpp, i)
+            pos += sz
+        assert pos == stream.size
+
+
 def test_full_state_checkpoint_resume_at_any_frame(scpr):
     """full = 1: previous frame + adaptive models + mvs[]; an encode resumed in another codec object continues byte-exactly"""
     w, h, n = 200, 120, 30
