@@ -202,6 +202,12 @@ int scpr_debug_blocks(scpr_codec* c, int frame, uint8_t* bts, int32_t* sxy4, int
  * device-resident frames `reps` times; returns the mean kernel time in milliseconds measured with
  * CUDA events on the codec's stream (bench.py's roofline leg), or < 0. */
 float scpr_bench_frame_scan(scpr_codec* c, const uint8_t* d_frames, int n, int reps);
+/* The same with the kernel chosen by the caller: mode 0 = what the encoder uses (the TMA tile stream, csrc/frame_scan_tma.cu, for
+ * 32 bpp frames at least 128 x 16 pixels), 1 = the plain-load kernels (csrc/frame_scan.cu), 2 = TMA or SCPR_E_UNSUPPORTED.
+ * d_prev: device frame that precedes frame 0 (NULL = the codec's own previous frame).  When blkinfo / summary are not NULL the
+ * outputs of the last run are copied to the host: n * nb block words (bit 0 changed, bit 1 partial, 4 x 4 bits sub-rect) and
+ * n x {notflat, changed, pixel0, pad} u32 -- the tests compare the kernels with each other on ragged geometries. */
+float scpr_debug_frame_scan(scpr_codec* c, int mode, const uint8_t* d_frames, const uint8_t* d_prev, int n, int reps, uint32_t* blkinfo, uint32_t* summary);
 
 #ifdef __cplusplus
 }

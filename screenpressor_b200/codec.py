@@ -165,6 +165,8 @@ def load_library() -> C.CDLL:
     lib.scpr_avi_read_frame.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(i32)]
     lib.scpr_avi_close.restype = i32
     lib.scpr_avi_close.argtypes = [vp]
+    lib.scpr_debug_frame_scan.restype = C.c_float
+    lib.scpr_debug_frame_scan.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
     lib.scpr_bench_frame_scan.restype = C.c_float
     lib.scpr_bench_frame_scan.argtypes = [vp, vp, i32, i32]
     _lib = lib
@@ -367,6 +369,17 @@ class ScreenCodec:
         if ms < 0:
             raise ScprError(int(ms), self._lib.scpr_last_error().decode())
         return ms
+
+    def debug_frame_scan(self, mode: int, device_ptr: int, prev_ptr: int, n: int, reps: int = 1, fetch: bool = True):
+        """scpr_debug_frame_scan: one chosen frame-scan kernel over device frames -> (ms, blkinfo (n, nb) u32, summary (n, 4) u32)"""
+        nb = ((self.params.width + 15) // 16) * ((self.params.height + 15) // 16)
+        bi = np.zeros((n, nb), dtype=np.uint32) if fetch else None
+        sm = np.zeros((n, 4), dtype=np.uint32) if fetch else None
+        ms = float(self._lib.scpr_debug_frame_scan(self._h, mode, device_ptr, prev_ptr or None, n, reps, _ptr(bi) if fetch else None,
+                                                   _ptr(sm) if fetch else None))
+        if ms < 0:
+            raise ScprError(int(ms), self._lib.scpr_last_error().decode())
+        return ms, bi, sm
 
     def _check(self, r: int) -> int:
         if r < 0:

@@ -815,29 +815,39 @@ int scpr_debug_blocks(scpr_codec* c, int frame, uint8_t* bts, int32_t* sxy4, int
     return h.n_changed;
 }
 
-float scpr_bench_frame_scan(scpr_codec* c, const uint8_t* d_frames, int n, int reps) {
-    if (!c || !d_frames || n <= 0 || reps <= 0) return (float)SCPR_E_PARAM;
+float scpr_debug_frame_scan(scpr_codec* c, int mode, const uint8_t* d_frames, const uint8_t* d_prev, int n, int reps, uint32_t* blkinfo, uint32_t* summary) {
+    if (!c || !d_frames || n <= 0 || reps <= 0 || mode < 0 || mode > 2) return (float)SCPR_E_PARAM;
     const Geo& g = c->g;
     if (cudaSetDevice(c->device) != cudaSuccess) return (float)SCPR_E_CUDA;
     if (c->blkinfo.ensure((size_t)n * g.nb * 4) < 0 || c->summary.ensure((size_t)n * sizeof(FrameSummary)) < 0)
         return (float)SCPR_E_CUDA;
+    const uint8_t* prev = d_prev ? d_prev : (const uint8_t*)c->prev.p;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, c->st,
-                      &c->launches);
+    bool ok = launch_frame_scan_mode(mode, d_frames, prev, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, c->st, &c->launches);  // warm-up
+    cudaMemsetAsync(c->summary.p, 0, (size_t)n * sizeof(FrameSummary), c->st);
     cudaEventRecord(e0, c->st);
-    for (int r = 0; r < reps; r++)
-        launch_frame_scan(d_frames, (const uint8_t*)c->prev.p, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p,
-                          c->st, &c->launches);
+    for (int r = 0; ok && r < reps; r++)
+        ok = launch_frame_scan_mode(mode, d_frames, prev, n, g, (uint32_t*)c->blkinfo.p, (FrameSummary*)c->summary.p, c->st, &c->launches);
     cudaEventRecord(e1, c->st);
     cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (!ok) {
+        set_error("the TMA frame scan cannot take this geometry");
+        return (float)SCPR_E_UNSUPPORTED;
+    }
     if (cudaGetLastError() != cudaSuccess) return (float)SCPR_E_CUDA;
+    if (blkinfo && cudaMemcpy(blkinfo, c->blkinfo.p, (size_t)n * g.nb * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return (float)SCPR_E_CUDA;
+    if (summary && cudaMemcpy(summary, c->summary.p, (size_t)n * sizeof(FrameSummary), cudaMemcpyDeviceToHost) != cudaSuccess) return (float)SCPR_E_CUDA;
     return ms / reps;
+}
+
+float scpr_bench_frame_scan(scpr_codec* c, const uint8_t* d_frames, int n, int reps) {
+    return scpr_debug_frame_scan(c, 0, d_frames, nullptr, n, reps, nullptr, nullptr);
 }
 
 }  // extern "C"

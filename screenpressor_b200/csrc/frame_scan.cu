@@ -13,6 +13,9 @@
 // streams 4 pixels (one 128-bit load) of 16 rows from both frames, 16 loads in flight per half
 // strip; the 4 lanes of a block merge their row/column difference masks with shuffles, so an
 // unchanged block costs no further work anywhere in the pipeline (its blkinfo word is 0).
+#include <stdlib.h>
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace scpr {
@@ -234,13 +237,20 @@ void launch_apply_loss(uint8_t* frames, int n, const Geo& g, const FrameSummary*
     ++*launches;
 }
 
-void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
-                       FrameSummary* summary, cudaStream_t st, uint64_t* launches) {
+// mode: 0 = pick (TMA tile stream when the geometry allows, unless SCPR_FRAME_SCAN=ld), 1 = plain-load kernels, 2 = TMA or fail.
+bool launch_frame_scan_mode(int mode, const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
+                            FrameSummary* summary, cudaStream_t st, uint64_t* launches) {
     if (g.bpp == 4 && (g.X & 3) == 0) {
+        static const bool force_ld = []() { const char* e = getenv("SCPR_FRAME_SCAN"); return e && !strcmp(e, "ld"); }();
+        if (mode == 2 || (mode == 0 && !force_ld)) {
+            if (frame_scan_tma_usable(frames, prev0, g) && launch_frame_scan_tma(frames, prev0, n, g, blkinfo, summary, st, launches)) return true;
+            if (mode == 2) return false;
+        }
         const long strips = (long)n * g.nby * ((g.nbx + 7) >> 3);
         k_frame_scan32<<<(unsigned)((strips + 7) / 8), 256, 0, st>>>(frames, prev0, n, g, blkinfo, summary);
         ++*launches;
     } else {
+        if (mode == 2) return false;
         const long blocks = (long)n * g.nb;
         k_frame_scan_generic<<<(unsigned)((blocks + 7) / 8), 256, 0, st>>>(frames, prev0, n, g, blkinfo, summary);
         ++*launches;
@@ -250,6 +260,11 @@ void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const
             ++*launches;
         }
     }
+    return true;
+}
+void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
+                       FrameSummary* summary, cudaStream_t st, uint64_t* launches) {
+    launch_frame_scan_mode(0, frames, prev0, n, g, blkinfo, summary, st, launches);
 }
 
 // ---- 16 bpp input / output (ScreenCodec::CompressFrame, screencap.cpp:1665-1678; DecompressFrame, :1726-1734) --------

@@ -65,6 +65,11 @@ struct RansBlk {
 // ---- stage A --------------------------------------------------------------------------------
 void launch_frame_scan(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
                        FrameSummary* summary, cudaStream_t st, uint64_t* launches);
+bool launch_frame_scan_mode(int mode, const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo,
+                            FrameSummary* summary, cudaStream_t st, uint64_t* launches);
+bool frame_scan_tma_usable(const uint8_t* frames, const uint8_t* prev0, const Geo& g);
+bool launch_frame_scan_tma(const uint8_t* frames, const uint8_t* prev0, int n, const Geo& g, uint32_t* blkinfo, FrameSummary* summary,
+                           cudaStream_t st, uint64_t* launches);
 void launch_apply_loss(uint8_t* frames, int n, const Geo& g, const FrameSummary* summary, int loss, cudaStream_t st, uint64_t* launches);
 // 16 bpp <-> RGB24 (channel masks of CodecParameters; shifts = position of each mask's lowest set bit, screencap.cpp:1575-1583)
 struct Rgb16 {

@@ -188,6 +188,54 @@ def test_full_length_configs_match_reference(scpr, name):
     assert np.array_equal(stream2, stream) and np.array_equal(sizes2, sizes) and np.array_equal(fts2, fts), f"{name}: host-buffer call differs"
 
 
+@pytest.mark.parametrize("size", [(128, 16), (132, 17), (640, 360), (1000, 50), (1920, 1080), (260, 33)])
+def test_tma_frame_scan_equals_plain_load_scan(scpr, size):
+    """The TMA tile stream (csrc/frame_scan_tma.cu: cp.async.bulk.tensor tiles, the previous frame's tile kept in registers along
+    a run of frames) against the plain-load kernel (csrc/frame_scan.cu) on the same device frames: block words, flat / changed
+    flags and pixel 0 of every frame must be identical -- ragged right and bottom tiles, runs of 1..32 frames, flat frames,
+    duplicates, single-pixel changes in tile corners."""
+    import torch
+
+    w, h = size
+    rng = np.random.default_rng(w * 7 + h)
+    for n in (1, 2, 5, 37, 70 if w * h < 500000 else 9):
+        clip = np.zeros((n, h, w, 4), np.uint8)
+        base = rng.integers(0, 4, (h, w, 3), dtype=np.uint8) * 50
+        for i in range(n):
+            kind = rng.integers(0, 6)
+            if kind == 0 and i:
+                pass                                         # duplicate of the previous frame
+            elif kind == 1:
+                base = base.copy(); base[:] = rng.integers(0, 256, 3, dtype=np.uint8)   # flat frame
+            elif kind == 2:
+                base = base.copy()
+                for _ in range(4):                           # single pixels, corners of tiles and of the frame among them
+                    y = int(rng.choice([0, h - 1, 15, 16 % h, rng.integers(0, h)])); x = int(rng.choice([0, w - 1, 127 % w, 128 % w, rng.integers(0, w)]))
+                    base[y, x] ^= rng.integers(1, 256, 3, dtype=np.uint8)
+            elif kind == 3:
+                base = rng.integers(0, 3, (h, w, 3), dtype=np.uint8) * 90
+            else:
+                base = base.copy()
+                y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+                base[y:y + int(rng.integers(1, 40)), x:x + int(rng.integers(1, 200))] = rng.integers(0, 256, 3, dtype=np.uint8)
+            clip[i, ..., :3] = base
+            clip[i, ..., 3] = rng.integers(0, 256)           # alpha is not part of the picture
+        prev = np.ascontiguousarray(clip[-1] if n > 1 else clip[0] ^ 1)
+        d = torch.from_numpy(clip).cuda()
+        dp = torch.from_numpy(prev).cuda()
+        sc = _new(scpr, w, h, 32)
+        _, bi1, sm1 = sc.debug_frame_scan(1, d.data_ptr(), dp.data_ptr(), n)
+        _, bi2, sm2 = sc.debug_frame_scan(2, d.data_ptr(), dp.data_ptr(), n)
+        assert np.array_equal(bi1, bi2), (size, n, np.argwhere(bi1 != bi2)[:5])
+        assert np.array_equal(sm1[:, :3], sm2[:, :3]), (size, n, sm1[:4], sm2[:4])
+        # and against numpy: changed / notflat flags, pixel 0
+        px = clip.view(np.uint32).reshape(n, h, w) & 0xFFFFFF
+        pv = np.concatenate([prev.view(np.uint32).reshape(1, h, w) & 0xFFFFFF, px[:-1]])
+        assert np.array_equal(sm2[:, 1] != 0, (px != pv).reshape(n, -1).any(1))
+        assert np.array_equal(sm2[:, 0] != 0, (px != px[:, :1, :1]).reshape(n, -1).any(1))
+        assert np.array_equal(sm2[:, 2], px[:, 0, 0])
+
+
 def test_full_size_round_trip_properties(scpr):
     """BASELINE configs at full resolution, more frames than the oracle could check in seconds:
     decode(encode(x)) == x, duplicate frames cost one byte, flat frames four."""
