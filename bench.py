@@ -475,23 +475,28 @@ def run_cuda(args):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = frames * W * H * 8  # cur + prev, 4 B/px each
+    # Algorithmic bytes of the frame scan: every pixel of every frame once, 4 B/px.  SURVEY.md 8(d) quotes W*H*(4+4) per frame
+    # (current + previous frame, how the reference and the round-1 kernel read them); k_frame_scan_tma carries the previous
+    # frame's tile in registers from one frame to the next, so the second read is not part of the algorithm any more -- the
+    # 8 B/px figure is reported beside it as `reference_equivalent_GBps` (it exceeds the HBM peak because those bytes never move).
+    alg_bytes = frames * W * H * 4
     achieved = alg_bytes / (scan_ms / 1e3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "frame_scan_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_frame_scan_tma_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_600f")
-    roofline = {"kernel": "k_frame_scan32", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        tj = json.load(open(tpath))
+        traffic = int((tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["frames_in_launch"] * frames)
+    roofline = {"kernel": "k_frame_scan_tma", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": scan_ms,
-                "share_of_step": scan_ms / (ms / args.steps)}
+                "share_of_step": scan_ms / (ms / args.steps),
+                "reference_equivalent_GBps": 2 * achieved,
+                "note": "TMA tile stream (cp.async.bulk.tensor.3d + mbarrier rings, one persistent CTA per SM); algorithmic bytes = "
+                        "4 B/px, every frame once (the previous frame's tile stays in registers); `traffic` = dram read + write bytes of "
+                        "the same launch from ncu (profiles/r02_frame_scan_tma_traffic.json). This kernel is a fraction of a percent of "
+                        "the step; the step is the decoder's serial GOP chain, see dominant_kernel"}
     if traffic:
-        # frame f - 1, read as "prev" of frame f, is still in the 126 MB L2: about half of the algorithmic bytes never cross
-        # HBM.  What does cross, per second, against the same peak:
-        roofline.update({"dram_GBps": traffic / (scan_ms / 1e3) / 1e9, "dram_frac": traffic / (scan_ms / 1e3) / 1e9 / peak,
-                         "note": "`achieved` counts algorithmic bytes (cur + prev per frame); `traffic` = dram bytes of the same launch "
-                                 "from ncu (profiles/): the previous frame is served by L2, so dram_frac is the honest HBM figure. This "
-                                 "kernel is a fraction of a percent of the step; the step is the decoder's serial GOP chain, see dominant_kernel"})
+        roofline.update({"dram_GBps": traffic / (scan_ms / 1e3) / 1e9, "dram_frac": traffic / (scan_ms / 1e3) / 1e9 / peak})
 
     cpu_on = not args.no_cpu_baseline
     cpu = parity = None
@@ -506,6 +511,14 @@ def run_cuda(args):
                "sample": f"the first {sample} of {frames} frames of the same clip, one CompressFrame + DecompressFrame call per frame, 1 thread "
                          "(canonical bitstream), one pass",
                "encode_fps": sample / te, "decode_fps": sample / td}
+        if kind == "reference" and "timing_split" not in args.skip:
+            # the reference's own TIMING mode on the first frames of the clip: where one host core spends an I and a P frame
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            try:
+                import ref_timing_split
+                cpu["timing_split"] = ref_timing_split.collect(WORKLOAD, 40)
+            except Exception as ex:  # a baseline detail must not take the bench line down
+                cpu["timing_split"] = {"unavailable": repr(ex)[:200]}
         pos, bad = 0, []
         for i, (data, ft) in enumerate(ref_frames):
             got = bytes(s_keep[pos:pos + int(sizes_keep[i])])

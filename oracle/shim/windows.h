@@ -152,4 +152,21 @@ static inline void GetSystemInfo(SYSTEM_INFO* si) { si->dwNumberOfProcessors = g
 #define max(a, b) (((a) > (b)) ? (a) : (b))
 #endif
 
+
+// ---- high-resolution counter (only the reference's own TIMING mode uses it, screencap.cpp:83-85, 325-341, 1096-1268) ------
+#include <time.h>
+union LARGE_INTEGER {
+    long long QuadPart;
+};
+static inline BOOL QueryPerformanceFrequency(LARGE_INTEGER* f) {
+    f->QuadPart = 1000000000LL;
+    return TRUE;
+}
+static inline BOOL QueryPerformanceCounter(LARGE_INTEGER* c) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    c->QuadPart = (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec;
+    return TRUE;
+}
+
 #endif
