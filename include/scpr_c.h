@@ -69,6 +69,16 @@ int scpr_compress_frame(scpr_codec* c, const uint8_t* src, uint8_t* dst, int dst
  * nobody can decode (the reference throws BadVersionException(v), screencap.cpp:1589-1590), or an SCPR_E_* code. */
 int scpr_decompress_frame(scpr_codec* c, const uint8_t* src, int src_len, uint8_t* dst, int pitch, int ftype);
 
+/* Bitstream layout of the multi-threaded reference, I frames only.  The reference splits pixel classification of
+ * an I frame into one row band per worker thread (CSquadWorker::GetSegment, squad.cpp:16-31; CMD_CLASSIFYPIXELSI,
+ * screencap.cpp:862-866) and every band starts a new run (ClassifyPixelsI :876-919, serialised band by band :365-388), so the bytes
+ * of an I frame depend -- deterministically -- on its thread count.  n_threads = 1 (default) is the canonical stream; n > 1 writes
+ * I frames byte-identical to the reference with n worker threads (n <= block rows of the frame, the limit of the reference's own
+ * per-thread table).  P frames of the multi-threaded reference depend on thread timing and cannot be reproduced by anyone
+ * (SURVEY.md 0.1): they are always written in the canonical 1-thread layout, which every reference decoder reads.  Decoding needs
+ * no setting. */
+int scpr_set_threads_layout(scpr_codec* c, int n_threads);
+
 /* ---- throughput entry points (no reference equivalent): many frames per call -------------
  * The frames of one call are processed as a batch: frame differencing, block typing, motion
  * search, pixel typing and event generation run in parallel over all frames; the adaptive

@@ -121,6 +121,8 @@ def load_library() -> C.CDLL:
     lib.scpr_compress_clip_multi.argtypes = [C.POINTER(_Params), vp, i32, vp, i32, vp, vp, C.c_size_t, vp, vp, vp, vp]
     lib.scpr_decompress_clip_multi.restype = i32
     lib.scpr_decompress_clip_multi.argtypes = [C.POINTER(_Params), vp, i32, vp, vp, vp, i32, vp, i32]
+    lib.scpr_set_threads_layout.restype = i32
+    lib.scpr_set_threads_layout.argtypes = [vp, i32]
     lib.scpr_reset.argtypes = [vp]
     lib.scpr_set_stream.restype = i32
     lib.scpr_set_stream.argtypes = [vp, vp]
@@ -268,6 +270,10 @@ class ScreenCodec:
                                    "frame; pass a larger capacity via reserve_clip_output()")
             self._check(r)
             return self._clip_dst[:r], sizes, ftypes
+
+    def set_threads_layout(self, n_threads: int) -> None:
+        """I frames in the layout of the reference running with n worker threads (scpr_set_threads_layout); 1 = canonical"""
+        self._check(self._lib.scpr_set_threads_layout(self._h, int(n_threads)))
 
     def reserve_clip_output(self, nbytes: int) -> None:
         self._clip_cap = int(nbytes)

@@ -427,6 +427,7 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         iw.starts = (uint16_t*)c->starts.p; iw.chunk_cnt = (uint32_t*)c->chunk_cnt.p;
         iw.frame_ev_off = (const uint32_t*)c->frame_ev_off.p;
         iw.tm = &tm;
+        iw.bands = c->threads_layout;
         launch_i_stage_a(iw, st, &c->launches);
         tm.mark("i_stage_a");
     }
@@ -776,6 +777,18 @@ int scpr_set_mvs_hooks(scpr_codec* c, void (*wait)(void*), void (*ready)(void*),
     c->mvs_wait = wait;
     c->mvs_ready = ready;
     c->mvs_user = user;
+    return SCPR_OK;
+}
+
+int scpr_set_threads_layout(scpr_codec* c, int n_threads) {
+    if (!c || n_threads < 1) return SCPR_E_PARAM;
+    // the reference indexes a per-thread table that is sized by block rows (screencap.cpp:1462, 366-367): more bands than block
+    // rows is undefined behaviour there; more bands than pixel rows makes no sense anywhere
+    if (n_threads > c->g.nby || n_threads > c->g.Y) {
+        set_error("threads layout %d exceeds the %d block rows of the frame", n_threads, c->g.nby);
+        return SCPR_E_PARAM;
+    }
+    c->threads_layout = n_threads;
     return SCPR_OK;
 }
 

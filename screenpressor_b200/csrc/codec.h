@@ -56,6 +56,7 @@ struct scpr_codec {
     void (*mvs_ready)(void*) = nullptr;
     void* mvs_user = nullptr;
     bool in_hook = false;
+    int threads_layout = 1;          // I-frame run breaks of the reference running with this many worker threads (scpr_set_threads_layout)
 
     // ---- encoder workspaces ---------------------------------------------------------------------
     scpr::DBuf summary2;

@@ -36,6 +36,20 @@ __device__ __forceinline__ uint32_t px_lin(const uint8_t* f, const Geo& g, long 
     return load_px(f, g, x, y);
 }
 
+// The multi-threaded reference classifies an I frame in `bands` row bands (CSquadWorker::GetSegment, squad.cpp:16-31: band b covers
+// rows [Y*b/bands, Y*(b+1)/bands)), one worker each, and every band starts a new run at its first pixel (ClassifyPixelsI,
+// screencap.cpp:876-919; the bands are serialised one after the other, :365-388).  That is the only way the thread count shows
+// in an I frame's bytes, and in this design it is one clamp: a run that would start at pixel q may not reach past the first
+// pixel of the next band.  The orbit q -> q + len(q) then lands on every band start by itself.  -> pixels left before that limit
+__device__ __forceinline__ long band_room(const Geo& g, int bands, long q) {
+    if (bands <= 1) return 1L << 40;
+    const int y = (int)(q / g.X);
+    int b = (int)(((long)y * bands) / g.Y);
+    while (b + 1 < bands && (long)g.Y * (b + 1) / bands <= y) b++;
+    if (b + 1 >= bands) return 1L << 40;
+    return ((long)g.Y * (b + 1) / bands) * g.X - q;
+}
+
 // number of consecutive set bits starting at bit position `pos`, at most `maxn`
 __device__ __forceinline__ int ones_from(const uint32_t* bits, int pos, int maxn) {
     int n = 0;
@@ -101,6 +115,7 @@ __global__ void __launch_bounds__(256) k_i_classify(IWork w) {
         if (q < total) {
             const int cls = type <= 1 ? 0 : type == 2 ? 1 : type == 4 ? 2 : 3;
             len = 1 + ones_from(s_bits[cls], p + 1, 254);
+            len = (int)min((long)len, band_room(g, w.bands, q));
             desc[q] = (uint16_t)((type << 8) | len);
         }
         s_jump[0][p] = (uint16_t)min(p + len, 2 * ICHUNK);

@@ -106,6 +106,7 @@ void mv_stats_report();
 struct IWork {
     const uint8_t* frames; Geo g;
     IFrameHdr* hdr; int n_iframes; int nchunks;
+    int bands;             // row bands that each start a new run (the reference's worker-thread count, 1 = canonical stream)
     uint16_t* desc;        // per pixel (type<<8 | len): the run that would start here
     uint8_t* exit_tab;     // per chunk: entry offset -> entry offset of the next chunk (256 entries)
     uint16_t* entry;       // per chunk: offset of the first run start

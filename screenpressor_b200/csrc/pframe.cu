@@ -324,33 +324,91 @@ __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
 struct MvRec {
     uint32_t bi, info, mmask;
     int fidx, fv;
+    int sp;   // speculated compare (helper warps): vector tried, packed; valid when spf & 1, its outcome in spf bit 1
+    int spf;
 };
 __device__ __forceinline__ MvRec load_mvrec(const ChgBlock* blocks, int k, int nchg) {
     MvRec r;
     r.bi = r.info = r.mmask = 0;
     r.fidx = 0x100;
     r.fv = 0;
+    r.sp = r.spf = 0;
     if (k < nchg) {
         const ChgBlock& b = blocks[k];
         r.bi = b.bi; r.info = b.info; r.mmask = b.mmask; r.fidx = b.has_f ? b.fidx : 0x100;
         r.fv = ((int)b.fmx & 0xFFFF) | ((int)b.fmy << 16);
+        r.sp = ((int)b.mx & 0xFFFF) | ((int)b.my << 16);
+        r.spf = b.pad[0];
     }
     return r;
 }
+// Helper warps (every warp that does not share warp 0's scheduler) answer the expensive question ahead of time: while warp 0
+// resolves frame pi, they take the changed blocks of frame pi + 1, read the vector currently stored for the block above, and --
+// when it is not one of that frame's prematched candidates -- run the direct compare, leaving {vector, outcome} in the block
+// record (mx / my / pad[0], which the resolve overwrites).  The stored vectors only change where a block is motion-coded, so the
+// guess is almost always the vector warp 0 will find there one frame later; it checks (vector equal?) and falls back to its own
+// compare otherwise.  The 25 000 serial compares of a 600-frame desktop clip (1.1 us each) become a few parallel rounds per frame.
+constexpr int MVR_WARPS = 16;
 template <bool SMV>
-__global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
+__device__ void mv_speculate(const PWork& w, const uint32_t* s_mvs, int pi, int hw, int nh, int lane) {
+    const Geo& g = w.g;
+    const int f = w.pframes[pi];
+    const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
+    const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
+    const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
+    const int nc = w.ncands[pi];
+    const int cand = w.cands[(size_t)pi * MAXC + lane];
+    for (int k = hw; k < nchg; k += nh) {
+        ChgBlock& b = w.blocks[off + k];
+        const uint32_t bi = b.bi, info = b.info;
+        int flag = 0, uv = 0;
+        if (bi >= (uint32_t)g.nbx) {
+            if (SMV)
+                uv = (int)((const volatile uint32_t*)s_mvs)[bi - g.nbx];
+            else {
+                const volatile int* u = (const volatile int*)(w.mvs + (bi - g.nbx));
+                uv = (u[0] & 0xFFFF) | (u[1] << 16);
+            }
+            uv = __shfl_sync(0xFFFFFFFFu, uv, 0);  // one value for the whole warp even while warp 0 is writing
+            if (uv != 0 && !__ballot_sync(0xFFFFFFFFu, lane < nc && cand == uv)) {
+                const SubRect r = subrect_of(bi, info, g);
+                const Windows win = windows_of(r, g);
+                const int mx = (int)(int16_t)(uv & 0xFFFF), my = uv >> 16;
+                const bool hit = in_far_window(r, win, mx, my) && warp_match_full(cur, prv, g, r, mx, my, lane);
+                flag = 1 | (hit ? 2 : 0);
+            }
+        }
+        if (lane == 0) {
+            b.mx = (int16_t)(uv & 0xFFFF);
+            b.my = (int16_t)(uv >> 16);
+            b.pad[0] = (uint8_t)flag;
+        }
+    }
+}
+template <bool SMV>
+__global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
     extern __shared__ uint32_t s_mvs[];  // SMV: packed vector of every block
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1;
     const Geo& g = w.g;
     if (SMV) {
-        for (int i = lane; i < g.nb; i += 32) {
+        for (int i = threadIdx.x; i < g.nb; i += blockDim.x) {
             const int2 u = w.mvs[i];
             s_mvs[i] = ((uint32_t)u.x & 0xFFFFu) | ((uint32_t)u.y << 16);
         }
-        __syncwarp();
     }
+    __syncthreads();
+    // helper warps: 1, 2, 3, 5, 6, 7, ... (warps 4, 8, 12 share warp 0's scheduler and only keep the barriers)
+    const int nh = MVR_WARPS - MVR_WARPS / 4;
+    const int hw = (warp & 3) ? warp - 1 - (warp >> 2) : -1;
+    if (hw >= 0 && w.n_pframes > 0) mv_speculate<SMV>(w, s_mvs, 0, hw, nh, lane);
+    __syncthreads();
     for (int pi = 0; pi < w.n_pframes; pi++) {
+        if (warp != 0) {
+            if (hw >= 0 && pi + 1 < w.n_pframes) mv_speculate<SMV>(w, s_mvs, pi + 1, hw, nh, lane);
+            __syncthreads();
+            continue;
+        }
         const int f = w.pframes[pi];
         const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
@@ -373,8 +431,11 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
             const int jw = k0 - w0 + lane, js = jw & 31;
             const bool lo = jw < 32;
             uint32_t bi, info, mmask;
-            int fidx, fv, uv = 0;
+            int fidx, fv, uv = 0, sp, spf;
             {
+                const int s0 = __shfl_sync(0xFFFFFFFFu, r0.sp, js), s1 = __shfl_sync(0xFFFFFFFFu, r1.sp, js);
+                const int t0 = __shfl_sync(0xFFFFFFFFu, r0.spf, js), t1 = __shfl_sync(0xFFFFFFFFu, r1.spf, js);
+                sp = lo ? s0 : s1; spf = lo ? t0 : t1;
                 const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, r0.bi, js), a1 = __shfl_sync(0xFFFFFFFFu, r1.bi, js);
                 const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, r0.info, js), b1 = __shfl_sync(0xFFFFFFFFu, r1.info, js);
                 const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, r0.mmask, js), c1 = __shfl_sync(0xFFFFFFFFu, r1.mmask, js);
@@ -420,7 +481,9 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
                 todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
             }
             bool f2 = try2 && uidx >= 0 && ((mmask >> uidx) & 1);
-            uint32_t slow = __ballot_sync(0xFFFFFFFFu, try2 && uidx < 0);
+            const bool spec_ok = (spf & 1) && sp == uv;  // a helper warp has already compared this block with this vector
+            if (try2 && uidx < 0 && spec_ok) f2 = (spf & 2) != 0;
+            uint32_t slow = __ballot_sync(0xFFFFFFFFu, try2 && uidx < 0 && !spec_ok);
             MV_STAT(if (lane == 0) {
                 atomicAdd(&g_mv_stats[0], 1ull);
                 atomicAdd(&g_mv_stats[2], (unsigned long long)__popc(slow));
@@ -483,6 +546,7 @@ __global__ void __launch_bounds__(32) k_mv_resolve(PWork w) {
             k0 += cnt;
         }
         __threadfence();  // mvs[] of this frame visible before the next frame reads it
+        __syncthreads();  // ... and the helpers' answers for the next frame are complete
     }
 }
 
@@ -788,9 +852,9 @@ void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
         const size_t mv_smem = (size_t)w.g.nb * 4;
         if (mv_smem <= 200 * 1024) {
             cudaFuncSetAttribute(k_mv_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mv_smem);
-            k_mv_resolve<true><<<1, 32, mv_smem, st>>>(w);
+            k_mv_resolve<true><<<1, 32 * MVR_WARPS, mv_smem, st>>>(w);
         } else
-            k_mv_resolve<false><<<1, 32, 0, st>>>(w);
+            k_mv_resolve<false><<<1, 32 * MVR_WARPS, 0, st>>>(w);
         if (w.tm) w.tm->mark("mv_resolve");
         if (w.post_resolve) {  // mvs[] is final for this call: the next range may start its resolve
             cudaStreamSynchronize(st);

@@ -102,3 +102,29 @@ def to_rgb555(clip32: np.ndarray) -> np.ndarray:
     """(n, h, w, 4) BGRA bytes -> (n, h, w) uint16 words, 5 bits per channel under the masks 0x7C00 / 0x3E0 / 0x1F"""
     c = clip32.astype(np.uint16)
     return ((c[..., 0] >> 3) << 10) | ((c[..., 1] >> 3) << 5) | (c[..., 2] >> 3)
+
+
+def band_clip(w: int, h: int, n: int, seed: int, bpp: int = 32) -> np.ndarray:
+    """flat background, rectangles, a gradient column band and a noise patch: runs that continue across row ends, so the row bands
+    of the multi-threaded reference (one new run per band) change the bytes of an I frame"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        rgb = np.zeros((h, w, 3), np.uint8)
+        rgb[:] = rng.integers(0, 256, 3, dtype=np.uint8)
+        yy, xx = np.mgrid[0:h, 0:w]
+        rgb[:, w // 3:w // 2, 0] = (xx[:, w // 3:w // 2] * 2 + yy[:, w // 3:w // 2]) & 255
+        for _ in range(6):
+            x1, y1 = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 8))
+            rgb[y1:y1 + int(rng.integers(2, h // 3)), x1:x1 + int(rng.integers(2, w // 3))] = rng.integers(0, 256, 3, dtype=np.uint8)
+        x1, y1 = int(rng.integers(0, w - 40)), int(rng.integers(0, h - 30))
+        rgb[y1:y1 + 30, x1:x1 + 40] = rng.integers(0, 16, (30, 40, 3), dtype=np.uint8) * 16
+        if bpp == 32:
+            fr = np.full((h, w, 4), 255, np.uint8)
+            fr[..., :3] = rgb
+        else:
+            st = (w * 3 + 3) & ~3
+            fr = np.zeros((h, st), np.uint8)
+            fr[:, :w * 3] = rgb.reshape(h, w * 3)
+        out.append(fr)
+    return np.stack(out)

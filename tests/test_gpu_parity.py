@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import _golden
-from _clips import fuzz_clip, motion_clip
+from _clips import band_clip, fuzz_clip, motion_clip
 
 pytestmark = pytest.mark.gpu
 
@@ -569,6 +569,46 @@ def test_cpp_facade_driven_like_the_vfw_layer(scpr, oracle_built, tmp_path):
             assert np.array_equal(decoded[i], refdec.decompress(data, ft)), (w, h, bpp, i)
             pos += sz
         assert pos == stream.size
+
+
+@pytest.mark.parametrize("case", [(320, 192, 32), (161, 90, 24), (640, 360, 32)])
+def test_threads_layout_matches_multithreaded_reference_i_frames(scpr, oracle_built, case):
+    """the reference with n worker threads splits an I frame into n row bands and every band starts a new run
+    (squad.cpp:16-31, screencap.cpp:862-866, 876-919, 365-388).  scpr_set_threads_layout(n) must write the same bytes -- checked
+    against the unmodified reference created with n threads on intra-only clips (its multi-threaded P frames are timing dependent,
+    SURVEY 0.1, so only I frames can be pinned), frame and clip API; any decoder reads them."""
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref not built")
+    w, h, bpp = case
+    n = 6
+    clip = band_clip(w, h, n, 900 + w, bpp)
+    keys = np.ones(n, np.uint8)
+    nby = (h + 15) // 16
+    canonical = None
+    for threads in (1, 2, 3, 5, nby):
+        ref = oracle_built.RefCodec(w, h, bpp, threads=threads)   # (the thread count is read at this codec's first CompressFrame)
+        want = [ref.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), False) for i in range(n)]
+        if threads == 1:
+            canonical = want
+        else:
+            assert want != canonical, "the clip does not exercise the band breaks"
+        enc = _new(scpr, w, h, bpp)
+        enc.set_threads_layout(threads)
+        got = _split(*enc.CompressClip(clip, keys))
+        flat = [i for i in range(n) if len(want[i][0]) <= 4]
+        assert len(flat) < n
+        assert got == want, (case, threads, [i for i in range(n) if got[i] != want[i]])
+        enc2 = _new(scpr, w, h, bpp)
+        enc2.set_threads_layout(threads)
+        assert [enc2.CompressFrame(clip[i], 0) for i in range(n)] == want, (case, threads)
+        dec = _new(scpr, w, h, bpp)
+        for i in range(n):
+            assert np.array_equal(dec.DecompressFrame(want[i][0], None, want[i][1]), clip[i].reshape(-1)), (case, threads, i)
+    bad = _new(scpr, w, h, bpp)
+    with pytest.raises(scpr.ScprError):
+        bad.set_threads_layout(nby + 1)
+    with pytest.raises(scpr.ScprError):
+        bad.set_threads_layout(0)
 
 
 def test_full_state_checkpoint_resume_at_any_frame(scpr):
