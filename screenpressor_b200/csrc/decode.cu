@@ -219,7 +219,10 @@ struct Ent {
 #ifdef SCPR_PROF
     long long c_fixed = 0, n_fixed = 0, c_color = 0, n_color = 0, c_tile = 0, n_blocks = 0, c_blkwr = 0, c_mv = 0, c_runs = 0, c_ifill = 0,
               c_hdr = 0, c_total = 0, n_gen = 0, n_resc = 0, c_rebuild = 0, n_rebuild = 0, c_small = 0, n_small = 0, c_flat = 0, n_flat = 0,
-              c_raw = 0, n_raw = 0, n_miss = 0, c_drain = 0, c_lpwait = 0, n_lpwait = 0;
+              c_raw = 0, n_raw = 0, n_miss = 0, c_drain = 0, c_lpwait = 0, n_lpwait = 0, n_lppoll = 0, n_lplong = 0;
+#endif
+#ifdef SCPR_LPSTAT
+    uint32_t s_waits = 0, s_polls = 0, s_long = 0;  // light counters (no clock reads on the per-symbol path)
 #endif
     uint32_t x;
     uint32_t w0, w1, k8;      // window: stream bytes from bit k8 of w0 on
@@ -959,9 +962,24 @@ __device__ __forceinline__ void fetch_lastpx(Ent& e) {
         // {commands executed up to and including the last run, that run's last pixel}: one 64-bit word, written at once
         PROF_T0
         uint2 lp;
+#if defined(SCPR_PROF) || defined(SCPR_LPSTAT)
+        int polls__ = 0;
+#endif
         do {
             asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lp.x), "=r"(lp.y) : "r"(e.sb + S_RSYNC + 8u) : "memory");
+#if defined(SCPR_PROF) || defined(SCPR_LPSTAT)
+            polls__++;
+#endif
         } while ((int)(lp.x - e.lp_wait) < 0);
+#ifdef SCPR_LPSTAT
+        e.s_waits++;
+        e.s_polls += polls__;
+        if (polls__ > 10) e.s_long++;
+#endif
+#ifdef SCPR_PROF
+        e.n_lppoll += polls__;
+        if (polls__ > 25) e.n_lplong++;
+#endif
         e.lastpx = lp.y;
         e.lp_wait = 0;
         PROF_ADD(c_lpwait) PROF_CNT(n_lpwait)
@@ -1611,7 +1629,11 @@ __device__ void decode_p(const DecWork& w, const BlockMap<SM>& map, Ent& e, uint
                 int n = dec_run<V2>(e, ptype, c);
                 if (n > npx - pos) n = npx - pos;
                 if (n <= 0) break;
+#ifdef SCPR_PROF
+                rq_post(e, RQ_RUN | ((uint32_t)ptype << 8) | ((uint32_t)n << 16), c, (uint32_t)clock64());
+#else
                 rq_post(e, RQ_RUN | ((uint32_t)ptype << 8) | ((uint32_t)n << 16), c, 0u);
+#endif
                 if (ptype) e.lp_wait = e.rposted;  // a predicted run: its last pixel is known once this command is done
                 pos += n;
             }
@@ -1644,7 +1666,8 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
     int ix = 0, iy = 0;
     uint32_t ilast = 0, rdone = 0;
 #ifdef SCPR_PROF
-    long long r_pub = 0, r_run = 0, r_nrun = 0, r_load = 0, r_nload = 0, r_end = 0, r_idle = 0;
+    long long r_pub = 0, r_run = 0, r_nrun = 0, r_load = 0, r_nload = 0, r_end = 0, r_idle = 0, r_qlat = 0, r_qlong = 0, r_qidle = 0, r_qprev[4] = {0, 0, 0, 0}, r_spins = 0, r_t[6] = {0, 0, 0, 0, 0, 0}, r_n[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t prev_op__ = 0, last_spins__ = 0;
 #endif
     for (uint32_t ridx = 0;; ridx++) {
 #ifdef SCPR_PROF
@@ -1653,9 +1676,15 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
         uint4 cmd;
         const uint32_t slot = sb + S_RQ + 16u * (ridx % RQ);
         for (uint32_t spins = 0;; spins++) {
+            // both halves every time, {command, sequence number} first: the writer stores the arguments before that word, so when
+            // the sequence number read here is the awaited one, the arguments read after it are the command's (one round trip
+            // instead of two on the way to every run)
             asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.x), "=r"(cmd.w) : "r"(slot) : "memory");
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.y), "=r"(cmd.z) : "r"(slot + 8u) : "memory");
             if (cmd.w == ridx + 1u) {
-                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cmd.y), "=r"(cmd.z) : "r"(slot + 8u) : "memory");
+#ifdef SCPR_PROF
+                last_spins__ = spins;
+#endif
                 break;
             }
             if (spins == 0u && rdone != ridx) {  // nothing waiting: let the chain warp see how far this warp has come (drains)
@@ -1666,9 +1695,11 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             if ((spins & 31u) == 31u) {
 #ifdef SCPR_PROF
                 if (ldv_shared(sy + 12) && lane == 0)
-                    printf("[rec prof] runs %lld: detect->publish %.0f cyc, whole run %.0f cyc | loads %lld: %.0f cyc | ends %.0f cyc | idle %.1f Mcyc\n", r_nrun,
+                    printf("[rec prof] runs %lld: detect->publish %.0f cyc, whole run %.0f cyc | loads %lld: %.0f cyc | ends %.0f cyc | idle %.1f Mcyc | post->detect %.0f cyc, %lld over 1000 (of those %lld had polled before, %lld polls; previous op run %lld load %lld begin %lld other %lld) | by type n/cyc: 0 %lld/%.0f 1 %lld/%.0f 2 %lld/%.0f 3 %lld/%.0f 4 %lld/%.0f 5 %lld/%.0f\n", r_nrun,
                            (double)r_pub / (double)max(1LL, r_nrun), (double)r_run / (double)max(1LL, r_nrun), r_nload, (double)r_load / (double)max(1LL, r_nload),
-                           (double)r_end / (double)max(1LL, r_nload), r_idle * 1e-6);
+                           (double)r_end / (double)max(1LL, r_nload), r_idle * 1e-6, (double)r_qlat / (double)max(1LL, r_nrun), r_qlong, r_qidle, r_spins, r_qprev[0], r_qprev[1], r_qprev[2], r_qprev[3],
+                           r_n[0], (double)r_t[0] / (double)max(1LL, r_n[0]), r_n[1], (double)r_t[1] / (double)max(1LL, r_n[1]), r_n[2], (double)r_t[2] / (double)max(1LL, r_n[2]),
+                           r_n[3], (double)r_t[3] / (double)max(1LL, r_n[3]), r_n[4], (double)r_t[4] / (double)max(1LL, r_n[4]), r_n[5], (double)r_t[5] / (double)max(1LL, r_n[5]));
 #endif
                 if (ldv_shared(sy + 12)) return;
                 if (spins > 2048) __nanosleep(spins > 65536 ? 400 : 50);
@@ -1683,37 +1714,54 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             const int ptype = (int)((cmd.x >> 8) & 0xFFu), n = (int)(cmd.x >> 16);
             const uint32_t c = cmd.y;
             const int xe = xx0 + n;
-            // The chain warp may be waiting for the run's last pixel (the context of a literal that follows): every source
-            // of a predicted pixel lies outside its run, so that pixel is computed and published first, the fill follows.
-            if (ptype != 4) {
-                const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16), lx = li - ly * sw;
-                uint32_t vlast = c;
-                if (ptype == 1) vlast = ly == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + ly, ox - 1);
-                else if (ptype == 2) vlast = tile_at(tb, oy + (lx >= xx0 ? yy0 : yy0 + 1) - 1, ox + lx);
-                else if (ptype == 3) vlast = tile_at(tb, oy + ly, ox + lx);
-                else if (ptype == 5) {
-                    const int k = min((int)(((uint32_t)(n - 1) * sw1inv) >> 16) + 1, lx + 1);
-                    vlast = tile_at(tb, oy + ly - k, ox + lx - k);
+#ifdef SCPR_PROF
+            {
+                const uint32_t lat = (uint32_t)td__ - cmd.z;  // post -> detect
+                r_qlat += lat;
+                if (lat > 1000u) {
+                    r_qlong++;
+                    if (last_spins__ > 0) r_qidle++;
+                    r_qprev[prev_op__ == RQ_RUN ? 0 : prev_op__ == RQ_LOAD ? 1 : prev_op__ == RQ_BEGIN ? 2 : 3]++;
+                    r_spins += last_spins__;
                 }
-                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+            }
+#endif
+            // The chain warp may be waiting for the run's last pixel (the context of a literal that follows), and it produces a
+            // predicted run every ~500 cycles: this warp has to be quicker than that per run or the chain queues up behind it
+            // (measured: 35 % of the chain's time went into that wait when a run cost 550 cycles here).
+            if (xe <= sw && ptype != 4) {
+                // The run stays in its row (the common case; at most 16 pixels): every source is one fixed step away -- left: the
+                // pixel before the run; top: one tile row up; top-left: one row up, one left; type 3 keeps the previous frame's
+                // pixel that is already in the tile.  Lane i computes pixel i, so the run's last pixel is simply lane n - 1's
+                // value: that lane publishes it, then the lanes store -- no separate look-up, no division, no shuffle.
+                const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
+                uint32_t v = c;
+                if (ptype == 1) v = lds32(ca - 4u);
+                else if (ptype == 2) v = lds32(a - 68u);
+                else if (ptype == 5) v = lds32(a - 72u);
+                else if (ptype == 3) v = lds32(a);
+                if (lane == n - 1) asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(v) : "memory");
 #ifdef SCPR_PROF
                 r_pub += clock64() - td__;
 #endif
-            }
-            if (xe <= sw && ptype != 4) {
-                // the run stays in its row (the common case; at most 16 pixels): every source is one fixed step
-                // away -- left: the pixel before the run; top: one tile row up; top-left: one row up, one left;
-                // type 3 keeps the previous frame's pixel that is already in the tile
-                if (ptype != 3) {
-                    const uint32_t a = ca + 4u * (uint32_t)min(lane, n - 1);
-                    uint32_t v = c;
-                    if (ptype == 1) v = lds32(ca - 4u);
-                    else if (ptype == 2) v = lds32(a - 68u);
-                    else if (ptype == 5) v = lds32(a - 72u);
-                    if (lane < n) sts32(a, v);
-                }
+                if (ptype != 3 && lane < n) sts32(a, v);
                 __syncwarp();
             } else {
+                if (ptype != 4) {  // every source of a predicted pixel lies outside its run: the last pixel first, the fill follows
+                    const int li = pos + n - 1, ly = (int)(((uint32_t)li * swinv) >> 16), lx = li - ly * sw;
+                    uint32_t vlast = c;
+                    if (ptype == 1) vlast = ly == yy0 ? tile_at(tb, oy + yy0, ox + xx0 - 1) : tile_at(tb, oy + ly, ox - 1);
+                    else if (ptype == 2) vlast = tile_at(tb, oy + (lx >= xx0 ? yy0 : yy0 + 1) - 1, ox + lx);
+                    else if (ptype == 3) vlast = tile_at(tb, oy + ly, ox + lx);
+                    else if (ptype == 5) {
+                        const int k = min((int)(((uint32_t)(n - 1) * sw1inv) >> 16) + 1, lx + 1);
+                        vlast = tile_at(tb, oy + ly - k, ox + lx - k);
+                    }
+                    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(rs + 8u), "r"(ridx + 1u), "r"(vlast) : "memory");
+#ifdef SCPR_PROF
+                    r_pub += clock64() - td__;
+#endif
+                }
                 if (ptype == 4) {  // gradient chains through the left pixel: serial
                     if (lane == 0) {
                         int xx = xx0, yy = yy0;
@@ -1901,7 +1949,8 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
             __syncwarp();
         }
 #ifdef SCPR_PROF
-        if (op == RQ_RUN) { r_run += clock64() - td__; r_nrun++; }
+        prev_op__ = op;
+        if (op == RQ_RUN) { r_run += clock64() - td__; r_nrun++; const int pt__ = min((int)((cmd.x >> 8) & 0xFFu), 5); r_t[pt__] += clock64() - td__; r_n[pt__]++; }
         else if (op == RQ_LOAD) { r_load += clock64() - td__; r_nload++; }
         else if (op == RQ_END) r_end += clock64() - td__;
 #endif
@@ -1960,7 +2009,7 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     e.msr_y = w.msr_y;
     e.rc_code = e.rc_range = 0;
     e.rc_p = nullptr;
-#ifdef SCPR_PROF
+#if defined(SCPR_PROF) || defined(SCPR_LPSTAT)
     const long long tk0 = clock64();
 #endif
     // fixed tables and context kinds of the chain's model state -> shared memory (a renewing first frame overwrites them)
@@ -2036,13 +2085,16 @@ __global__ void __launch_bounds__(32 * DEC_WARPS, 1) k_dec_chain(DecWork w) {
     __threadfence();
     publish_progress(w, ch.first + ch.count, lane);
     stv_shared(sb + S_SYNC + 12, 1u);  // helpers leave
+#ifdef SCPR_LPSTAT
+    if (lane == 0) printf("[lp stat] chain %d frames %d: %.1f Mcyc, %u waits for a run's last pixel, %u polls, %u waits of > 10 polls\n", (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.s_waits, e.s_polls, e.s_long);
+#endif
 #ifdef SCPR_PROF
     if (lane == 0)
         printf("[dec prof] chain %d frames %d: total %.1f Mcyc | fixed %.1f Mcyc / %lld sym (%.0f cyc) | color %.1f / %lld (%.0f cyc; %lld serial, %lld rescales) | "
-               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f | cache misses %lld | lastpx waits %.1f / %lld\n",
+               "p-hdr %.1f | tile %.1f / %lld blocks | mv %.1f | runs(incl sym) %.1f | blkwr %.1f | ifill %.1f | rebuild %.1f / %lld | small %.1f / %lld flat %.1f / %lld raw %.1f / %lld | drain %.1f | cache misses %lld | lastpx waits %.1f / %lld (%lld polls, %lld waits of > 25 polls)\n",
                (int)blockIdx.x, ch.count, (clock64() - tk0) * 1e-6, e.c_fixed * 1e-6, e.n_fixed, (double)e.c_fixed / (double)max(1LL, e.n_fixed),
                e.c_color * 1e-6, e.n_color, (double)e.c_color / (double)max(1LL, e.n_color), e.n_gen, e.n_resc, e.c_hdr * 1e-6, e.c_tile * 1e-6,
-               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6, e.n_miss, e.c_lpwait * 1e-6, e.n_lpwait);
+               e.n_blocks, e.c_mv * 1e-6, e.c_runs * 1e-6, e.c_blkwr * 1e-6, e.c_ifill * 1e-6, e.c_rebuild * 1e-6, e.n_rebuild, e.c_small * 1e-6, e.n_small, e.c_flat * 1e-6, e.n_flat, e.c_raw * 1e-6, e.n_raw, e.c_drain * 1e-6, e.n_miss, e.c_lpwait * 1e-6, e.n_lpwait, e.n_lppoll, e.n_lplong);
 #endif
     // leave the cached contexts, the fixed tables and the kinds behind for the next call (v2 tables are already in place)
     __syncwarp();
