@@ -152,6 +152,14 @@ int64_t scpr_compress_clip_multi(const scpr_params* p, const int* devices, int n
 /* The decoding counterpart: ranges start at coded I frames, no hand-off.  frames: host memory, row pitch `pitch`. */
 int scpr_decompress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* stream, const uint32_t* sizes,
                                const uint8_t* ftypes, int n, uint8_t* frames, int pitch);
+/* The same with a standing set of codec objects (an encoder and a decoder per device ordinal, created once: workspaces and model
+ * states stay on the devices between calls).  Every call codes a clip of its own (the objects are reset first). */
+typedef struct scpr_multi scpr_multi;
+int scpr_multi_create(const scpr_params* p, const int* devices, int n_dev, scpr_multi** out);
+void scpr_multi_destroy(scpr_multi* m);
+int64_t scpr_multi_compress_clip(scpr_multi* m, const uint8_t* frames, int n, const uint8_t* keyflags, uint8_t* dst, size_t dst_cap,
+                                 uint32_t* sizes, uint8_t* ftypes, int* range_first, int* n_ranges);
+int scpr_multi_decompress_clip(scpr_multi* m, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* frames, int pitch);
 
 /* ---- host layer above the codec object: VfW policy and the AVI container (csrc/vfw_host.cpp) -------------------
  * What CodecInst does around ScreenCodec (screenpressor.cpp:343-437, 579-620), for hosts that are not VfW. */

@@ -123,6 +123,13 @@ def load_library() -> C.CDLL:
     lib.scpr_decompress_clip_multi.argtypes = [C.POINTER(_Params), vp, i32, vp, vp, vp, i32, vp, i32]
     lib.scpr_set_threads_layout.restype = i32
     lib.scpr_set_threads_layout.argtypes = [vp, i32]
+    lib.scpr_multi_create.restype = i32
+    lib.scpr_multi_create.argtypes = [C.POINTER(_Params), vp, i32, C.POINTER(vp)]
+    lib.scpr_multi_destroy.argtypes = [vp]
+    lib.scpr_multi_compress_clip.restype = C.c_int64
+    lib.scpr_multi_compress_clip.argtypes = [vp, vp, i32, vp, vp, C.c_size_t, vp, vp, vp, vp]
+    lib.scpr_multi_decompress_clip.restype = i32
+    lib.scpr_multi_decompress_clip.argtypes = [vp, vp, vp, vp, i32, vp, i32]
     lib.scpr_reset.argtypes = [vp]
     lib.scpr_set_stream.restype = i32
     lib.scpr_set_stream.argtypes = [vp, vp]
@@ -488,6 +495,59 @@ def decompress_clip_multi(params: "CodecParameters", devices, stream, sizes, fty
     if r != 1:
         raise ScprError(int(r), lib.scpr_last_error().decode())
     return out
+
+
+class MultiCodec:
+    """A standing set of codec objects over several GPUs driven from this process (scpr_multi_*): one clip per call, cut by
+    GOP-aligned frame ranges, byte-identical to one codec."""
+
+    def __init__(self, params: "CodecParameters", devices):
+        self._lib = load_library()
+        self.params = params
+        self.devices = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        p = params._c()
+        r = self._lib.scpr_multi_create(C.byref(p), _ptr(self.devices), len(self.devices), C.byref(h))
+        if r < 0:
+            raise ScprError(int(r), self._lib.scpr_last_error().decode())
+        self._h = h
+        bpp = params.bits_per_pixel // 8
+        self.pitch = ((params.width * 3 + 3) & ~3) if bpp == 3 else params.width * bpp
+        self._dst = None
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.scpr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress_clip(self, frames_ptr: int, keyflags: np.ndarray, cap: int = 256 << 20):
+        """frames_ptr: host address of n frames back to back (pinned memory uploads fastest) -> (stream view, sizes, ftypes, firsts)"""
+        keyflags = np.ascontiguousarray(keyflags, dtype=np.uint8)
+        n = int(keyflags.size)
+        if self._dst is None or self._dst.size < cap:
+            self._dst = np.empty(cap, dtype=np.uint8)
+        sizes, ftypes = np.zeros(n, np.uint32), np.zeros(n, np.uint8)
+        first, nr = np.zeros(len(self.devices), np.int32), C.c_int(0)
+        r = self._lib.scpr_multi_compress_clip(self._h, frames_ptr, n, _ptr(keyflags), _ptr(self._dst), self._dst.size, _ptr(sizes), _ptr(ftypes),
+                                               _ptr(first), C.addressof(nr))
+        if r < 0:
+            raise ScprError(int(r), self._lib.scpr_last_error().decode())
+        return self._dst[:r], sizes, ftypes, [int(x) for x in first[:nr.value]]
+
+    def decompress_clip(self, stream: np.ndarray, sizes: np.ndarray, ftypes: np.ndarray, out_ptr: int, pitch: int | None = None) -> None:
+        """out_ptr: host address of the destination frames (n * height * pitch bytes)"""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+        ftypes = np.ascontiguousarray(ftypes, dtype=np.uint8)
+        r = self._lib.scpr_multi_decompress_clip(self._h, _ptr(stream), _ptr(sizes), _ptr(ftypes), int(sizes.size), out_ptr, pitch or self.pitch)
+        if r != 1:
+            raise ScprError(int(r), self._lib.scpr_last_error().decode())
 
 
 class AviWriter:

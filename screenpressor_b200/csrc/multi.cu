@@ -113,127 +113,206 @@ void hook_ready(void* user) {  // range k: its resolve has completed
 
 }  // namespace
 
+// ---- a standing set of codec objects, one per device ordinal given (created once: device workspaces and model states stay) ----
+struct scpr_multi {
+    scpr_params p;
+    std::vector<int> devices;
+    std::vector<scpr_codec*> enc, dec;   // one of each per entry of `devices`
+};
+
+namespace {
+
+int64_t multi_compress(scpr_multi* m, const uint8_t* frames, int n, const uint8_t* keyflags, uint8_t* dst, size_t dst_cap, uint32_t* sizes,
+                       uint8_t* ftypes, int* range_first, int* n_ranges) {
+    const scpr_params* p = &m->p;
+    const int bpp = p->bits_per_pixel / 8;
+    const size_t pitch = bpp == 3 ? (((size_t)p->width * 3 + 3) & ~(size_t)3) : (size_t)p->width * bpp;
+    const size_t fb = pitch * p->height;
+    std::vector<uint8_t> cuts(n, 0);
+    for (int f = 1; f < n; f++) cuts[f] = keyflags[f] && !host_frame_is_flat(*p, frames + (size_t)f * fb);
+    const std::vector<Range> ranges = plan_ranges(n, cuts, m->devices.data(), (int)m->devices.size());
+    const int R = (int)ranges.size();
+    if (n_ranges) *n_ranges = R;
+    if (range_first)
+        for (int k = 0; k < R; k++) range_first[k] = ranges[k].first;
+    Relay relay;
+    relay.ready.assign(R, 0);
+    relay.failed.assign(R, 0);
+    relay.codec.assign(R, nullptr);
+    std::vector<HookCtx> ctx(R);
+    std::vector<std::unique_ptr<uint8_t[]>> out(R);
+    std::vector<size_t> out_cap(R, 0);
+    std::vector<int64_t> used(R, 0);
+    for (int k = 0; k < R; k++) {
+        relay.codec[k] = m->enc[k];  // range k runs on the k-th device given (plan_ranges hands them out in order)
+        const int r = scpr_reset(relay.codec[k]);
+        if (r < 0) return r;
+        ctx[k].relay = &relay;
+        ctx[k].k = k;
+        scpr_set_mvs_hooks(relay.codec[k], hook_wait, hook_ready, &ctx[k]);
+        // worst case per frame is W*H*6 (CompressGetSize) but never more than the caller's whole buffer; the pages of an
+        // untouched new[] are not committed
+        size_t cap = (size_t)ranges[k].count * scpr_max_compressed_size(p);
+        if (cap > dst_cap) cap = dst_cap;
+        out_cap[k] = cap;
+        out[k].reset(new uint8_t[cap + 16]);
+    }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < R; k++)
+        pool.emplace_back([&, k]() {
+            const Range& rg = ranges[k];
+            std::vector<uint8_t> keys(keyflags + rg.first, keyflags + rg.first + rg.count);
+            keys[0] = 1;
+            // a fresh codec treats its first frame as a keyframe anyway; for k > 0 the cut guarantees the reference does too
+            int64_t r = scpr_compress_clip(relay.codec[k], frames + (size_t)rg.first * fb, rg.count, keys.data(), out[k].get(), out_cap[k],
+                                           sizes + rg.first, ftypes + rg.first);
+            if (r >= 0 && ctx[k].err) r = SCPR_E_CUDA;
+            used[k] = r;
+            if (r < 0) {
+                {
+                    std::lock_guard<std::mutex> lk(relay.m);
+                    relay.failed[k] = 1;
+                }
+                relay.cv.notify_all();
+            }
+        });
+    for (auto& t : pool) t.join();
+    for (int k = 0; k < R; k++) scpr_set_mvs_hooks(relay.codec[k], nullptr, nullptr, nullptr);
+    int64_t total = 0, err = 0;
+    for (int k = 0; k < R; k++) {
+        if (used[k] < 0 && !err) err = used[k];
+        if (used[k] > 0) total += used[k];
+    }
+    if (!err && (size_t)total > dst_cap) {
+        set_error("destination too small: need %lld bytes", (long long)total);
+        err = SCPR_E_DSTSIZE;
+    }
+    if (!err) {  // host-side concatenation in frame order
+        size_t pos = 0;
+        for (int k = 0; k < R; k++) {
+            memcpy(dst + pos, out[k].get(), (size_t)used[k]);
+            pos += (size_t)used[k];
+        }
+    }
+    return err ? err : total;
+}
+
+int multi_decompress(scpr_multi* m, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* frames, int pitch) {
+    const scpr_params* p = &m->p;
+    // a range may start at any I frame that is not a flat frame (a flat frame's successors can be P frames on older models)
+    std::vector<uint8_t> cuts(n, 0);
+    std::vector<size_t> off(n + 1, 0);
+    for (int f = 0; f < n; f++) off[f + 1] = off[f] + sizes[f];
+    for (int f = 1; f < n; f++) cuts[f] = ftypes[f] == 0 && sizes[f] >= 1 && (stream[off[f]] & 0x0F) == 2;
+    const std::vector<Range> ranges = plan_ranges(n, cuts, m->devices.data(), (int)m->devices.size());
+    const int R = (int)ranges.size();
+    std::vector<int> res(R, 1);
+    std::vector<std::thread> pool;
+    const size_t fb = (size_t)pitch * p->height;
+    for (int k = 0; k < R; k++)
+        pool.emplace_back([&, k]() {
+            const Range& rg = ranges[k];
+            scpr_codec* c = m->dec[k];
+            int r = scpr_reset(c);
+            if (r >= 0) r = scpr_decompress_clip(c, stream + off[rg.first], sizes + rg.first, ftypes + rg.first, rg.count, frames + (size_t)rg.first * fb, pitch);
+            res[k] = r;
+        });
+    for (auto& t : pool) t.join();
+    for (int k = 0; k < R; k++)
+        if (res[k] != 1) return res[k];
+    return 1;
+}
+
+}  // namespace
+
 extern "C" {
 
-int64_t scpr_compress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* frames, int n, const uint8_t* keyflags,
-                                 uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes, int* range_first, int* n_ranges) {
-    if (!p || !devices || n_dev < 1 || !frames || !keyflags || !dst || !sizes || !ftypes || n < 0) return SCPR_E_PARAM;
-    if (n == 0) return 0;
+int scpr_multi_create(const scpr_params* p, const int* devices, int n_dev, scpr_multi** out) {
+    if (!p || !devices || n_dev < 1 || !out) return SCPR_E_PARAM;
+    *out = nullptr;
     try {
         if (p->bits_per_pixel == 16) {
             set_error("frame-range splitting of 16 bpp clients is not built");
             return SCPR_E_UNSUPPORTED;
         }
-        const int bpp = p->bits_per_pixel / 8;
-        const size_t pitch = bpp == 3 ? (((size_t)p->width * 3 + 3) & ~(size_t)3) : (size_t)p->width * bpp;
-        const size_t fb = pitch * p->height;
-        std::vector<uint8_t> cuts(n, 0);
-        for (int f = 1; f < n; f++) cuts[f] = keyflags[f] && !host_frame_is_flat(*p, frames + (size_t)f * fb);
-        const std::vector<Range> ranges = plan_ranges(n, cuts, devices, n_dev);
-        const int R = (int)ranges.size();
-        if (n_ranges) *n_ranges = R;
-        if (range_first)
-            for (int k = 0; k < R; k++) range_first[k] = ranges[k].first;
-        Relay relay;
-        relay.ready.assign(R, 0);
-        relay.failed.assign(R, 0);
-        relay.codec.assign(R, nullptr);
-        std::vector<HookCtx> ctx(R);
-        std::vector<std::unique_ptr<uint8_t[]>> out(R);
-        std::vector<size_t> out_cap(R, 0);
-        std::vector<int64_t> used(R, 0);
-        for (int k = 0; k < R; k++) {
-            const int r = scpr_create(p, ranges[k].device, &relay.codec[k]);
+        std::unique_ptr<scpr_multi> m(new scpr_multi());
+        m->p = *p;
+        m->devices.assign(devices, devices + n_dev);
+        for (int k = 0; k < n_dev; k++) {
+            scpr_codec *e = nullptr, *d = nullptr;
+            int r = scpr_create(p, devices[k], &e);
+            if (r >= 0) {
+                m->enc.push_back(e);
+                r = scpr_create(p, devices[k], &d);
+            }
+            if (r >= 0) m->dec.push_back(d);
             if (r < 0) {
-                for (int q = 0; q < k; q++) scpr_destroy(relay.codec[q]);
+                for (auto c : m->enc) scpr_destroy(c);
+                for (auto c : m->dec) scpr_destroy(c);
                 return r;
             }
-            ctx[k].relay = &relay;
-            ctx[k].k = k;
-            scpr_set_mvs_hooks(relay.codec[k], hook_wait, hook_ready, &ctx[k]);
-            // worst case per frame is W*H*6 (CompressGetSize) but never more than the caller's whole buffer; the pages of an
-            // untouched new[] are not committed
-            size_t cap = (size_t)ranges[k].count * scpr_max_compressed_size(p);
-            if (cap > dst_cap) cap = dst_cap;
-            out_cap[k] = cap;
-            out[k].reset(new uint8_t[cap + 16]);
         }
-        std::vector<std::thread> pool;
-        for (int k = 0; k < R; k++)
-            pool.emplace_back([&, k]() {
-                const Range& rg = ranges[k];
-                std::vector<uint8_t> keys(keyflags + rg.first, keyflags + rg.first + rg.count);
-                keys[0] = 1;
-                // a fresh codec treats its first frame as a keyframe anyway; for k > 0 the cut guarantees the reference does too
-                int64_t r = scpr_compress_clip(relay.codec[k], frames + (size_t)rg.first * fb, rg.count, keys.data(), out[k].get(), out_cap[k],
-                                               sizes + rg.first, ftypes + rg.first);
-                if (r >= 0 && ctx[k].err) r = SCPR_E_CUDA;
-                used[k] = r;
-                if (r < 0) {
-                    {
-                        std::lock_guard<std::mutex> lk(relay.m);
-                        relay.failed[k] = 1;
-                    }
-                    relay.cv.notify_all();
-                }
-            });
-        for (auto& t : pool) t.join();
-        int64_t total = 0, err = 0;
-        for (int k = 0; k < R; k++) {
-            if (used[k] < 0 && !err) err = used[k];
-            if (used[k] > 0) total += used[k];
-        }
-        if (!err && (size_t)total > dst_cap) {
-            set_error("destination too small: need %lld bytes", (long long)total);
-            err = SCPR_E_DSTSIZE;
-        }
-        if (!err) {  // host-side concatenation in frame order
-            size_t pos = 0;
-            for (int k = 0; k < R; k++) {
-                memcpy(dst + pos, out[k].get(), (size_t)used[k]);
-                pos += (size_t)used[k];
-            }
-        }
-        for (int k = 0; k < R; k++) scpr_destroy(relay.codec[k]);
-        return err ? err : total;
+        *out = m.release();
+        return SCPR_OK;
     } catch (...) {
         set_error("out of memory");
         return SCPR_E_PARAM;
     }
 }
 
-int scpr_decompress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* stream, const uint32_t* sizes,
-                               const uint8_t* ftypes, int n, uint8_t* frames, int pitch) {
-    if (!p || !devices || n_dev < 1 || !stream || !sizes || !ftypes || !frames || n < 0) return SCPR_E_PARAM;
-    if (n == 0) return 1;
+void scpr_multi_destroy(scpr_multi* m) {
+    if (!m) return;
+    for (auto c : m->enc) scpr_destroy(c);
+    for (auto c : m->dec) scpr_destroy(c);
+    delete m;
+}
+
+int64_t scpr_multi_compress_clip(scpr_multi* m, const uint8_t* frames, int n, const uint8_t* keyflags, uint8_t* dst, size_t dst_cap, uint32_t* sizes,
+                                 uint8_t* ftypes, int* range_first, int* n_ranges) {
+    if (!m || !frames || !keyflags || !dst || !sizes || !ftypes || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 0;
     try {
-        // a range may start at any I frame that is not a flat frame (a flat frame's successors can be P frames on older models)
-        std::vector<uint8_t> cuts(n, 0);
-        std::vector<size_t> off(n + 1, 0);
-        for (int f = 0; f < n; f++) off[f + 1] = off[f] + sizes[f];
-        for (int f = 1; f < n; f++) cuts[f] = ftypes[f] == 0 && sizes[f] >= 1 && (stream[off[f]] & 0x0F) == 2;
-        const std::vector<Range> ranges = plan_ranges(n, cuts, devices, n_dev);
-        const int R = (int)ranges.size();
-        std::vector<int> res(R, 1);
-        std::vector<std::thread> pool;
-        const size_t fb = (size_t)pitch * p->height;
-        for (int k = 0; k < R; k++)
-            pool.emplace_back([&, k]() {
-                const Range& rg = ranges[k];
-                scpr_codec* c = nullptr;
-                int r = scpr_create(p, rg.device, &c);
-                if (r >= 0) r = scpr_decompress_clip(c, stream + off[rg.first], sizes + rg.first, ftypes + rg.first, rg.count, frames + (size_t)rg.first * fb, pitch);
-                if (c) scpr_destroy(c);
-                res[k] = r;
-            });
-        for (auto& t : pool) t.join();
-        for (int k = 0; k < R; k++)
-            if (res[k] != 1) return res[k];
-        return 1;
+        return multi_compress(m, frames, n, keyflags, dst, dst_cap, sizes, ftypes, range_first, n_ranges);
     } catch (...) {
         set_error("out of memory");
         return SCPR_E_PARAM;
     }
+}
+
+int scpr_multi_decompress_clip(scpr_multi* m, const uint8_t* stream, const uint32_t* sizes, const uint8_t* ftypes, int n, uint8_t* frames, int pitch) {
+    if (!m || !stream || !sizes || !ftypes || !frames || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 1;
+    try {
+        return multi_decompress(m, stream, sizes, ftypes, n, frames, pitch);
+    } catch (...) {
+        set_error("out of memory");
+        return SCPR_E_PARAM;
+    }
+}
+
+// one-shot forms: create the set, run, destroy
+int64_t scpr_compress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* frames, int n, const uint8_t* keyflags,
+                                 uint8_t* dst, size_t dst_cap, uint32_t* sizes, uint8_t* ftypes, int* range_first, int* n_ranges) {
+    if (!p || !devices || n_dev < 1 || !frames || !keyflags || !dst || !sizes || !ftypes || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 0;
+    scpr_multi* m = nullptr;
+    const int r = scpr_multi_create(p, devices, n_dev, &m);
+    if (r < 0) return r;
+    const int64_t used = scpr_multi_compress_clip(m, frames, n, keyflags, dst, dst_cap, sizes, ftypes, range_first, n_ranges);
+    scpr_multi_destroy(m);
+    return used;
+}
+
+int scpr_decompress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* stream, const uint32_t* sizes,
+                               const uint8_t* ftypes, int n, uint8_t* frames, int pitch) {
+    if (!p || !devices || n_dev < 1 || !stream || !sizes || !ftypes || !frames || n < 0) return SCPR_E_PARAM;
+    if (n == 0) return 1;
+    scpr_multi* m = nullptr;
+    int r = scpr_multi_create(p, devices, n_dev, &m);
+    if (r < 0) return r;
+    r = scpr_multi_decompress_clip(m, stream, sizes, ftypes, n, frames, pitch);
+    scpr_multi_destroy(m);
+    return r;
 }
 
 }  // extern "C"

@@ -531,6 +531,18 @@ def test_multi_device_entry_is_byte_identical(scpr):
         assert 30 not in firsts and all(keys[f] for f in firsts) and len(firsts) == min(len(devs), 4), (devs, firsts)
         out = scpr.decompress_clip_multi(params, devs, stream, sizes, fts)
         assert np.array_equal(out.reshape(n, -1), clip.reshape(n, -1)), devs
+    # the standing set (scpr_multi_*): several clips through the same objects
+    mc = scpr.MultiCodec(params, [0, 0, 0])
+    flat = np.ascontiguousarray(clip.reshape(-1))
+    out = np.zeros_like(flat)
+    for rep in range(3):
+        src = flat if rep != 1 else np.ascontiguousarray(clip[::-1].reshape(-1))   # another clip in between
+        stream, sizes, fts, firsts = mc.compress_clip(src.ctypes.data, keys)
+        if rep != 1:
+            assert np.array_equal(stream, want[0]) and np.array_equal(sizes, want[1]) and np.array_equal(fts, want[2]), rep
+        mc.decompress_clip(stream.copy(), sizes, fts, out.ctypes.data)
+        assert np.array_equal(out, src), rep
+    mc.close()
 
 
 def test_cpp_facade_driven_like_the_vfw_layer(scpr, oracle_built, tmp_path):
