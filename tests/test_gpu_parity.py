@@ -623,6 +623,24 @@ def test_threads_layout_matches_multithreaded_reference_i_frames(scpr, oracle_bu
         bad.set_threads_layout(0)
 
 
+def test_threads_layout_matches_committed_reference_digests(scpr):
+    """the same against the committed fixture (tests/golden/ref_threads_digests.json, written by make_threads_golden.py from the
+    unmodified reference with 1, 2, 3, 5, 8 worker threads): does not need oracle/_ref on the box"""
+    import json
+    import os
+
+    with open(os.path.join(_golden.GOLDEN_DIR, "ref_threads_digests.json")) as f:
+        fixture = json.load(f)
+    for name, entry in fixture.items():
+        w, h, bpp, n, seed = entry["args"]
+        clip = band_clip(w, h, n, seed, bpp)
+        for threads, rows in entry["threads"].items():
+            enc = _new(scpr, w, h, bpp)
+            enc.set_threads_layout(int(threads))
+            produced = _split(*enc.CompressClip(clip, np.ones(n, np.uint8)))
+            _golden.check_frames(f"{name} threads={threads}", rows, produced)
+
+
 def test_full_state_checkpoint_resume_at_any_frame(scpr):
     """full = 1: previous frame + adaptive models + mvs[]; an encode resumed in another codec object continues byte-exactly"""
     w, h, n = 200, 120, 30
