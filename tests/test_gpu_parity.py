@@ -236,6 +236,34 @@ def test_tma_frame_scan_equals_plain_load_scan(scpr, size):
         assert np.array_equal(sm2[:, 2], px[:, 0, 0])
 
 
+def test_maximum_frame_size_matches_reference(scpr, oracle_built):
+    """4096 x 4096 = 65 536 blocks, the most the format can address (the changed range of a P frame is two 16-bit block indices,
+    screencap.cpp:1145-1150): an I frame, a P frame that scrolls the lower half (motion vectors up to the last block) and
+    touches the first and the last pixel, a duplicate.  Bytes against the reference, decode bit-exact.  One block more is refused."""
+    w = h = 4096
+    clip = band_clip(w, h, 1, 4096, 32)
+    f0 = clip[0]
+    f1 = f0.copy()
+    f1[h // 2:, :, :3] = np.roll(f0[h // 2:, :, :3], -16, axis=0)
+    f1[0, 0, :3] ^= 0x5A
+    f1[h - 1, w - 1, :3] ^= 0xA5
+    frames = np.stack([f0, f1, f1])
+    keys = np.array([1, 0, 0], np.uint8)
+    ref = oracle_built.RefCodec(w, h, 32) if oracle_built.have_ref() else oracle_built.OracleCodec(w, h, 32)
+    want = [ref.compress(np.ascontiguousarray(frames[i]).reshape(-1).copy(), i > 0) for i in range(3)]
+    enc = _new(scpr, w, h, 32)
+    got = _split(*enc.CompressClip(frames, keys))
+    assert [g[1] for g in got] == [x[1] for x in want]
+    assert got == want, [i for i in range(3) if got[i] != want[i]]
+    assert len(want[2][0]) == 1          # the duplicate is a one-byte frame
+    dec = _new(scpr, w, h, 32)
+    for i in range(3):
+        assert np.array_equal(dec.DecompressFrame(want[i][0], None, want[i][1]), frames[i].reshape(-1)), i
+    sc = scpr.ScreenCodec(0)
+    with pytest.raises(scpr.ScprError):
+        sc.Init(scpr.CodecParameters(4096 + 16, 4096, 32))
+
+
 def test_full_size_round_trip_properties(scpr):
     """BASELINE configs at full resolution, more frames than the oracle could check in seconds:
     decode(encode(x)) == x, duplicate frames cost one byte, flat frames four."""
