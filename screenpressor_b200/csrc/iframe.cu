@@ -242,30 +242,40 @@ __device__ __forceinline__ void emit_literal_i(uint32_t* ev, uint32_t c, uint32_
 }
 
 // k_i_emit_hdr: RGB(pixel 0), then (N, RGB) per run break, final N -- all lengths in ntab[0].
+// The walk over pixels 1..X is serial (the 255 cap), but its loads need not be: the warp stages 2048 pixels at a time in shared
+// memory (coalesced), lane 0 walks them there (one global round trip per pixel before: 318 us per 1080p I frame).
 __global__ void __launch_bounds__(32) k_i_emit_hdr(IWork w) {
-    const int fi = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    __shared__ uint32_t s_px[2048];
+    const int fi = blockIdx.x, lane = threadIdx.x;
     const Geo& g = w.g;
     const int frame = w.hdr[fi].frame;
     const uint8_t* f = w.frames + (size_t)frame * g.frame_bytes;
     uint32_t* ev = w.events + w.frame_ev_off[frame];
     uint32_t prev = px_lin(f, g, 0);
-    emit_literal_i(ev, prev, 0, false);
+    if (lane == 0) emit_literal_i(ev, prev, 0, false);
     ev += 3;
     int n = 1;
-    for (int k = 1; k <= g.X; k++) {
-        const uint32_t c = px_lin(f, g, k);
-        if (c == prev && n < 255)
-            n++;
-        else {
-            *ev++ = make_ev(CX_NTAB + 0, n);
-            emit_literal_i(ev, c, prev, true);
-            ev += 3;
-            n = 1;
+    for (int k0 = 1; k0 <= g.X; k0 += 2048) {
+        const int cnt = min(2048, g.X + 1 - k0);
+        for (int i = lane; i < cnt; i += 32) s_px[i] = px_lin(f, g, k0 + i);
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < cnt; i++) {
+                const uint32_t c = s_px[i];
+                if (c == prev && n < 255)
+                    n++;
+                else {
+                    *ev++ = make_ev(CX_NTAB + 0, n);
+                    emit_literal_i(ev, c, prev, true);
+                    ev += 3;
+                    n = 1;
+                }
+                prev = c;
+            }
         }
-        prev = c;
+        __syncwarp();
     }
-    *ev = make_ev(CX_NTAB + 0, n);
+    if (lane == 0) *ev = make_ev(CX_NTAB + 0, n);
 }
 
 // k_i_emit: events of the runs of one chunk.  grid = (nchunks, n_iframes), 256 threads, 8 runs each.

@@ -403,18 +403,33 @@ __global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
     const int hw = (warp & 3) ? warp - 1 - (warp >> 2) : -1;
     if (hw >= 0 && w.n_pframes > 0) mv_speculate<SMV>(w, s_mvs, 0, hw, nh, lane);
     __syncthreads();
+    // the frame's header words (frame index, block count, offset, candidates) are fetched one frame ahead: three dependent global
+    // round trips per frame otherwise sit in front of warp 0's first step
+    int nf = 0, nnchg = 0, noff = 0, nnc = 0, ncand = 0;
+    if (warp == 0 && w.n_pframes > 0) {
+        nf = w.pframes[0];
+        nnchg = w.hdr[nf].n_changed;
+        noff = w.hdr[nf].chg_off;
+        nnc = w.ncands[0];
+        ncand = w.cands[lane];
+    }
     for (int pi = 0; pi < w.n_pframes; pi++) {
         if (warp != 0) {
             if (hw >= 0 && pi + 1 < w.n_pframes) mv_speculate<SMV>(w, s_mvs, pi + 1, hw, nh, lane);
             __syncthreads();
             continue;
         }
-        const int f = w.pframes[pi];
-        const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
+        const int f = nf, nchg = nnchg, off = noff, nc = nnc;
+        const int cand = ncand;  // lane k: candidate k
+        if (pi + 1 < w.n_pframes) {
+            nf = w.pframes[pi + 1];
+            nnchg = w.hdr[nf].n_changed;
+            noff = w.hdr[nf].chg_off;
+            nnc = w.ncands[pi + 1];
+            ncand = w.cands[(size_t)(pi + 1) * MAXC + lane];
+        }
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
         const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
-        const int nc = w.ncands[pi];
-        const int cand = w.cands[(size_t)pi * MAXC + lane];  // lane k: candidate k
         int lv = 0, lidx = -1;   // last_mv (packed) and its index in the candidate list (-1: (0,0), -2: not listed)
         int cv = 0;              // last coded MV (lastmx/lastmy of CompressP, screencap.cpp:1177)
         int prev_nonmv = -1;

@@ -20,10 +20,11 @@ constexpr int RTILE = 1024;
 
 __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__ intervals, RansBlk* __restrict__ blks,
                                                     uint8_t* __restrict__ scratch) {
-    // per interval, everything the serial lane needs that does not depend on the state, as one 64-bit operand:
-    //   .x = reciprocal m;  .y = (4096 - freq) << 18 | shift << 13 | bias, bias = start (+ 4095 for freq 1, see below).
-    //   x_max = freq << 19 is recovered from .y; freq 0 (raw byte, .y = 4096 << 18 | byte) gives x_max = 0.
-    __shared__ uint2 s_op[RTILE];
+    // per interval, everything the serial lane needs that does not depend on the state, as one 128-bit operand (one shared load,
+    // no field extraction on the serial path -- a lone lane pays ~4 cycles per instruction whatever it does):
+    //   .x = reciprocal m;  .y = x_max = freq << 19 (0: raw byte);  .z = bias = start (+ 4095 for freq 1, see below; the byte for a raw
+    //   one);  .w = (4096 - freq) | shift << 16.
+    __shared__ uint4 s_op[RTILE];
     __shared__ uint8_t s_out[2 * RTILE + 8];
     const int lane = threadIdx.x;
     RansBlk& blk = blks[blockIdx.x];
@@ -48,19 +49,18 @@ __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__
                 m = 0xFFFFFFFFu;
                 bias = start + 4095u;
             }
-            s_op[i] = make_uint2(m, (((1u << PROB_BITS) - f) << 18) | (f ? (sh << 13) | bias : start));
+            s_op[i] = make_uint4(m, f << 19, f ? bias : start, (((1u << PROB_BITS) - f) & 0xFFFFu) | (sh << 16));
         }
         __syncwarp();
         int nout = 0;
         if (lane == 0) {
             int pi = (int)sizeof(s_out);  // write index into s_out, moves down
-            uint2 op = s_op[cnt - 1];
+            uint4 op = s_op[cnt - 1];
 #pragma unroll 4
             for (int i = cnt - 1; i >= 0; i--) {
                 // the next interval's operand is fetched before this state update (it does not depend on x)
-                const uint2 nx = s_op[i > 0 ? i - 1 : 0];
-                const uint32_t cmpl = op.y >> 18;
-                const uint32_t xmax = ((1u << PROB_BITS) - cmpl) << 19;
+                const uint4 nx = s_op[i > 0 ? i - 1 : 0];
+                const uint32_t xmax = op.y;
                 if (xmax) {
                     // RansEncRenorm (rans_byte.h:59-71) without branches: the state is below 2^31 and x_max at least
                     // 2^19, so at most two bytes leave; both are stored, the cursor moves by the number that count
@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(32) k_rans_encode(const uint32_t* __restrict__
                     pi -= r1 + r2;
                     x = r2 ? (x >> 16) : (r1 ? x8 : x);
                     // RansEncPut (rans_byte.h:76-84): (q << 12) + (x - q * freq) + start
-                    const uint32_t q = __umulhi(x, op.x) >> ((op.y >> 13) & 31);
-                    x = x + (op.y & 0x1FFFu) + q * cmpl;
+                    const uint32_t q = __umulhi(x, op.x) >> (op.w >> 16);
+                    x = x + op.z + q * (op.w & 0xFFFFu);
                 } else
-                    s_out[--pi] = (uint8_t)op.y;  // raw byte, ransmt.h:127-128
+                    s_out[--pi] = (uint8_t)op.z;  // raw byte, ransmt.h:127-128
                 op = nx;
             }
             if (lo == 0) {  // RansEncFlush, rans_byte.h:87-100
