@@ -183,6 +183,11 @@ void scpr_destroy(scpr_codec* c) {
     if (c->dec_progress) cudaFreeHost((void*)c->dec_progress);
     for (cudaEvent_t e : c->copy_ev) cudaEventDestroy(e);
     if (c->copy_st) cudaStreamDestroy(c->copy_st);
+    if (c->aux_st) {
+        cudaStreamDestroy(c->aux_st);
+        cudaEventDestroy(c->aux_fork);
+        cudaEventDestroy(c->aux_join);
+    }
     delete c;
 }
 
@@ -506,6 +511,12 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         rw.states = (uint8_t*)c->states.p; rw.f0 = 32;
         rw.sorted = (uint32_t*)c->sorted.p; rw.sorted_sym = (uint16_t*)c->sorted_sym.p; rw.seg_off = (uint32_t*)c->seg_off.p; rw.chunk_hist = (uint32_t*)c->chunk_hist.p;
         rw.chunk_base = (const uint32_t*)c->chunk_base.p; rw.total_events = total_ev; rw.tm = &tm;
+        if (!c->aux_st) {
+            CK(cudaStreamCreateWithFlags(&c->aux_st, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->aux_join, cudaEventDisableTiming));
+        }
+        rw.aux = c->aux_st; rw.fork = c->aux_fork; rw.join = c->aux_join;
         launch_replay(rw, st, &c->launches);
         tm.mark("replay");
         CK(cudaStreamSynchronize(st));  // `cb` and `chains` are host vectors read by the async copies above
@@ -567,7 +578,8 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
     tm.mark("assemble+d2h");
     CK(cudaStreamSynchronize(st));
     hmark(4);
-    if (tm.on)
+    static const bool host_wall = getenv("SCPR_HOSTWALL") != nullptr;  // the same without the stage events (no stage serialisation)
+    if (tm.on || host_wall)
         fprintf(stderr, "[scpr timing] encode_batch host wall: scan+sync %.3f | stage A+sync %.3f | replay+sync %.3f | rans+sync %.3f | out+sync %.3f ms\n",
                 hw[0], hw[1] - hw[0], hw[2] ? hw[2] - hw[1] : 0.0, hw[3] - (hw[2] ? hw[2] : hw[1]), hw[4] - hw[3]);
     tm.report("encode_batch");

@@ -34,6 +34,8 @@ struct scpr_codec {
     cudaStream_t st = 0;
     cudaStream_t copy_st = nullptr;         // uploads of host frames, overlapped with the kernels (scpr_compress_clip)
     std::vector<cudaEvent_t> copy_ev;
+    cudaStream_t aux_st = nullptr;          // second lane for independent kernels of one call (fixed-table replay beside the colour replay)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     scpr::Geo g;                     // geometry of the resident frames (16 bpp clients: the RGB24 image the codec works on)
     bool rgb16 = false;              // the caller's frames are 16 bpp (converted on the device on the way in and out)
     scpr::Rgb16 m16 = {0, 0, 0, 0, 0, 0};

@@ -137,6 +137,9 @@ struct ReplayWork {
     uint32_t* sorted; uint16_t* sorted_sym; uint32_t* seg_off; uint32_t* chunk_hist; const uint32_t* chunk_base;
     uint32_t total_events;
     struct StageTimer* tm;
+    // optional second stream: the 21 fixed tables replay there while the colour contexts replay on the main stream (disjoint
+    // contexts, disjoint interval slots); fork / join are events owned by the caller
+    cudaStream_t aux; cudaEvent_t fork, join;
 };
 size_t replay_hist_entries(uint32_t n_ev);     // u32 entries of chunk_hist needed for a chain of n_ev events
 size_t build_sort_chunks(const ChainDesc* chains, int n_chains, uint32_t* out);  // host image of chunk_base; returns words

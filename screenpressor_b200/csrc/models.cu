@@ -10,6 +10,8 @@
 //     table look-ups + a shared-memory histogram + one table rebuild (warp scan);
 //   * the 12288 colour contexts: one thread per context walking the Cx1..Cx7 state machine.
 // Intervals are scattered back to bitstream order for the rANS stage.
+#include <stdlib.h>
+
 #include "codec.h"
 #include "models.cuh"
 
@@ -468,9 +470,21 @@ void launch_replay(const ReplayWork& w, cudaStream_t st, uint64_t* launches) {
         ++*launches;
     }
     if (w.tm) w.tm->mark("sort");
-    k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, st>>>(w, w.seg_off);
-    if (w.tm) w.tm->mark("fixed");
-    k_replay_color<<<dim3(NUM_COLOR_CX / 4, w.n_chains), 128, 0, st>>>(w, w.seg_off);
+    const bool timing = w.tm && w.tm->on;
+    static const bool no_aux = []() { const char* e = getenv("SCPR_AUX"); return e && e[0] == '0'; }();  // SCPR_AUX=0: one stream (A/B runs)
+    if (w.aux && !timing && !no_aux) {
+        // k_replay_fixed is 21 warps per chain with long serial epochs: it runs beside the colour replay instead of in front of it
+        cudaEventRecord(w.fork, st);
+        cudaStreamWaitEvent(w.aux, w.fork, 0);
+        k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, w.aux>>>(w, w.seg_off);
+        cudaEventRecord(w.join, w.aux);
+        k_replay_color<<<dim3(NUM_COLOR_CX / 4, w.n_chains), 128, 0, st>>>(w, w.seg_off);
+        cudaStreamWaitEvent(st, w.join, 0);
+    } else {
+        k_replay_fixed<<<dim3(NUM_FIXED_CX, w.n_chains), 32, 0, st>>>(w, w.seg_off);
+        if (w.tm) w.tm->mark("fixed");
+        k_replay_color<<<dim3(NUM_COLOR_CX / 4, w.n_chains), 128, 0, st>>>(w, w.seg_off);
+    }
     *launches += 2;
 }
 
