@@ -187,6 +187,12 @@ constexpr uint32_t S_TILE = S_KMAP + NUM_COLOR_CX;       // u32[17][17]
 constexpr uint32_t S_CTAG = S_TILE + 1168;               // u32[NCACHE]: context id held by a cache entry (~0 = none)
 constexpr uint32_t S_CHDR = S_CTAG + NCACHE * 4;         // uint2[NCACHE]: totFr | maxpos<<16 | d<<20 | shift<<28, bonus | sfreq[maxpos]<<16
 constexpr uint32_t S_CENT = S_CHDR + NCACHE * 8;         // u32[NCACHE][16]: entry k = ssym | sfreq << 8 | start << 20
+#ifndef SCPR_RECON_NAP
+#define SCPR_RECON_NAP 0         // ns slept per empty look of the idle reconstruction warp (0: spin)
+#endif
+#ifndef SCPR_COPY_BACKOFF
+#define SCPR_COPY_BACKOFF 2048  // longest sleep (ns) of an idle copy warp between two looks at its ring slot
+#endif
 constexpr int RING = 256;                                // MV-copy commands in flight (see "helper warps" below)
 constexpr uint32_t S_RING = S_CENT + NCACHE * 64;        // uint4[RING]
 constexpr uint32_t S_SYNC = S_RING + RING * 16;          // u32: head, next, done, quit
@@ -1484,7 +1490,7 @@ __device__ void helper_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t 
             }
             if (ldv_shared(sy + 12)) return;  // quit is only raised after a drain: nothing posted is left behind
             __nanosleep(ns);
-            ns = min(ns * 2u, 2048u);
+            ns = min(ns * 2u, (uint32_t)SCPR_COPY_BACKOFF);
         }
         mv_copy<SM>(w, map, (int)(cmd.x >> 16), (int)(cmd.x & 0xFFFFu), cmd.y, (int)(int16_t)(cmd.z & 0xFFFFu), (int)(int16_t)(cmd.z >> 16), lane);
         __threadfence_block();
@@ -1687,6 +1693,9 @@ __device__ void recon_loop(const DecWork& w, const BlockMap<SM>& map, uint32_t s
 #endif
                 break;
             }
+#if SCPR_RECON_NAP > 0
+            if (spins >= 2u) __nanosleep(SCPR_RECON_NAP);  // an idle poll loop takes shared-memory bandwidth from the chain warp
+#endif
             if (spins == 0u && rdone != ridx) {  // nothing waiting: let the chain warp see how far this warp has come (drains)
                 __threadfence_block();
                 stv_shared(rs + 4, ridx);
