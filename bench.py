@@ -619,6 +619,7 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         c.set_stream(stream.cuda_stream)
     enc.reserve_clip_output(64 << 20)
     stage = {"enc": 0.0, "dec": 0.0}
+    relay_stats = {}
 
     def one_step(host: bool):
         """every rank: encode its range (the mvs[] blob arrives before / leaves after its in-order resolve), decode it again"""
@@ -628,7 +629,8 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         if host:
             rng, s, sizes, fts = shard.encode_sharded(enc, h_in.numpy()[:n_mine * fb] if n_mine else None, keys, rank, world, dist)
         else:
-            rng, s, sizes, fts = shard.encode_sharded(enc, None, keys, rank, world, dist, device_ptr=d_in.data_ptr() if n_mine else None)
+            rng, s, sizes, fts = shard.encode_sharded(enc, None, keys, rank, world, dist, device_ptr=d_in.data_ptr() if n_mine else None,
+                                                      stats=relay_stats)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if n_mine:
@@ -668,7 +670,9 @@ def run_cuda_split(args, torch, dist, world, rank, local):
     if rank == 0:
         sampler.start()
     l0 = enc.kernel_launches() + dec.kernel_launches()
+    relay_stats.clear()
     (ms, enc_ms, dec_ms), (rng, s, sizes, fts) = timed(False, args.steps)
+    my_relay = {k: round(v / args.steps, 3) for k, v in relay_stats.items() if not k.startswith("_")}
     launches = enc.kernel_launches() + dec.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     (ms_e2e, e2e_enc_ms, e2e_dec_ms), (_, s2, sizes2, _) = timed(True, args.steps)
@@ -677,7 +681,7 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         assert np.array_equal(s2, s), "host-buffer stream differs from the device-resident one"
     # host-side concatenation on rank 0
     parts = [None] * world
-    dist.gather_object((rng, np.array(s), np.array(sizes), np.array(fts)), parts if rank == 0 else None, dst=0)
+    dist.gather_object((rng, np.array(s), np.array(sizes), np.array(fts), my_relay), parts if rank == 0 else None, dst=0)
     if rank != 0:
         # leave the GPU to rank 0's one-process leg: free this rank's device buffers and wait on the CPU
         del d_in, d_out, enc, dec
@@ -685,7 +689,8 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         dist.barrier(group=cpu_group)
         dist.destroy_process_group()
         return
-    cs, csz, cft = shard.gather_streams(parts)
+    relay = [p[4] for p in parts]
+    cs, csz, cft = shard.gather_streams([p[:4] for p in parts])
     # the same clip on this rank's GPU alone: the single-GPU stream (parity) and the single-GPU time (what N ranks are set against)
     del d_in, d_out
     torch.cuda.empty_cache()
@@ -762,6 +767,7 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         "encode_fps": frames * args.steps / (enc_ms / 1e3), "decode_fps": frames * args.steps / (dec_ms / 1e3),
         "mpix_per_s": value * W * H / 1e6,
         "single_gpu": single,
+        "encode_relay_ms_per_rank": relay,
         "one_process": one_process,
         "e2e": {"value": frames * args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": frames * fb + stream_bytes,
                 "d2h_bytes_per_step": frames * fb + stream_bytes, "ms_per_step": ms_e2e / args.steps,

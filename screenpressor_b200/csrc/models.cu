@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32
     while (i < m) {
         const int kind = x.kind;
         // this step's events: lane t holds event i + t
-        const bool valid = i + lane < m;
+        bool valid = i + lane < m;
         uint32_t idx = 0;
         int c = -1;
         if (valid) {
@@ -292,20 +292,26 @@ __global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32
             c = (int)(w.sorted_sym[pos0 + i + lane] & 0xFFu);
         }
         if (kind == 4 || kind == 5) {
-            const int d = x.d, maxpos = x.maxpos;
+            // The context's sorted list (<= 16 symbols, their frequencies, maxpos, the running total) stays in registers from step
+            // to step and goes back to the canonical state once, when the steps end (events exhausted, or a symbol the list
+            // does not hold yet): a step used to begin and end with a round trip to the ColorState in global memory.
+            const int d = x.d;
+            int maxpos = x.maxpos;
             const int ls = lane < d ? x.ssym[lane] : -1;            // lane k: symbol k
-            const int lf = lane < d ? x.sfreq[lane] : 0;            //         and its frequency
+            int lf = lane < d ? x.sfreq[lane] : 0;                  //         and its frequency
             int tot = x.cntsum;
-            if (kind == 4) tot = 256 - d + (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)lf);  // ans_contexts.h:303
-            // position of each event's symbol
-            int pos = -1;
-            for (int k = 0; k < d; k++)
-                if (__shfl_sync(0xFFFFFFFFu, ls, k) == c) pos = k;
-            const uint32_t bad = __ballot_sync(0xFFFFFFFFu, !valid || pos < 0);
-            int B = bad ? __ffs(bad) - 1 : 32;                                   // (a) new symbol / end of events
-            const int kR = tot + 100 > PROB_SCALE ? 0 : (PROB_SCALE - 100 - tot) / 50 + 1;
-            B = min(B, kR + 1);                                                  // (b) rescale after event kR
-            if (B > 0) {
+            bool stepped = false;
+            for (;;) {
+                if (kind == 4) tot = 256 - d + (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)lf);  // ans_contexts.h:303
+                // position of each event's symbol
+                int pos = -1;
+                for (int k = 0; k < d; k++)
+                    if (__shfl_sync(0xFFFFFFFFu, ls, k) == c) pos = k;
+                const uint32_t bad = __ballot_sync(0xFFFFFFFFu, !valid || pos < 0);
+                int B = bad ? __ffs(bad) - 1 : 32;                                   // (a) new symbol / end of events
+                const int kR = tot + 100 > PROB_SCALE ? 0 : (PROB_SCALE - 100 - tot) / 50 + 1;
+                B = min(B, kR + 1);                                                  // (b) rescale after event kR
+                if (B <= 0) break;
                 const uint32_t same = __match_any_sync(0xFFFFFFFFu, pos);
                 const int cnt_same = __popc(same & lt);                          // earlier events with my symbol
                 const int fpos = __shfl_sync(0xFFFFFFFFu, lf, pos < 0 ? 0 : pos);
@@ -351,12 +357,26 @@ __global__ void __launch_bounds__(128) k_replay_color(ReplayWork w, const uint32
                     nf -= nf >> 1;
                     tot = 256 - d + (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)(lane < d ? nf : 0));
                 }
-                if (lane < d) x.sfreq[lane] = (uint16_t)nf;
+                if (lane < d) lf = nf;
+                maxpos = newmax;
+                stepped = true;
+                i += B;
+                if (i >= m) break;
+                // the next step's events
+                valid = i + lane < m;
+                idx = 0;
+                c = -1;
+                if (valid) {
+                    idx = w.sorted[pos0 + i + lane];
+                    c = (int)(w.sorted_sym[pos0 + i + lane] & 0xFFu);
+                }
+            }
+            if (stepped) {
+                if (lane < d) x.sfreq[lane] = (uint16_t)lf;
                 if (lane == 0) {
-                    x.maxpos = (uint8_t)newmax;
+                    x.maxpos = (uint8_t)maxpos;
                     if (kind == 5) x.cntsum = tot;
                 }
-                i += B;
                 __syncwarp();
                 continue;
             }

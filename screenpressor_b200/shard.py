@@ -76,7 +76,7 @@ def assign_ranges(keyflags: np.ndarray, world: int, not_cuttable=()) -> list[Fra
 
 
 def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, dist=None, device_ptr=None, pipelined: bool = True,
-                   not_cuttable=()):
+                   not_cuttable=(), stats: dict | None = None):
     """Encode this rank's range of the clip.  `frames`: this rank's frames only (host ndarray, or None with a device
     pointer).  Returns (FrameRange | None, stream, sizes, ftypes) for the range.  `dist` = torch.distributed (already
     initialised) or None for a single process; the mvs[] blob travels rank -> rank + 1.
@@ -93,15 +93,37 @@ def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, d
     blob_len = len(codec.ExportRangeState(False))
     has_prev, has_next = rank > 0 and dist is not None, dist is not None and rank + 1 < len(ranges)
 
+    import time
+    t_call = time.perf_counter()
+
+    def note(key, t0):
+        if stats is not None:
+            stats[key] = stats.get(key, 0.0) + (time.perf_counter() - t0) * 1e3
+
     def recv_blob():
+        if stats is not None:
+            stats["to_resolve_ms"] = stats.get("to_resolve_ms", 0.0) + (time.perf_counter() - t_call) * 1e3
         if has_prev:
+            t0 = time.perf_counter()
             t = torch.empty(blob_len, dtype=torch.uint8)
             dist.recv(t, src=rank - 1)
+            note("recv_wait_ms", t0)
+            t0 = time.perf_counter()
             codec.ImportRangeState(t.numpy())
+            note("import_ms", t0)
+        if stats is not None:
+            stats["_t_resolve"] = time.perf_counter()
 
     def send_blob():
+        if stats is not None and "_t_resolve" in stats:
+            stats["resolve_ms"] = stats.get("resolve_ms", 0.0) + (time.perf_counter() - stats.pop("_t_resolve")) * 1e3
         if has_next:
-            dist.send(torch.from_numpy(np.ascontiguousarray(codec.ExportRangeState(False)).copy()), dst=rank + 1)
+            t0 = time.perf_counter()
+            blob = torch.from_numpy(np.ascontiguousarray(codec.ExportRangeState(False)).copy())
+            note("export_ms", t0)
+            t0 = time.perf_counter()
+            dist.send(blob, dst=rank + 1)
+            note("send_ms", t0)
 
     keys = np.array(keyflags[mine.first:mine.first + mine.count], dtype=np.uint8)
     keys[0] = 1
@@ -115,6 +137,7 @@ def encode_sharded(codec, frames, keyflags: np.ndarray, rank: int, world: int, d
         recv_blob()
         stream, sizes, ftypes = codec.CompressClip(frames, keys, device_ptr=device_ptr, n=mine.count)
         send_blob()
+    note("call_ms", t_call)
     return mine, stream, sizes, ftypes
 
 
