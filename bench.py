@@ -660,6 +660,41 @@ def run_cuda_split(args, torch, dist, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(x) for x in t.tolist()], res
 
+    def timed_phases(host: bool, steps: int):
+        """encode and decode rates with the ranks in step: a barrier in front of each phase, so that a rank does not count the
+        time it waits for a neighbour that is still decoding the previous step as encode time (the ranks' GOPs differ, their
+        decode times with them).  -> [encode ms, decode ms] per `steps`, max over ranks, device events."""
+        tot = torch.zeros(2, device="cuda")
+        for _ in range(steps):
+            enc.Reset()
+            dec.Reset()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev[0].record(stream)
+            if host:
+                rng_, s_, sizes_, fts_ = shard.encode_sharded(enc, h_in.numpy()[:n_mine * fb] if n_mine else None, keys, rank, world, dist)
+            else:
+                rng_, s_, sizes_, fts_ = shard.encode_sharded(enc, None, keys, rank, world, dist, device_ptr=d_in.data_ptr() if n_mine else None,
+                                                              stats=relay_stats)
+            ev[1].record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev[2].record(stream)
+            if n_mine:
+                if host:
+                    r = dec._lib.scpr_decompress_clip(dec._h, s_.ctypes.data, sizes_.ctypes.data, fts_.ctypes.data, n_mine, h_out.data_ptr(), W * 4)
+                    assert r == 1, r
+                else:
+                    dec.DecompressClip(s_, sizes_, fts_, device_ptr=d_out.data_ptr())
+            ev[3].record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot += t
+        return [float(x) for x in tot.tolist()]
+
     # correctness gate + warm-up
     rng, s, sizes, fts = one_step(False)
     if n_mine:
@@ -670,12 +705,15 @@ def run_cuda_split(args, torch, dist, world, rank, local):
     if rank == 0:
         sampler.start()
     l0 = enc.kernel_launches() + dec.kernel_launches()
-    relay_stats.clear()
-    (ms, enc_ms, dec_ms), (rng, s, sizes, fts) = timed(False, args.steps)
-    my_relay = {k: round(v / args.steps, 3) for k, v in relay_stats.items() if not k.startswith("_")}
+    (ms, _, _), (rng, s, sizes, fts) = timed(False, args.steps)
     launches = enc.kernel_launches() + dec.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
-    (ms_e2e, e2e_enc_ms, e2e_dec_ms), (_, s2, sizes2, _) = timed(True, args.steps)
+    (ms_e2e, _, _), (_, s2, sizes2, _) = timed(True, args.steps)
+    # the split of a step into its encode and its decode phase, ranks in step
+    relay_stats.clear()
+    enc_ms, dec_ms = timed_phases(False, args.steps)
+    my_relay = {k: round(v / args.steps, 3) for k, v in relay_stats.items() if not k.startswith("_")}
+    e2e_enc_ms, e2e_dec_ms = timed_phases(True, args.steps)
     if n_mine:
         assert np.array_equal(h_out.numpy()[:n_mine * fb], h_in.numpy()[:n_mine * fb]), "host-buffer decode(encode(range)) != range"
         assert np.array_equal(s2, s), "host-buffer stream differs from the device-resident one"
@@ -766,6 +804,8 @@ def run_cuda_split(args, torch, dist, world, rank, local):
                    "tests/golden and the N = 1 bench line)", "stream_md5": hashlib.md5(cs.tobytes()).hexdigest()},
         "encode_fps": frames * args.steps / (enc_ms / 1e3), "decode_fps": frames * args.steps / (dec_ms / 1e3),
         "mpix_per_s": value * W * H / 1e6,
+        "phases": "encode_fps / decode_fps (also inside e2e): extra steps with a barrier in front of each phase so that the ranks are in step, "
+                  "max over ranks, device events; value and e2e.value: free-running steps (a rank may decode while its successor still encodes)",
         "single_gpu": single,
         "encode_relay_ms_per_rank": relay,
         "one_process": one_process,

@@ -210,6 +210,7 @@ __device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& w
 // lane k keeps candidate k.  Also records each block's index into that list (fidx, 0xFF = none).
 // ------------------------------------------------------------------------------------------------
 constexpr int MAXC = 32;
+__device__ unsigned long long g_mv_stats2[4];  // frames whose own list is full, blocks with an unlisted F, lidx == -2 steps, -
 __device__ unsigned long long g_mv_stats[4];  // steps, c1 direct compares, c2 direct compares, blocks (-DSCPR_MVSTATS builds only)
 #ifdef SCPR_MVSTATS
 #define MV_STAT(...) __VA_ARGS__
@@ -247,7 +248,12 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
             todo &= ~same;
         }
         if (k < nchg) w.blocks[off + k].fidx = (uint8_t)myidx;
+        MV_STAT({
+            const uint32_t un = __ballot_sync(0xFFFFFFFFu, k < nchg && fv != 0x7FFFFFFF && myidx == 0xFF);
+            if (lane == 0 && un) atomicAdd(&g_mv_stats2[1], (unsigned long long)__popc(un));
+        })
     }
+    MV_STAT(if (lane == 0 && ncand == MAXC) atomicAdd(&g_mv_stats2[0], 1ull);)
     w.cands0[(size_t)blockIdx.x * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
     if (lane == 0) w.ncands0[blockIdx.x] = ncand;
 }
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
             if (lidx >= 0)
                 found = in && ((mmask >> lidx) & 1);
             else if (lidx == -2) {  // last_mv is not in the candidate list: direct compares, lane by lane
-                MV_STAT(if (lane == 0) atomicAdd(&g_mv_stats[1], (unsigned long long)cnt);)
+                MV_STAT(if (lane == 0) { atomicAdd(&g_mv_stats[1], (unsigned long long)cnt); atomicAdd(&g_mv_stats2[2], 1ull); })
                 for (int i = 0; i < cnt; i++) {
                     const SubRect r = subrect_of(__shfl_sync(0xFFFFFFFFu, bi, i), __shfl_sync(0xFFFFFFFFu, info, i), g);
                     const Windows win = windows_of(r, g);
@@ -846,7 +852,11 @@ void mv_stats_report() {
     unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
     cudaMemcpyFromSymbol(h, g_mv_stats, sizeof(h));
     cudaMemcpyToSymbol(g_mv_stats, z, sizeof(z));
-    fprintf(stderr, "[scpr timing] mv_resolve: %llu blocks in %llu steps, direct compares: last_mv %llu, upper %llu\n", h[3], h[0], h[1], h[2]);
+    unsigned long long h2[4] = {0, 0, 0, 0};
+    cudaMemcpyFromSymbol(h2, g_mv_stats2, sizeof(h2));
+    cudaMemcpyToSymbol(g_mv_stats2, z, sizeof(z));
+    fprintf(stderr, "[scpr timing] mv_resolve: %llu blocks in %llu steps, direct compares: last_mv %llu (in %llu steps), upper %llu | frames with a full own candidate list %llu, blocks with an unlisted F %llu\n",
+            h[3], h[0], h[1], h2[2], h[2], h2[0], h2[1]);
 }
 
 void launch_p_stage_a(const PWork& w, cudaStream_t st, uint64_t* launches) {
