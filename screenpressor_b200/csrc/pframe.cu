@@ -354,7 +354,7 @@ __device__ __forceinline__ MvRec load_mvrec(const ChgBlock* blocks, int k, int n
 // record (mx / my / pad[0], which the resolve overwrites).  The stored vectors only change where a block is motion-coded, so the
 // guess is almost always the vector warp 0 will find there one frame later; it checks (vector equal?) and falls back to its own
 // compare otherwise.  The 25 000 serial compares of a 600-frame desktop clip (1.1 us each) become a few parallel rounds per frame.
-constexpr int MVR_WARPS = 16;
+constexpr int MVR_WARPS = 16;  // MVR_RES resolver warps (below) + the speculating warps
 template <bool SMV>
 __device__ void mv_speculate(const PWork& w, const uint32_t* s_mvs, int pi, int hw, int nh, int lane) {
     const Geo& g = w.g;
@@ -391,9 +391,21 @@ __device__ void mv_speculate(const PWork& w, const uint32_t* s_mvs, int pi, int 
         }
     }
 }
+// Frames in a pipeline.  The only things one frame's resolve hands to the next are the stored vectors: block b of frame p reads
+// mvs[b - nbx] and may write mvs[b].  Frame p + 1 can therefore run while frame p is still going, as long as it stays more than one
+// block row behind it -- then everything it reads has been settled by the earlier frames, and nothing it writes is still to be read
+// by them.  MVR_RES resolver warps (one per scheduler) take the frames round robin; each publishes {frame, first block of the step
+// it is about to do} in a shared word before every step and waits until every earlier frame still in flight is past its own step's
+// last block + one row.  The remaining warps speculate a few frames ahead (mv_speculate) and count the frames they have finished.
+constexpr int MVR_RES = 4;
+constexpr int MVR_LOOK = MVR_RES + 2;   // the speculating warps stay at most this many frames ahead of the slowest resolver
+constexpr uint32_t MVR_DONE = 0x1FFFFu; // block position "frame complete" (block indices are below 65536)
+__device__ __forceinline__ uint32_t ldv_u32(const volatile uint32_t* p) { return *p; }
 template <bool SMV>
-__global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
+__global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
     extern __shared__ uint32_t s_mvs[];  // SMV: packed vector of every block
+    __shared__ uint32_t s_key[MVR_RES];  // resolver r: frame << 17 | blocks below this index are done (MVR_DONE: the whole frame)
+    __shared__ uint32_t s_spec;          // frames the speculating warps have finished
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1;
     const Geo& g = w.g;
@@ -403,37 +415,55 @@ __global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
             s_mvs[i] = ((uint32_t)u.x & 0xFFFFu) | ((uint32_t)u.y << 16);
         }
     }
+    if (threadIdx.x < MVR_RES) s_key[threadIdx.x] = (int)threadIdx.x < w.n_pframes ? 0u : 0x7FFFFFFFu;
+    if (threadIdx.x == 0) s_spec = 0;
     __syncthreads();
-    // helper warps: 1, 2, 3, 5, 6, 7, ... (warps 4, 8, 12 share warp 0's scheduler and only keep the barriers)
-    const int nh = MVR_WARPS - MVR_WARPS / 4;
-    const int hw = (warp & 3) ? warp - 1 - (warp >> 2) : -1;
-    if (hw >= 0 && w.n_pframes > 0) mv_speculate<SMV>(w, s_mvs, 0, hw, nh, lane);
-    __syncthreads();
-    // the frame's header words (frame index, block count, offset, candidates) are fetched one frame ahead: three dependent global
-    // round trips per frame otherwise sit in front of warp 0's first step
+    const int nh = MVR_WARPS - MVR_RES;
+    if (warp >= MVR_RES) {
+        // ---- speculating warps: frame after frame, a bounded distance ahead of the resolvers
+        const int hw = warp - MVR_RES;
+        for (int q = 0; q < w.n_pframes; q++) {
+            if (q >= MVR_LOOK) {
+                const uint32_t need = (uint32_t)(q - MVR_LOOK) << 17;
+                for (;;) {
+                    uint32_t lo = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int r = 0; r < MVR_RES; r++) lo = min(lo, ldv_u32(&s_key[r]));
+                    if (lo >= need) break;
+                    __nanosleep(200);
+                }
+            }
+            mv_speculate<SMV>(w, s_mvs, q, hw, nh, lane);
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;" ::"r"(nh * 32) : "memory");  // the speculating warps only: the frame is finished by all of them
+            if (hw == 0 && lane == 0) *(volatile uint32_t*)&s_spec = (uint32_t)(q + 1);
+        }
+        return;
+    }
+    // ---- resolver warps.  The frame's header words (frame index, block count, offset, candidates) are fetched one frame ahead:
+    // three dependent global round trips per frame otherwise sit in front of the first step
     int nf = 0, nnchg = 0, noff = 0, nnc = 0, ncand = 0;
-    if (warp == 0 && w.n_pframes > 0) {
-        nf = w.pframes[0];
+    if (warp < w.n_pframes) {
+        nf = w.pframes[warp];
         nnchg = w.hdr[nf].n_changed;
         noff = w.hdr[nf].chg_off;
-        nnc = w.ncands[0];
-        ncand = w.cands[lane];
+        nnc = w.ncands[warp];
+        ncand = w.cands[(size_t)warp * MAXC + lane];
     }
-    for (int pi = 0; pi < w.n_pframes; pi++) {
-        if (warp != 0) {
-            if (hw >= 0 && pi + 1 < w.n_pframes) mv_speculate<SMV>(w, s_mvs, pi + 1, hw, nh, lane);
-            __syncthreads();
-            continue;
-        }
+    for (int pi = warp; pi < w.n_pframes; pi += MVR_RES) {
         const int f = nf, nchg = nnchg, off = noff, nc = nnc;
         const int cand = ncand;  // lane k: candidate k
-        if (pi + 1 < w.n_pframes) {
-            nf = w.pframes[pi + 1];
+        if (pi + MVR_RES < w.n_pframes) {
+            nf = w.pframes[pi + MVR_RES];
             nnchg = w.hdr[nf].n_changed;
             noff = w.hdr[nf].chg_off;
-            nnc = w.ncands[pi + 1];
-            ncand = w.cands[(size_t)(pi + 1) * MAXC + lane];
+            nnc = w.ncands[pi + MVR_RES];
+            ncand = w.cands[(size_t)(pi + MVR_RES) * MAXC + lane];
         }
+        // the speculating warps have answered this frame's questions (and their writes to the block records are visible)
+        while (ldv_u32(&s_spec) < (uint32_t)(pi + 1)) {
+        }
+        __threadfence_block();
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
         const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
         int lv = 0, lidx = -1;   // last_mv (packed) and its index in the candidate list (-1: (0,0), -2: not listed)
@@ -464,16 +494,35 @@ __global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
                 const int e0 = __shfl_sync(0xFFFFFFFFu, r0.fv, js), e1 = __shfl_sync(0xFFFFFFFFu, r1.fv, js);
                 bi = lo ? a0 : a1; info = lo ? b0 : b1; mmask = lo ? c0 : c1; fidx = lo ? d0 : d1; fv = lo ? e0 : e1;
             }
-            if (k < nchg && bi >= (uint32_t)g.nbx) {
-                if (SMV)
-                    uv = (int)s_mvs[bi - g.nbx];
-                else {
-                    const int2 u = w.mvs[bi - g.nbx];
-                    uv = (u.x & 0xFFFF) | (u.y << 16);
-                }
-            }
             const uint32_t bi0 = __shfl_sync(0xFFFFFFFFu, bi, 0);
             int cnt = __popc(__ballot_sync(0xFFFFFFFFu, k < nchg && bi - bi0 < (uint32_t)g.nbx));
+            {
+                // every block below bi0 is done (the stores of the previous step are ordered in front of this word) ...
+                if (SMV) __threadfence_block(); else __threadfence();
+                if (lane == 0) *(volatile uint32_t*)&s_key[warp] = ((uint32_t)pi << 17) | bi0;
+                // ... and every earlier frame still in flight must be more than a row past this step's last block
+                const uint32_t bmax = __shfl_sync(0xFFFFFFFFu, bi, cnt - 1);
+                const uint32_t past = min(bmax + (uint32_t)g.nbx + 1u, MVR_DONE);
+#pragma unroll
+                for (int d = 1; d < MVR_RES; d++) {
+                    const int q = pi - d;
+                    if (q >= 0) {
+                        const uint32_t need = ((uint32_t)q << 17) | past;
+                        const volatile uint32_t* kp = &s_key[(warp - d + MVR_RES) % MVR_RES];
+                        while (ldv_u32(kp) < need) {
+                        }
+                    }
+                }
+                if (SMV) __threadfence_block(); else __threadfence();
+            }
+            if (k < nchg && bi >= (uint32_t)g.nbx) {
+                if (SMV)
+                    uv = (int)((const volatile uint32_t*)s_mvs)[bi - g.nbx];
+                else {
+                    const volatile int* u = (const volatile int*)(w.mvs + (bi - g.nbx));
+                    uv = (u[0] & 0xFFFF) | (u[1] << 16);
+                }
+            }
             const bool in = lane < cnt;
             // ---- candidate 1: last_mv (same for every lane of the step) ----
             bool found = false;
@@ -566,9 +615,11 @@ __global__ void __launch_bounds__(32 * MVR_WARPS) k_mv_resolve(PWork w) {
             MV_STAT(if (lane == 0) atomicAdd(&g_mv_stats[3], (unsigned long long)cnt);)
             k0 += cnt;
         }
-        __threadfence();  // mvs[] of this frame visible before the next frame reads it
-        __syncthreads();  // ... and the helpers' answers for the next frame are complete
+        __threadfence();  // mvs[] of this frame visible ...
+        if (lane == 0) *(volatile uint32_t*)&s_key[warp] = ((uint32_t)pi << 17) | MVR_DONE;  // ... before the frame is declared complete
     }
+    __threadfence();
+    if (lane == 0) *(volatile uint32_t*)&s_key[warp] = 0x7FFFFFFFu;  // no more frames on this warp: nobody waits for it
 }
 
 // ------------------------------------------------------------------------------------------------
