@@ -401,10 +401,15 @@ constexpr int MVR_RES = 4;
 constexpr int MVR_LOOK = MVR_RES + 2;   // the speculating warps stay at most this many frames ahead of the slowest resolver
 constexpr uint32_t MVR_DONE = 0x1FFFFu; // block position "frame complete" (block indices are below 65536)
 __device__ __forceinline__ uint32_t ldv_u32(const volatile uint32_t* p) { return *p; }
+__device__ __forceinline__ unsigned long long ldv_u64(const volatile unsigned long long* p) { return *p; }
+constexpr unsigned long long MVR_IDLE = ~0ull;  // a resolver warp without (more) frames
+// The waits below cannot deadlock (a frame only waits for earlier frames and for speculation that does not depend on it), but a
+// kernel that spins for ever takes the device with it: after ~10 s of spinning on one word the kernel traps instead.
+constexpr uint32_t MVR_SPIN_LIMIT = 1u << 28;
 template <bool SMV>
 __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
     extern __shared__ uint32_t s_mvs[];  // SMV: packed vector of every block
-    __shared__ uint32_t s_key[MVR_RES];  // resolver r: frame << 17 | blocks below this index are done (MVR_DONE: the whole frame)
+    __shared__ unsigned long long s_key[MVR_RES];  // resolver r: frame << 17 | blocks below this index are done (MVR_DONE: the whole frame)
     __shared__ uint32_t s_spec;          // frames the speculating warps have finished
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1;
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             s_mvs[i] = ((uint32_t)u.x & 0xFFFFu) | ((uint32_t)u.y << 16);
         }
     }
-    if (threadIdx.x < MVR_RES) s_key[threadIdx.x] = (int)threadIdx.x < w.n_pframes ? 0u : 0x7FFFFFFFu;
+    if (threadIdx.x < MVR_RES) s_key[threadIdx.x] = (int)threadIdx.x < w.n_pframes ? 0ull : MVR_IDLE;
     if (threadIdx.x == 0) s_spec = 0;
     __syncthreads();
     const int nh = MVR_WARPS - MVR_RES;
@@ -424,12 +429,13 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
         const int hw = warp - MVR_RES;
         for (int q = 0; q < w.n_pframes; q++) {
             if (q >= MVR_LOOK) {
-                const uint32_t need = (uint32_t)(q - MVR_LOOK) << 17;
-                for (;;) {
-                    uint32_t lo = 0xFFFFFFFFu;
+                const unsigned long long need = (unsigned long long)(q - MVR_LOOK) << 17;
+                for (uint32_t spins = 0;; spins++) {
+                    unsigned long long lo = MVR_IDLE;
 #pragma unroll
-                    for (int r = 0; r < MVR_RES; r++) lo = min(lo, ldv_u32(&s_key[r]));
+                    for (int r = 0; r < MVR_RES; r++) lo = min(lo, ldv_u64(&s_key[r]));
                     if (lo >= need) break;
+                    if (spins > MVR_SPIN_LIMIT / 8) __trap();  // (see MVR_SPIN_LIMIT)
                     __nanosleep(200);
                 }
             }
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             ncand = w.cands[(size_t)(pi + MVR_RES) * MAXC + lane];
         }
         // the speculating warps have answered this frame's questions (and their writes to the block records are visible)
-        while (ldv_u32(&s_spec) < (uint32_t)(pi + 1)) {
-        }
+        for (uint32_t spins = 0; ldv_u32(&s_spec) < (uint32_t)(pi + 1); spins++)
+            if (spins > MVR_SPIN_LIMIT) __trap();
         __threadfence_block();
         const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
         const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             {
                 // every block below bi0 is done (the stores of the previous step are ordered in front of this word) ...
                 if (SMV) __threadfence_block(); else __threadfence();
-                if (lane == 0) *(volatile uint32_t*)&s_key[warp] = ((uint32_t)pi << 17) | bi0;
+                if (lane == 0) *(volatile unsigned long long*)&s_key[warp] = ((unsigned long long)pi << 17) | bi0;
                 // ... and every earlier frame still in flight must be more than a row past this step's last block
                 const uint32_t bmax = __shfl_sync(0xFFFFFFFFu, bi, cnt - 1);
                 const uint32_t past = min(bmax + (uint32_t)g.nbx + 1u, MVR_DONE);
@@ -507,10 +513,10 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
                 for (int d = 1; d < MVR_RES; d++) {
                     const int q = pi - d;
                     if (q >= 0) {
-                        const uint32_t need = ((uint32_t)q << 17) | past;
-                        const volatile uint32_t* kp = &s_key[(warp - d + MVR_RES) % MVR_RES];
-                        while (ldv_u32(kp) < need) {
-                        }
+                        const unsigned long long need = ((unsigned long long)q << 17) | past;
+                        const volatile unsigned long long* kp = &s_key[(warp - d + MVR_RES) % MVR_RES];
+                        for (uint32_t spins = 0; ldv_u64(kp) < need; spins++)
+                            if (spins > MVR_SPIN_LIMIT) __trap();
                     }
                 }
                 if (SMV) __threadfence_block(); else __threadfence();
@@ -616,10 +622,10 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             k0 += cnt;
         }
         __threadfence();  // mvs[] of this frame visible ...
-        if (lane == 0) *(volatile uint32_t*)&s_key[warp] = ((uint32_t)pi << 17) | MVR_DONE;  // ... before the frame is declared complete
+        if (lane == 0) *(volatile unsigned long long*)&s_key[warp] = ((unsigned long long)pi << 17) | MVR_DONE;  // ... before the frame is declared complete
     }
     __threadfence();
-    if (lane == 0) *(volatile uint32_t*)&s_key[warp] = 0x7FFFFFFFu;  // no more frames on this warp: nobody waits for it
+    if (lane == 0) *(volatile unsigned long long*)&s_key[warp] = MVR_IDLE;  // no more frames on this warp: nobody waits for it
 }
 
 // ------------------------------------------------------------------------------------------------
