@@ -146,7 +146,10 @@ int64_t multi_compress(scpr_multi* m, const uint8_t* frames, int n, const uint8_
     for (int k = 0; k < R; k++) {
         relay.codec[k] = m->enc[k];  // range k runs on the k-th device given (plan_ranges hands them out in order)
         const int r = scpr_reset(relay.codec[k]);
-        if (r < 0) return r;
+        if (r < 0) {
+            for (int q = 0; q < k; q++) scpr_set_mvs_hooks(relay.codec[q], nullptr, nullptr, nullptr);  // they point into this frame
+            return r;
+        }
         ctx[k].relay = &relay;
         ctx[k].k = k;
         scpr_set_mvs_hooks(relay.codec[k], hook_wait, hook_ready, &ctx[k]);
