@@ -392,12 +392,12 @@ static int64_t encode_batch(scpr_codec* c, const uint8_t* d_frames, int n, const
         TRY(c->blocks.ensure((size_t)(total_blocks + 1) * sizeof(ChgBlock)));
         TRY(c->runs.ensure((size_t)(total_blocks + 1) * 256 * 2));
         TRY(c->bts_rle.ensure((size_t)n_p * 2 * g.nb * 4));
-        TRY(c->cands.ensure((size_t)n_p * 66 * 4));
+        TRY(c->cands.ensure((size_t)n_p * (2 * MV_MAXC + 2) * 4));
         CK(cudaMemcpyAsync(c->pframes.p, pframes.data(), (size_t)n_p * 4, cudaMemcpyHostToDevice, st));
         pw.blocks = (ChgBlock*)c->blocks.p; pw.pframes = (const int*)c->pframes.p; pw.runs = (uint16_t*)c->runs.p;
         pw.bts_rle = (uint32_t*)c->bts_rle.p;
-        pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * 32;
-        pw.cands0 = (int*)c->cands.p + (size_t)n_p * 33; pw.ncands0 = (int*)c->cands.p + (size_t)n_p * 65;
+        pw.cands = (int*)c->cands.p; pw.ncands = (int*)c->cands.p + (size_t)n_p * MV_MAXC;
+        pw.cands0 = (int*)c->cands.p + (size_t)n_p * (MV_MAXC + 1); pw.ncands0 = (int*)c->cands.p + (size_t)n_p * (2 * MV_MAXC + 1);
         pw.pre_resolve = (hooks & 1) ? c->mvs_wait : nullptr;
         pw.post_resolve = (hooks & 2) ? c->mvs_ready : nullptr;
         pw.hook_user = c->mvs_user;

@@ -24,6 +24,8 @@ struct PFrameHdr {
     uint32_t pad[2];
 };
 
+constexpr int MV_MAXC = 64;  // candidate vectors per P frame (k_mv_cands): slot k lives in lane k & 31, half k >> 5
+
 // one changed 16x16 block of a P frame
 struct ChgBlock {
     uint32_t bi;        // block index in the frame
@@ -35,7 +37,8 @@ struct ChgBlock {
     uint8_t rep;        // MV equals the previously coded MV of this frame (encodeBool(true))
     uint8_t fidx;       // index of F(bi) in the frame's candidate list, 0xFF = not listed (k_mv_cands)
     uint8_t pad[3];
-    uint32_t mmask;     // bit k: candidate k of the frame reproduces this block (k_mv_prematch)
+    uint32_t mmask;     // bit k: candidate k of the frame reproduces this block (k_mv_prematch); candidates 32..63 in mmask2
+    uint32_t mmask2;
     int32_t prev_nonmv; // previous pixel-coded changed block of the frame (slot index), -1 if none
     uint32_t n_runs;    // pixel runs of a pixel-coded block
     uint32_t n_ev;      // events this block contributes

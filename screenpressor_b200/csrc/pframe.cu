@@ -209,7 +209,36 @@ __device__ __forceinline__ bool in_far_window(const SubRect& r, const Windows& w
 // appearance) -- the only values last_mv can take in this frame besides (0,0).  One warp per frame;
 // lane k keeps candidate k.  Also records each block's index into that list (fidx, 0xFF = none).
 // ------------------------------------------------------------------------------------------------
-constexpr int MAXC = 32;
+constexpr int MAXC = MV_MAXC;
+static_assert(MAXC == 64, "two candidates per lane");
+// a frame's candidate list across the warp: slot k in lane k & 31, `a` for k < 32, `b` for k >= 32
+struct Cands {
+    int a, b;
+    __device__ __forceinline__ int find(int v, int n, int lane) const {  // index of v among the first n slots, -1 if absent
+        const uint32_t ha = __ballot_sync(0xFFFFFFFFu, lane < n && a == v);
+        if (ha) return __ffs(ha) - 1;
+        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, lane + 32 < n && b == v);
+        return hb ? 31 + __ffs(hb) : -1;
+    }
+    __device__ __forceinline__ void put(int v, int n, int lane) {  // slot n := v
+        if (n < 32) {
+            if (lane == n) a = v;
+        } else if (lane == n - 32)
+            b = v;
+    }
+    __device__ __forceinline__ int get(int k) const {  // slot k, broadcast
+        const int va = __shfl_sync(0xFFFFFFFFu, a, k & 31), vb = __shfl_sync(0xFFFFFFFFu, b, k & 31);
+        return k < 32 ? va : vb;
+    }
+    __device__ __forceinline__ void load(const int* p, int lane) {
+        a = p[lane];
+        b = p[32 + lane];
+    }
+    __device__ __forceinline__ void store(int* p, int n, int lane) const {
+        p[lane] = lane < n ? a : 0x7FFFFFFF;
+        p[32 + lane] = lane + 32 < n ? b : 0x7FFFFFFF;
+    }
+};
 __device__ unsigned long long g_mv_stats2[4];  // frames whose own list is full, blocks with an unlisted F, lidx == -2 steps, -
 __device__ unsigned long long g_mv_stats[4];  // steps, c1 direct compares, c2 direct compares, blocks (-DSCPR_MVSTATS builds only)
 #ifdef SCPR_MVSTATS
@@ -221,7 +250,8 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
     const int lane = threadIdx.x;
     const int f = w.pframes[blockIdx.x];
     const int nchg = w.hdr[f].n_changed, off = w.hdr[f].chg_off;
-    int cand = 0x7FFFFFFF;  // packed (mx & 0xFFFF) | (my << 16)
+    Cands cand;  // packed (mx & 0xFFFF) | (my << 16)
+    cand.a = cand.b = 0x7FFFFFFF;
     int ncand = 0;
     for (int k0 = 0; k0 < nchg; k0 += 32) {
         const int k = k0 + lane;
@@ -233,15 +263,14 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
         while (todo) {
             const int src = __ffs(todo) - 1;
             const int v = __shfl_sync(0xFFFFFFFFu, fv, src);
-            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < ncand && cand == v);
-            int idx;
-            if (hit)
-                idx = __ffs(hit) - 1;
-            else if (ncand < MAXC) {
-                if (lane == ncand) cand = v;
-                idx = ncand++;
-            } else
-                idx = 0xFF;
+            int idx = cand.find(v, ncand, lane);
+            if (idx < 0) {
+                if (ncand < MAXC) {
+                    cand.put(v, ncand, lane);
+                    idx = ncand++;
+                } else
+                    idx = 0xFF;
+            }
             // every block of this step with the same vector gets the same answer
             const uint32_t same = __ballot_sync(0xFFFFFFFFu, fv == v);
             if (fv == v) myidx = idx;
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(32) k_mv_cands(PWork w) {
         })
     }
     MV_STAT(if (lane == 0 && ncand == MAXC) atomicAdd(&g_mv_stats2[0], 1ull);)
-    w.cands0[(size_t)blockIdx.x * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
+    cand.store(w.cands0 + (size_t)blockIdx.x * MAXC, ncand, lane);
     if (lane == 0) w.ncands0[blockIdx.x] = ncand;
 }
 
@@ -264,26 +293,28 @@ constexpr int MERGE_BACK = 192;  // a drag or scroll session ends, the vectors i
 __global__ void __launch_bounds__(32) k_mv_cands_merge(PWork w) {
     const int lane = threadIdx.x;
     const int pi = blockIdx.x;
-    int cand = w.cands0[(size_t)pi * MAXC + lane];
+    Cands cand;
+    cand.load(w.cands0 + (size_t)pi * MAXC, lane);
     int ncand = w.ncands0[pi];
     for (int back = 1; back <= MERGE_BACK && pi - back >= 0 && ncand < MAXC; back++) {
-        const int pv = w.cands0[(size_t)(pi - back) * MAXC + lane];
+        Cands pv;
+        pv.load(w.cands0 + (size_t)(pi - back) * MAXC, lane);
         const int pn = w.ncands0[pi - back];
         for (int k = 0; k < pn && ncand < MAXC; k++) {
-            const int v = __shfl_sync(0xFFFFFFFFu, pv, k);
-            if (!__ballot_sync(0xFFFFFFFFu, lane < ncand && cand == v)) {
-                if (lane == ncand) cand = v;
+            const int v = pv.get(k);
+            if (cand.find(v, ncand, lane) < 0) {
+                cand.put(v, ncand, lane);
                 ncand++;
             }
         }
     }
-    w.cands[(size_t)pi * MAXC + lane] = lane < ncand ? cand : 0x7FFFFFFF;
+    cand.store(w.cands + (size_t)pi * MAXC, ncand, lane);
     if (lane == 0) w.ncands[pi] = ncand;
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_mv_prematch: for every changed block, which of its frame's candidate vectors reproduce the
-// block from the previous frame (window test included).  One warp per block -> 16-bit mask.
+// block from the previous frame (window test included).  One warp per block -> 64-bit mask.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -299,17 +330,20 @@ __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
     const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
     const int nc = w.ncands[pi];
     const int fidx = b.fidx;
-    uint32_t mask = 0;
+    unsigned long long mask = 0;
     for (int k = 0; k < nc; k++) {
         if (k == fidx) {  // F(b) matches by construction and lies inside the far window
-            mask |= 1u << k;
+            mask |= 1ull << k;
             continue;
         }
         const int cv = w.cands[(size_t)pi * MAXC + k];
         const int mx = (int)(int16_t)(cv & 0xFFFF), my = cv >> 16;
-        if (in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane)) mask |= 1u << k;
+        if (in_far_window(r, win, mx, my) && warp_match(cur, prv, g, r, mx, my, lane)) mask |= 1ull << k;
     }
-    if (lane == 0) b.mmask = mask;
+    if (lane == 0) {
+        b.mmask = (uint32_t)mask;
+        b.mmask2 = (uint32_t)(mask >> 32);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,20 +362,20 @@ __global__ void __launch_bounds__(128) k_mv_prematch(PWork w) {
 // the kernel runs (SMV; written through to global memory), and the block records of a frame are read 64 ahead into
 // two register windows, a step picking its 32 records out of them with shuffles.
 struct MvRec {
-    uint32_t bi, info, mmask;
+    uint32_t bi, info, mmask, mmask2;
     int fidx, fv;
     int sp;   // speculated compare (helper warps): vector tried, packed; valid when spf & 1, its outcome in spf bit 1
     int spf;
 };
 __device__ __forceinline__ MvRec load_mvrec(const ChgBlock* blocks, int k, int nchg) {
     MvRec r;
-    r.bi = r.info = r.mmask = 0;
+    r.bi = r.info = r.mmask = r.mmask2 = 0;
     r.fidx = 0x100;
     r.fv = 0;
     r.sp = r.spf = 0;
     if (k < nchg) {
         const ChgBlock& b = blocks[k];
-        r.bi = b.bi; r.info = b.info; r.mmask = b.mmask; r.fidx = b.has_f ? b.fidx : 0x100;
+        r.bi = b.bi; r.info = b.info; r.mmask = b.mmask; r.mmask2 = b.mmask2; r.fidx = b.has_f ? b.fidx : 0x100;
         r.fv = ((int)b.fmx & 0xFFFF) | ((int)b.fmy << 16);
         r.sp = ((int)b.mx & 0xFFFF) | ((int)b.my << 16);
         r.spf = b.pad[0];
@@ -363,7 +397,8 @@ __device__ void mv_speculate(const PWork& w, const uint32_t* s_mvs, int pi, int 
     const uint8_t* cur = w.frames + (size_t)f * g.frame_bytes;
     const uint8_t* prv = f > 0 ? cur - g.frame_bytes : w.prev0;
     const int nc = w.ncands[pi];
-    const int cand = w.cands[(size_t)pi * MAXC + lane];
+    Cands cand;
+    cand.load(w.cands + (size_t)pi * MAXC, lane);
     for (int k = hw; k < nchg; k += nh) {
         ChgBlock& b = w.blocks[off + k];
         const uint32_t bi = b.bi, info = b.info;
@@ -376,7 +411,7 @@ __device__ void mv_speculate(const PWork& w, const uint32_t* s_mvs, int pi, int 
                 uv = (u[0] & 0xFFFF) | (u[1] << 16);
             }
             uv = __shfl_sync(0xFFFFFFFFu, uv, 0);  // one value for the whole warp even while warp 0 is writing
-            if (uv != 0 && !__ballot_sync(0xFFFFFFFFu, lane < nc && cand == uv)) {
+            if (uv != 0 && cand.find(uv, nc, lane) < 0) {
                 const SubRect r = subrect_of(bi, info, g);
                 const Windows win = windows_of(r, g);
                 const int mx = (int)(int16_t)(uv & 0xFFFF), my = uv >> 16;
@@ -448,23 +483,25 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
     }
     // ---- resolver warps.  The frame's header words (frame index, block count, offset, candidates) are fetched one frame ahead:
     // three dependent global round trips per frame otherwise sit in front of the first step
-    int nf = 0, nnchg = 0, noff = 0, nnc = 0, ncand = 0;
+    int nf = 0, nnchg = 0, noff = 0, nnc = 0;
+    Cands ncand;
+    ncand.a = ncand.b = 0x7FFFFFFF;
     if (warp < w.n_pframes) {
         nf = w.pframes[warp];
         nnchg = w.hdr[nf].n_changed;
         noff = w.hdr[nf].chg_off;
         nnc = w.ncands[warp];
-        ncand = w.cands[(size_t)warp * MAXC + lane];
+        ncand.load(w.cands + (size_t)warp * MAXC, lane);
     }
     for (int pi = warp; pi < w.n_pframes; pi += MVR_RES) {
         const int f = nf, nchg = nnchg, off = noff, nc = nnc;
-        const int cand = ncand;  // lane k: candidate k
+        const Cands cand = ncand;  // lane k: candidates k and 32 + k
         if (pi + MVR_RES < w.n_pframes) {
             nf = w.pframes[pi + MVR_RES];
             nnchg = w.hdr[nf].n_changed;
             noff = w.hdr[nf].chg_off;
             nnc = w.ncands[pi + MVR_RES];
-            ncand = w.cands[(size_t)(pi + MVR_RES) * MAXC + lane];
+            ncand.load(w.cands + (size_t)(pi + MVR_RES) * MAXC, lane);
         }
         // the speculating warps have answered this frame's questions (and their writes to the block records are visible)
         for (uint32_t spins = 0; ldv_u32(&s_spec) < (uint32_t)(pi + 1); spins++)
@@ -487,7 +524,7 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             const int k = k0 + lane;
             const int jw = k0 - w0 + lane, js = jw & 31;
             const bool lo = jw < 32;
-            uint32_t bi, info, mmask;
+            uint32_t bi, info, mmask, mmask2;
             int fidx, fv, uv = 0, sp, spf;
             {
                 const int s0 = __shfl_sync(0xFFFFFFFFu, r0.sp, js), s1 = __shfl_sync(0xFFFFFFFFu, r1.sp, js);
@@ -498,7 +535,8 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
                 const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, r0.mmask, js), c1 = __shfl_sync(0xFFFFFFFFu, r1.mmask, js);
                 const int d0 = __shfl_sync(0xFFFFFFFFu, r0.fidx, js), d1 = __shfl_sync(0xFFFFFFFFu, r1.fidx, js);
                 const int e0 = __shfl_sync(0xFFFFFFFFu, r0.fv, js), e1 = __shfl_sync(0xFFFFFFFFu, r1.fv, js);
-                bi = lo ? a0 : a1; info = lo ? b0 : b1; mmask = lo ? c0 : c1; fidx = lo ? d0 : d1; fv = lo ? e0 : e1;
+                const uint32_t g0 = __shfl_sync(0xFFFFFFFFu, r0.mmask2, js), g1 = __shfl_sync(0xFFFFFFFFu, r1.mmask2, js);
+                bi = lo ? a0 : a1; info = lo ? b0 : b1; mmask = lo ? c0 : c1; mmask2 = lo ? g0 : g1; fidx = lo ? d0 : d1; fv = lo ? e0 : e1;
             }
             const uint32_t bi0 = __shfl_sync(0xFFFFFFFFu, bi, 0);
             int cnt = __popc(__ballot_sync(0xFFFFFFFFu, k < nchg && bi - bi0 < (uint32_t)g.nbx));
@@ -534,7 +572,7 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             bool found = false;
             int mv = 0;
             if (lidx >= 0)
-                found = in && ((mmask >> lidx) & 1);
+                found = in && (((lidx < 32 ? mmask : mmask2) >> (lidx & 31)) & 1);
             else if (lidx == -2) {  // last_mv is not in the candidate list: direct compares, lane by lane
                 MV_STAT(if (lane == 0) { atomicAdd(&g_mv_stats[1], (unsigned long long)cnt); atomicAdd(&g_mv_stats2[2], 1ull); })
                 for (int i = 0; i < cnt; i++) {
@@ -551,12 +589,12 @@ __global__ void __launch_bounds__(32 * MVR_WARPS, 1) k_mv_resolve(PWork w) {
             int uidx = -1;  // its index in the candidate list: one ballot per distinct vector among the lanes that need it
             for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, try2); todo;) {
                 const int v = __shfl_sync(0xFFFFFFFFu, uv, __ffs(todo) - 1);
-                const uint32_t hit = __ballot_sync(0xFFFFFFFFu, lane < nc && cand == v);
+                const int at = cand.find(v, nc, lane);
                 const bool mine = uv == v;
-                if (mine) uidx = hit ? __ffs(hit) - 1 : -1;
+                if (mine) uidx = at;
                 todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
             }
-            bool f2 = try2 && uidx >= 0 && ((mmask >> uidx) & 1);
+            bool f2 = try2 && uidx >= 0 && (((uidx < 32 ? mmask : mmask2) >> (uidx & 31)) & 1);
             const bool spec_ok = (spf & 1) && sp == uv;  // a helper warp has already compared this block with this vector
             if (try2 && uidx < 0 && spec_ok) f2 = (spf & 2) != 0;
             uint32_t slow = __ballot_sync(0xFFFFFFFFu, try2 && uidx < 0 && !spec_ok);
