@@ -70,6 +70,15 @@ std::vector<Range> plan_ranges(int n, const std::vector<uint8_t>& cuts, const in
     return out;
 }
 
+// joins whatever threads were started, also when starting a later one throws (a joinable std::thread must not be destroyed)
+struct Pool {
+    std::vector<std::thread> t;
+    ~Pool() {
+        for (auto& x : t)
+            if (x.joinable()) x.join();
+    }
+};
+
 // hand-off of mvs[] between neighbouring ranges
 struct Relay {
     std::mutex m;
@@ -160,9 +169,9 @@ int64_t multi_compress(scpr_multi* m, const uint8_t* frames, int n, const uint8_
         out_cap[k] = cap;
         out[k].reset(new uint8_t[cap + 16]);
     }
-    std::vector<std::thread> pool;
+    Pool pool;
     for (int k = 0; k < R; k++)
-        pool.emplace_back([&, k]() {
+        pool.t.emplace_back([&, k]() {
             const Range& rg = ranges[k];
             std::vector<uint8_t> keys(keyflags + rg.first, keyflags + rg.first + rg.count);
             keys[0] = 1;
@@ -179,7 +188,7 @@ int64_t multi_compress(scpr_multi* m, const uint8_t* frames, int n, const uint8_
                 relay.cv.notify_all();
             }
         });
-    for (auto& t : pool) t.join();
+    for (auto& t : pool.t) t.join();
     for (int k = 0; k < R; k++) scpr_set_mvs_hooks(relay.codec[k], nullptr, nullptr, nullptr);
     int64_t total = 0, err = 0;
     for (int k = 0; k < R; k++) {
@@ -210,17 +219,17 @@ int multi_decompress(scpr_multi* m, const uint8_t* stream, const uint32_t* sizes
     const std::vector<Range> ranges = plan_ranges(n, cuts, m->devices.data(), (int)m->devices.size());
     const int R = (int)ranges.size();
     std::vector<int> res(R, 1);
-    std::vector<std::thread> pool;
+    Pool pool;
     const size_t fb = (size_t)pitch * p->height;
     for (int k = 0; k < R; k++)
-        pool.emplace_back([&, k]() {
+        pool.t.emplace_back([&, k]() {
             const Range& rg = ranges[k];
             scpr_codec* c = m->dec[k];
             int r = scpr_reset(c);
             if (r >= 0) r = scpr_decompress_clip(c, stream + off[rg.first], sizes + rg.first, ftypes + rg.first, rg.count, frames + (size_t)rg.first * fb, pitch);
             res[k] = r;
         });
-    for (auto& t : pool) t.join();
+    for (auto& t : pool.t) t.join();
     for (int k = 0; k < R; k++)
         if (res[k] != 1) return res[k];
     return 1;
