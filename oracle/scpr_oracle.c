@@ -556,6 +556,7 @@ static void rdec_advance(RDec* r, uint32_t start, uint32_t freq) { /* rans_byte.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     int X, Y, bpp; /* bytes per pixel of the caller's format: 3 or 4 */
+    int bands;     /* I-frame row bands = worker threads of the reference that is being restated (1: canonical) */
     int stride;    /* RGB24 padded row pitch (screencap.cpp:75) */
     int nbx, nby;
     unsigned fn;
@@ -591,10 +592,20 @@ static void set_loss(Orc* o, int loss) { /* SetupLossMask screencap.cpp:127-139 
     o->loss = loss;
 }
 
-void* orc_create(int width, int height, int bits_per_pixel, int loss, int threads_ignored) {
-    (void)threads_ignored;
+/* threads: I frames only.  The reference classifies an I frame in one row band per worker thread (CSquadWorker::GetSegment,
+ * squad.cpp:16-31: band b covers rows [Y*b/n, Y*(b+1)/n)) and every band starts a new run (ClassifyPixelsI, screencap.cpp:876-919;
+ * serialised band by band, :365-388).  1 = the canonical stream.  P frames of the multi-threaded reference depend on thread timing
+ * and are not restated: they are always coded in the one-thread order. */
+static int band_start(const Orc* o, int y) { /* is row y the first row of a band b >= 1?  (squad.cpp:18-22, totalsize >= nw) */
+    if (o->bands <= 1 || o->Y < o->bands || y <= 0) return 0;
+    long b = ((long)y * o->bands + o->Y - 1) / o->Y; /* smallest b with Y*b/n >= y */
+    return b > 0 && b < o->bands && (long)o->Y * b / o->bands == y;
+}
+
+void* orc_create(int width, int height, int bits_per_pixel, int loss, int threads) {
     if (bits_per_pixel != 24 && bits_per_pixel != 32) return NULL;
     Orc* o = (Orc*)calloc(1, sizeof(Orc));
+    o->bands = threads < 1 ? 1 : threads;
     o->X = width;
     o->Y = height;
     o->bpp = bits_per_pixel / 8;
@@ -771,6 +782,7 @@ static void events_i(Orc* o, const unsigned char* s) {
         }
         while (y < Y) {
             int i = y * stride + x * 3;
+            if (x == 0 && band_start(o, y)) break; /* a new band starts a new run (screencap.cpp:881-891) */
             if (n < 255 && fits_i(ptype, s + i, s + lasti, off)) {
                 n++;
                 lasti = i;

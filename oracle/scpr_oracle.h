@@ -31,7 +31,7 @@ typedef struct {
     uint16_t freq, cum; /* freq == 0: raw byte `cum` (ransmt.h:125-128) */
 } orc_freq;
 
-void* orc_create(int width, int height, int bits_per_pixel, int loss, int threads_ignored);
+void* orc_create(int width, int height, int bits_per_pixel, int loss, int threads); /* threads: I-frame row bands of the reference with that many workers */
 void orc_destroy(void* h);
 /* *ftype in: 0 = I, 1 = P request; out: actual.  Returns bytes written. */
 int orc_compress(void* h, unsigned char* src, unsigned char* dst, int dst_cap, int* ftype, int loss);

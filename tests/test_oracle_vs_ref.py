@@ -53,7 +53,35 @@ def test_all_model_promotions_exercised(both):
     """The fuzz content must drive every colour-model promotion of ans_contexts.cpp:3-50."""
     _run(both, 640, 200, 6, 3, 32, 256)
     _run(both, 320, 200, 6, 4, 32, 64)
+    _run(both, 640, 360, 30, 15, 32, 256)  # the one fuzz clip that takes a context through Cx2 -> Cx3 -> Cx7 (this test stands alone)
     lib = C.CDLL(both.ORACLE_SO)
     lib.orc_transition_count.restype = C.c_ulong
     for a, b in [(0, 1), (1, 2), (1, 4), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (5, 6), (6, 7)]:
         assert lib.orc_transition_count(a, b) > 0, f"promotion {a}->{b} never happened"
+
+
+@pytest.mark.parametrize("case", [(320, 192, 32), (161, 90, 24), (640, 360, 32)])
+def test_oracle_band_layout_matches_multithreaded_reference(oracle_built, case):
+    """SURVEY 8(f)5 on the CPU: the plain-C restatement with `threads` row bands against the unmodified reference created with as
+    many worker threads, intra-only clips (the reference's multi-threaded P frames are timing dependent), bytes and decode."""
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from _clips import band_clip
+
+    w, h, bpp = case
+    n = 4
+    clip = band_clip(w, h, n, 900 + w, bpp)
+    canonical = None
+    for threads in (1, 2, 3, 5, (h + 15) // 16):
+        ref = oracle_built.RefCodec(w, h, bpp, threads=threads)
+        want = [ref.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), False) for i in range(n)]
+        orc = oracle_built.OracleCodec(w, h, bpp, threads=threads)
+        got = [orc.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), False) for i in range(n)]
+        assert got == want, (case, threads, [i for i in range(n) if got[i] != want[i]])
+        if threads == 1:
+            canonical = want
+        else:
+            assert want != canonical
+        dec = oracle_built.OracleCodec(w, h, bpp)
+        for i in range(n):
+            assert np.array_equal(dec.decompress(want[i][0], want[i][1]), clip[i].reshape(-1)), (case, threads, i)
