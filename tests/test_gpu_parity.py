@@ -617,8 +617,7 @@ def test_threads_layout_matches_multithreaded_reference_i_frames(scpr, oracle_bu
     (squad.cpp:16-31, screencap.cpp:862-866, 876-919, 365-388).  scpr_set_threads_layout(n) must write the same bytes -- checked
     against the unmodified reference created with n threads on intra-only clips (its multi-threaded P frames are timing dependent,
     SURVEY 0.1, so only I frames can be pinned), frame and clip API; any decoder reads them."""
-    if not oracle_built.have_ref():
-        pytest.skip("oracle/_ref not built")
+    Checker = oracle_built.RefCodec if oracle_built.have_ref() else oracle_built.OracleCodec   # (the port restates the bands too)
     w, h, bpp = case
     n = 6
     clip = band_clip(w, h, n, 900 + w, bpp)
@@ -626,7 +625,7 @@ def test_threads_layout_matches_multithreaded_reference_i_frames(scpr, oracle_bu
     nby = (h + 15) // 16
     canonical = None
     for threads in (1, 2, 3, 5, nby):
-        ref = oracle_built.RefCodec(w, h, bpp, threads=threads)   # (the thread count is read at this codec's first CompressFrame)
+        ref = Checker(w, h, bpp, threads=threads)   # (the reference reads the thread count at this codec's first CompressFrame)
         want = [ref.compress(np.ascontiguousarray(clip[i]).reshape(-1).copy(), False) for i in range(n)]
         if threads == 1:
             canonical = want
