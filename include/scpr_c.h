@@ -152,6 +152,10 @@ int64_t scpr_compress_clip_multi(const scpr_params* p, const int* devices, int n
 /* The decoding counterpart: ranges start at coded I frames, no hand-off.  frames: host memory, row pitch `pitch`. */
 int scpr_decompress_clip_multi(const scpr_params* p, const int* devices, int n_dev, const uint8_t* stream, const uint32_t* sizes,
                                const uint8_t* ftypes, int n, uint8_t* frames, int pitch);
+/* The plan those entries use, by itself (host arithmetic only, no device): cuts[f] = 1 where a range may start at frame f (a coded,
+ * non-flat keyframe; frame 0 always may).  Writes up to n_ranges_max GOP-aligned contiguous ranges balanced by frame count and
+ * returns how many (fewer when the clip has fewer GOPs). */
+int scpr_plan_ranges(const uint8_t* cuts, int n, int n_ranges_max, int* first, int* count);
 /* The same with a standing set of codec objects (an encoder and a decoder per device ordinal, created once: workspaces and model
  * states stay on the devices between calls).  Every call codes a clip of its own (the objects are reset first). */
 typedef struct scpr_multi scpr_multi;

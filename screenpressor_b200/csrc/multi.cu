@@ -239,6 +239,23 @@ int multi_decompress(scpr_multi* m, const uint8_t* stream, const uint32_t* sizes
 
 extern "C" {
 
+int scpr_plan_ranges(const uint8_t* cuts, int n, int n_ranges_max, int* first, int* count) {
+    if (!cuts || n < 1 || n_ranges_max < 1 || !first || !count) return SCPR_E_PARAM;
+    try {
+        std::vector<uint8_t> c(cuts, cuts + n);
+        std::vector<int> dev(n_ranges_max, 0);
+        const std::vector<Range> r = plan_ranges(n, c, dev.data(), n_ranges_max);
+        for (size_t k = 0; k < r.size(); k++) {
+            first[k] = r[k].first;
+            count[k] = r[k].count;
+        }
+        return (int)r.size();
+    } catch (...) {
+        set_error("out of memory");
+        return SCPR_E_PARAM;
+    }
+}
+
 int scpr_multi_create(const scpr_params* p, const int* devices, int n_dev, scpr_multi** out) {
     if (!p || !devices || n_dev < 1 || !out) return SCPR_E_PARAM;
     *out = nullptr;

@@ -207,3 +207,33 @@ def test_sharded_encode_relays_state_in_rank_order_gloo(pipelined):
     parts = [(shard.FrameRange(f, c, r), np.array(s, np.uint8), np.ones(c, np.uint32), np.array(t, np.uint8)) for r, (f, c), s, t in res]
     stream, sizes, fts = shard.gather_streams(parts[::-1])
     assert stream.tolist() == [0] * 20 + [20] * 20 and sizes.size == 40
+
+
+def test_cpp_range_planner_equals_the_python_planner():
+    """csrc/multi.cu plans the frame ranges of the one-process multi-GPU entry, screenpressor_b200/shard.py those of the
+    one-process-per-GPU driver (bench.py --gpus N): both must cut a clip the same way (scpr_plan_ranges needs no device)."""
+    import ctypes as C
+    import os
+    import subprocess
+
+    import numpy as np
+
+    from screenpressor_b200 import shard
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-j8", "-C", os.path.join(root, "screenpressor_b200", "csrc")], check=True)
+    lib = C.CDLL(os.path.join(root, "screenpressor_b200", "libscpr_b200.so"))
+    lib.scpr_plan_ranges.restype = C.c_int
+    lib.scpr_plan_ranges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n = int(rng.integers(1, 400))
+        keys = (rng.random(n) < rng.choice([0.01, 0.05, 0.3])).astype(np.uint8)
+        keys[0] = 1
+        world = int(rng.integers(1, 10))
+        want = [(r.first, r.count) for r in shard.assign_ranges(keys, world)]
+        first, count = np.zeros(world, np.int32), np.zeros(world, np.int32)
+        k = lib.scpr_plan_ranges(keys.ctypes.data, n, world, first.ctypes.data, count.ctypes.data)
+        got = [(int(first[i]), int(count[i])) for i in range(k)]
+        assert got == want, (trial, n, world, np.flatnonzero(keys).tolist(), got, want)
+        assert sum(c for _, c in got) == n and all(keys[f] for f, _ in got)
